@@ -1,0 +1,440 @@
+"""ctypes binding of libcdm_b200.so (the C ABI in include/cdm_b200.h) plus thin
+host-side classes that mirror the reference's MFEM surface for this path:
+
+    Mesh / H1Space              Mesh, H1_FECollection + ParFiniteElementSpace
+                                (linear_convection_diffusion_2D.cpp:290-312)
+    ConvectionDiffusionOperator ParBilinearForm + Diffusion/Convection/Mass integrators,
+                                Operator::Mult, FormLinearSystem  (:335-351)
+    GMRESSolver / CGSolver      PetscLinearSolver (:368-374), mfem::CGSolver
+                                (mesh_recession_handler.cpp:270-276)
+
+PyTorch is used only as the owner of device memory / the CUDA stream; there is no
+CPU fallback: every compute call raises if the CUDA library or a GPU is missing.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcdm_b200.so")
+
+OK, EINVAL, ENOGPU, ECUDA, ENOMEM, ENCCL, EUNSUP = 0, -1, -2, -3, -4, -5, -6
+COEFF_NONE, COEFF_CONST, COEFF_QPT = 0, 1, 2
+GMRES_PETSC, GMRES_MFEM = 0, 1
+
+
+class CdmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cdm error {code}: {msg}")
+        self.code = code
+
+
+class Coeff(C.Structure):
+    _fields_ = [("kind", C.c_int), ("ncomp", C.c_int), ("data", C.c_void_p)]
+
+
+class KrylovOpts(C.Structure):
+    _fields_ = [("variant", C.c_int), ("restart", C.c_int), ("max_it", C.c_int),
+                ("rtol", C.c_double), ("atol", C.c_double), ("zero_guess", C.c_int),
+                ("jacobi", C.c_int)]
+
+
+class KrylovResult(C.Structure):
+    _fields_ = [("iters", C.c_int), ("converged", C.c_int), ("final_norm", C.c_double),
+                ("hist_len", C.c_int), ("seconds", C.c_double)]
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc")
+    if force:
+        subprocess.run(["make", "-C", src, "clean"], check=True, capture_output=not verbose)
+    subprocess.run(["make", "-C", src, "-j8"], check=True, capture_output=not verbose)
+    return LIB_PATH
+
+
+_lib = None
+
+# every symbol include/cdm_b200.h declares, with its signature
+_vp, _i64, _ci, _cd = C.c_void_p, C.c_int64, C.c_int, C.c_double
+_pp = C.POINTER(C.c_void_p)
+SIGNATURES = {
+    "cdm_init": (_ci, [_ci, _vp, _pp]),
+    "cdm_init_host": (_ci, [_pp]),
+    "cdm_finalize": (_ci, [_vp]),
+    "cdm_last_error": (C.c_char_p, [_vp]),
+    "cdm_sync": (_ci, [_vp]),
+    "cdm_stream": (_vp, [_vp]),
+    "cdm_version": (C.c_char_p, []),
+    "cdm_comm_unique_id": (_ci, [_vp]),
+    "cdm_comm_init": (_ci, [_vp, _ci, _ci, _vp]),
+    "cdm_comm_rank": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_ci)]),
+    "cdm_mesh_cartesian": (_ci, [_vp, _ci, C.POINTER(_i64), C.POINTER(_cd), _cd, _pp]),
+    "cdm_mesh_from_arrays": (_ci, [_vp, _ci, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _pp]),
+    "cdm_mesh_sizes": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "cdm_mesh_get": (_ci, [_vp, _vp, _vp, _vp, _vp]),
+    "cdm_mesh_destroy": (_ci, [_vp]),
+    "cdm_mesh_partition_box": (_ci, [_vp, _vp, C.POINTER(_ci), _ci, _pp]),
+    "cdm_space_create_h1": (_ci, [_vp, _vp, _ci, _pp]),
+    "cdm_space_create_from_table": (_ci, [_vp, _vp, _ci, _i64, _vp, _pp]),
+    "cdm_space_sizes": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_ci), C.POINTER(_i64), C.POINTER(_i64),
+                              C.POINTER(_ci), C.POINTER(_ci), C.POINTER(_i64)]),
+    "cdm_space_get_maps": (_ci, [_vp, _vp, _vp, _vp]),
+    "cdm_space_essential_dofs": (_ci, [_vp, _vp, _ci, _vp, C.POINTER(_i64)]),
+    "cdm_space_get_basis": (_ci, [_vp, _vp, _vp, _vp, _vp]),
+    "cdm_space_dof_coords": (_ci, [_vp, _vp]),
+    "cdm_space_qpt_coords": (_ci, [_vp, _vp]),
+    "cdm_space_destroy": (_ci, [_vp]),
+    "cdm_operator_create": (_ci, [_vp, C.POINTER(Coeff), C.POINTER(Coeff), _cd, C.POINTER(Coeff), _vp, _i64, _pp]),
+    "cdm_operator_update": (_ci, [_vp, C.POINTER(Coeff), C.POINTER(Coeff), _cd, C.POINTER(Coeff)]),
+    "cdm_operator_destroy": (_ci, [_vp]),
+    "cdm_operator_size": (_i64, [_vp]),
+    "cdm_operator_apply": (_ci, [_vp, _vp, _vp]),
+    "cdm_operator_apply_unconstrained": (_ci, [_vp, _vp, _vp]),
+    "cdm_operator_mult_host": (_ci, [_vp, _vp, _vp, _ci]),
+    "cdm_operator_diag": (_ci, [_vp, _vp]),
+    "cdm_eliminate_rhs": (_ci, [_vp, _vp, _vp]),
+    "cdm_operator_get_qdata": (_ci, [_vp, _vp, _vp, _vp]),
+    "cdm_operator_set_option": (_ci, [_vp, C.c_char_p, _ci]),
+    "cdm_launch_count": (_i64, [_vp]),
+    "cdm_vec_alloc": (_ci, [_vp, _i64, _pp]),
+    "cdm_vec_free": (_ci, [_vp, _vp]),
+    "cdm_vec_set": (_ci, [_vp, _i64, _cd, _vp]),
+    "cdm_vec_upload": (_ci, [_vp, _i64, _vp, _vp]),
+    "cdm_vec_download": (_ci, [_vp, _i64, _vp, _vp]),
+    "cdm_axpy": (_ci, [_vp, _i64, _cd, _vp, _vp]),
+    "cdm_add": (_ci, [_vp, _i64, _vp, _cd, _vp, _vp]),
+    "cdm_pointwise_mult": (_ci, [_vp, _i64, _vp, _vp, _vp]),
+    "cdm_dot": (_ci, [_vp, _i64, _vp, _vp, C.POINTER(_cd)]),
+    "cdm_mdot": (_ci, [_vp, _i64, _ci, _vp, _vp, _i64, _vp]),
+    "cdm_maxpy": (_ci, [_vp, _i64, _ci, _vp, _vp, _i64, _vp]),
+    "cdm_norm2": (_ci, [_vp, _i64, _vp, C.POINTER(_cd)]),
+    "cdm_gmres": (_ci, [_vp, _vp, _vp, C.POINTER(KrylovOpts), C.POINTER(KrylovResult), _vp]),
+    "cdm_cg": (_ci, [_vp, _vp, _vp, C.POINTER(KrylovOpts), C.POINTER(KrylovResult), _vp]),
+}
+
+
+def lib():
+    """Load the CUDA extension; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CdmError(ENOGPU, f"{LIB_PATH} is missing: run __graft_entry__.build() "
+                               "(make -C continuum-mechanics-mfem_b200/csrc); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """host numpy array / torch tensor / int -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class Context:
+    """Device("cuda:i") analogue; host_only=True allows mesh/space construction without a GPU."""
+
+    def __init__(self, device=0, stream=None, host_only=False):
+        self.h = C.c_void_p()
+        self.host_only = host_only
+        L = lib()
+        rc = L.cdm_init_host(C.byref(self.h)) if host_only else L.cdm_init(device, stream, C.byref(self.h))
+        if rc != OK:
+            raise CdmError(rc, "cdm_init failed (no usable CUDA device; there is no CPU fallback)")
+        self.device = device
+
+    def check(self, rc):
+        if rc != OK:
+            raise CdmError(rc, lib().cdm_last_error(self.h).decode())
+
+    def sync(self):
+        self.check(lib().cdm_sync(self.h))
+
+    @property
+    def stream(self):
+        return lib().cdm_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(lib().cdm_launch_count(self.h))
+
+    def comm_init(self, rank, nranks, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+        self.check(lib().cdm_comm_init(self.h, rank, nranks, buf))
+
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        rc = lib().cdm_comm_unique_id(buf)
+        if rc != OK:
+            raise CdmError(rc, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def close(self):
+        if self.h:
+            lib().cdm_finalize(self.h)
+            self.h = C.c_void_p()
+
+    # ---- vector kernels (device pointers: torch tensors)
+    def dot(self, x, y):
+        r = C.c_double()
+        self.check(lib().cdm_dot(self.h, x.numel(), _ptr(x), _ptr(y), C.byref(r)))
+        return r.value
+
+    def norm2(self, x):
+        r = C.c_double()
+        self.check(lib().cdm_norm2(self.h, x.numel(), _ptr(x), C.byref(r)))
+        return r.value
+
+    def axpy(self, a, x, y):
+        self.check(lib().cdm_axpy(self.h, x.numel(), a, _ptr(x), _ptr(y)))
+
+    def add(self, x, a, y, z):
+        self.check(lib().cdm_add(self.h, x.numel(), _ptr(x), a, _ptr(y), _ptr(z)))
+
+    def mdot(self, w, V, k):
+        out = np.zeros(k)
+        self.check(lib().cdm_mdot(self.h, w.numel(), k, _ptr(w), _ptr(V), V.stride(0), _ptr(out)))
+        return out
+
+    def maxpy(self, h, V, w):
+        h = np.ascontiguousarray(h, np.float64)
+        self.check(lib().cdm_maxpy(self.h, w.numel(), len(h), _ptr(h), _ptr(V), V.stride(0), _ptr(w)))
+
+
+class Mesh:
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+        dim, nv, ne, nbe = C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+        lib().cdm_mesh_sizes(self.h, C.byref(dim), C.byref(nv), C.byref(ne), C.byref(nbe))
+        self.dim, self.nv, self.ne, self.nbe = dim.value, nv.value, ne.value, nbe.value
+
+    @classmethod
+    def cartesian(cls, ctx, dim, n, size=None, perturb=0.0):
+        n = list(n) if not np.isscalar(n) else [n] * dim
+        nn = (C.c_int64 * 3)(*(n + [0] * (3 - len(n))))
+        ss = (C.c_double * 3)(*((list(size) + [1.0] * 3)[:3] if size is not None else [1.0] * 3))
+        h = C.c_void_p()
+        ctx.check(lib().cdm_mesh_cartesian(ctx.h, dim, nn, ss, float(perturb), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_arrays(cls, ctx, vx, ev, bv, battr):
+        vx = np.ascontiguousarray(vx, np.float64)
+        ev = np.ascontiguousarray(ev, np.int32)
+        bv = np.ascontiguousarray(bv, np.int32)
+        battr = np.ascontiguousarray(battr, np.int32)
+        h = C.c_void_p()
+        ctx.check(lib().cdm_mesh_from_arrays(ctx.h, vx.shape[1], vx.shape[0], _ptr(vx), ev.shape[0], _ptr(ev),
+                                             bv.shape[0], _ptr(bv), _ptr(battr), C.byref(h)))
+        return cls(ctx, h)
+
+    def partition_box(self, parts, rank):
+        pp = (C.c_int * 3)(*(list(parts) + [1] * (3 - len(parts))))
+        h = C.c_void_p()
+        self.ctx.check(lib().cdm_mesh_partition_box(self.ctx.h, self.h, pp, rank, C.byref(h)))
+        return Mesh(self.ctx, h)
+
+    def arrays(self):
+        vx = np.zeros((self.nv, self.dim))
+        ev = np.zeros((self.ne, 2 ** self.dim), np.int32)
+        bv = np.zeros((self.nbe, 2 ** (self.dim - 1)), np.int32)
+        battr = np.zeros(self.nbe, np.int32)
+        lib().cdm_mesh_get(self.h, _ptr(vx), _ptr(ev), _ptr(bv), _ptr(battr))
+        return vx, ev, bv, battr
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().cdm_mesh_destroy(self.h)
+            self.h = None
+
+
+class H1Space:
+    """H1_FECollection(order, dim) + FiniteElementSpace on `mesh`."""
+
+    def __init__(self, mesh, order, elem_dof=None, ndof=None):
+        self.mesh, self.ctx = mesh, mesh.ctx
+        self.h = C.c_void_p()
+        if elem_dof is None:
+            self.ctx.check(lib().cdm_space_create_h1(self.ctx.h, mesh.h, order, C.byref(self.h)))
+        else:
+            elem_dof = np.ascontiguousarray(elem_dof, np.int32)
+            self.ctx.check(lib().cdm_space_create_from_table(self.ctx.h, mesh.h, order, int(ndof), _ptr(elem_dof),
+                                                             C.byref(self.h)))
+        dim, p, d1d, q1d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        ne, ndof_, ntrue = C.c_int64(), C.c_int64(), C.c_int64()
+        lib().cdm_space_sizes(self.h, C.byref(dim), C.byref(p), C.byref(ne), C.byref(ndof_), C.byref(d1d),
+                              C.byref(q1d), C.byref(ntrue))
+        self.dim, self.order, self.ne, self.ndof = dim.value, p.value, ne.value, ndof_.value
+        self.d1d, self.q1d, self.ntrue = d1d.value, q1d.value, ntrue.value
+        self.nd, self.nq = self.d1d ** self.dim, self.q1d ** self.dim
+
+    def maps(self):
+        """ElementRestriction gather_map / offsets / indices (int32)."""
+        g = np.zeros((self.ne, self.nd), np.int32)
+        o = np.zeros(self.ndof + 1, np.int32)
+        i = np.zeros(self.ne * self.nd, np.int32)
+        lib().cdm_space_get_maps(self.h, _ptr(g), _ptr(o), _ptr(i))
+        return g, o, i
+
+    def essential_dofs(self, marker):
+        marker = np.ascontiguousarray(marker, np.int32)
+        cnt = C.c_int64()
+        self.ctx.check(lib().cdm_space_essential_dofs(self.h, _ptr(marker), len(marker), None, C.byref(cnt)))
+        out = np.zeros(cnt.value, np.int32)
+        self.ctx.check(lib().cdm_space_essential_dofs(self.h, _ptr(marker), len(marker), _ptr(out), C.byref(cnt)))
+        return out
+
+    def basis(self):
+        B, G = np.zeros((self.q1d, self.d1d)), np.zeros((self.q1d, self.d1d))
+        qw, nodes = np.zeros(self.q1d), np.zeros(self.d1d)
+        lib().cdm_space_get_basis(self.h, _ptr(B), _ptr(G), _ptr(qw), _ptr(nodes))
+        return B, G, qw, nodes
+
+    def dof_coords(self):
+        out = np.zeros((self.ndof, self.dim))
+        lib().cdm_space_dof_coords(self.h, _ptr(out))
+        return out
+
+    def qpt_coords(self):
+        out = np.zeros((self.ne, self.nq, self.dim))
+        lib().cdm_space_qpt_coords(self.h, _ptr(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().cdm_space_destroy(self.h)
+            self.h = None
+
+
+def _coeff(c, dim, which, keep):
+    """None | scalar | vector | per-qpt array (ne, nq[, ncomp]) -> Coeff"""
+    if c is None:
+        return Coeff(COEFF_NONE, 0, None)
+    a = np.ascontiguousarray(np.asarray(c, dtype=np.float64))
+    keep.append(a)
+    if a.ndim <= 1:
+        return Coeff(COEFF_CONST, int(a.size), a.ctypes.data_as(C.c_void_p))
+    ncomp = int(a.shape[2]) if a.ndim == 3 else 1
+    return Coeff(COEFF_QPT, ncomp, a.ctypes.data_as(C.c_void_p))
+
+
+class ConvectionDiffusionOperator:
+    """a(u,v) = (kappa grad u, grad v) + alpha (vel . grad u, v) + (mass u, v), partially assembled.
+
+    Mult / MultUnconstrained follow mfem::Operator::Mult(x, y) on device vectors
+    (torch.float64 CUDA tensors); mult_host takes numpy arrays."""
+
+    def __init__(self, space, kappa=None, vel=None, alpha=1.0, mass=None, ess_dofs=None):
+        self.space, self.ctx = space, space.ctx
+        keep = []
+        if vel is not None and np.ndim(vel) == 1:
+            vel = np.asarray(vel, dtype=np.float64)[:space.dim]
+        ck, cv, cm = (_coeff(kappa, space.dim, 0, keep), _coeff(vel, space.dim, 1, keep),
+                      _coeff(mass, space.dim, 2, keep))
+        ess = None if ess_dofs is None else np.ascontiguousarray(ess_dofs, np.int32)
+        self.h = C.c_void_p()
+        self.ctx.check(lib().cdm_operator_create(space.h, C.byref(ck), C.byref(cv), float(alpha), C.byref(cm),
+                                                 _ptr(ess), 0 if ess is None else len(ess), C.byref(self.h)))
+        self.height = self.width = int(lib().cdm_operator_size(self.h))
+        self.flags = (kappa is not None, vel is not None, mass is not None)
+
+    def update(self, kappa=None, vel=None, alpha=1.0, mass=None):
+        keep = []
+        if vel is not None and np.ndim(vel) == 1:
+            vel = np.asarray(vel, dtype=np.float64)[:self.space.dim]
+        ck, cv, cm = (_coeff(kappa, self.space.dim, 0, keep), _coeff(vel, self.space.dim, 1, keep),
+                      _coeff(mass, self.space.dim, 2, keep))
+        self.ctx.check(lib().cdm_operator_update(self.h, C.byref(ck), C.byref(cv), float(alpha), C.byref(cm)))
+
+    def set_option(self, name, value):
+        self.ctx.check(lib().cdm_operator_set_option(self.h, name.encode(), int(value)))
+
+    def Mult(self, x, y):
+        self.ctx.check(lib().cdm_operator_apply(self.h, _ptr(x), _ptr(y)))
+
+    def MultUnconstrained(self, x, y):
+        self.ctx.check(lib().cdm_operator_apply_unconstrained(self.h, _ptr(x), _ptr(y)))
+
+    def mult_host(self, x, y=None, constrained=True):
+        x = np.ascontiguousarray(x, np.float64)
+        if y is None:
+            y = np.zeros(self.height)
+        self.ctx.check(lib().cdm_operator_mult_host(self.h, _ptr(x), _ptr(y), 1 if constrained else 0))
+        return y
+
+    def AssembleDiagonal(self, d):
+        self.ctx.check(lib().cdm_operator_diag(self.h, _ptr(d)))
+
+    def EliminateRHS(self, x, b):
+        self.ctx.check(lib().cdm_eliminate_rhs(self.h, _ptr(x), _ptr(b)))
+
+    def qdata(self):
+        sp = self.space
+        nsym = sp.dim * (sp.dim + 1) // 2
+        Dd = np.zeros((sp.ne, nsym, sp.nq)) if self.flags[0] else None
+        Dc = np.zeros((sp.ne, sp.dim, sp.nq)) if self.flags[1] else None
+        Dm = np.zeros((sp.ne, sp.nq)) if self.flags[2] else None
+        self.ctx.check(lib().cdm_operator_get_qdata(self.h, _ptr(Dd), _ptr(Dc), _ptr(Dm)))
+        return Dd, Dc, Dm
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().cdm_operator_destroy(self.h)
+            self.h = None
+
+
+class _IterativeSolver:
+    """mfem::IterativeSolver surface: SetRelTol/SetAbsTol/SetMaxIter/SetOperator/Mult/Get*."""
+    _fn = None
+
+    def __init__(self, variant=GMRES_PETSC, restart=0, max_it=500, rtol=1e-10, atol=1e-12, jacobi=True):
+        self.opts = KrylovOpts(variant, restart, max_it, rtol, atol, 1, 1 if jacobi else 0)
+        self.res = KrylovResult()
+        self.op = None
+        self.iterative_mode = False
+        self.history = np.zeros(0)
+
+    def SetRelTol(self, v): self.opts.rtol = v
+    def SetAbsTol(self, v): self.opts.atol = v
+    def SetMaxIter(self, v): self.opts.max_it = int(v)
+    def SetKDim(self, v): self.opts.restart = int(v)
+    def SetPrintLevel(self, v): pass
+    def SetOperator(self, op): self.op = op
+    def GetNumIterations(self): return self.res.iters
+    def GetConverged(self): return bool(self.res.converged)
+    def GetFinalNorm(self): return self.res.final_norm
+
+    def Mult(self, b, x):
+        if self.op is None:
+            raise CdmError(EINVAL, "SetOperator has not been called")
+        self.opts.zero_guess = 0 if self.iterative_mode else 1
+        hist = np.zeros(self.opts.max_it + 2)
+        fn = getattr(lib(), self._fn)
+        self.op.ctx.check(fn(self.op.h, _ptr(b), _ptr(x), C.byref(self.opts), C.byref(self.res), _ptr(hist)))
+        self.history = hist[:self.res.hist_len].copy()
+
+
+class GMRESSolver(_IterativeSolver):
+    _fn = "cdm_gmres"
+
+
+class CGSolver(_IterativeSolver):
+    _fn = "cdm_cg"
+
+    def __init__(self, max_it=500, rtol=1e-12, atol=0.0, jacobi=False):
+        super().__init__(GMRES_MFEM, 0, max_it, rtol, atol, jacobi)

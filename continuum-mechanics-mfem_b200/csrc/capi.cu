@@ -1,0 +1,635 @@
+// capi.cu -- C ABI entry points: context, space, operator, vectors.
+// Every exported symbol is declared in include/cdm_b200.h together with the
+// reference interface it stands behind.
+#include "cdm_internal.hpp"
+#include "kernels_common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#define CDM_VERSION_STR "cdm_b200 0.1 (sm_100a)"
+
+namespace
+{
+template <typename T>
+int upload(cdm_ctx *ctx, const std::vector<T> &h, T **d)
+{
+   if (h.empty()) { *d = nullptr; return CDM_OK; }
+   CDM_CUDA(ctx, cudaMalloc((void **)d, h.size() * sizeof(T)));
+   CDM_CUDA(ctx, cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+   return CDM_OK;
+}
+inline int ipow(int b, int e) { int r = 1; while (e-- > 0) { r *= b; } return r; }
+}
+
+extern "C" {
+
+const char *cdm_version(void) { return CDM_VERSION_STR; }
+
+int cdm_init(int device, void *stream, cdm_ctx **out)
+{
+   if (!out) { return CDM_EINVAL; }
+   *out = nullptr;
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+   {
+      cudaGetLastError();
+      return CDM_ENOGPU;
+   }
+   cdm_ctx *c = new (std::nothrow) cdm_ctx;
+   if (!c) { return CDM_ENOMEM; }
+   c->device = device;
+   if (cudaSetDevice(device) != cudaSuccess) { delete c; return CDM_ENOGPU; }
+   if (stream) { c->stream = (cudaStream_t)stream; }
+   else
+   {
+      if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CDM_ENOGPU; }
+      c->own_stream = true;
+   }
+   cudaDeviceProp prop;
+   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) { c->sm_count = prop.multiProcessorCount; }
+   const size_t nred = (size_t)CDM_RED_MAXK * CDM_RED_BLOCKS + 4 * CDM_RED_MAXK;
+   if (cudaMalloc(&c->red_dev, nred * sizeof(double)) != cudaSuccess ||
+       cudaMallocHost(&c->red_host, 4 * CDM_RED_MAXK * sizeof(double)) != cudaSuccess ||
+       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess)
+   {
+      cdm_finalize(c);
+      return CDM_ENOGPU;
+   }
+   *out = c;
+   return CDM_OK;
+}
+
+int cdm_init_host(cdm_ctx **out)
+{
+   if (!out) { return CDM_EINVAL; }
+   cdm_ctx *c = new (std::nothrow) cdm_ctx;
+   if (!c) { return CDM_ENOMEM; }
+   c->device = -1;
+   *out = c;
+   return CDM_OK;
+}
+
+int cdm_finalize(cdm_ctx *c)
+{
+   if (!c) { return CDM_OK; }
+   if (c->device >= 0)
+   {
+      cudaSetDevice(c->device);
+      if (c->stream) { cudaStreamSynchronize(c->stream); }
+      if (c->red_dev) { cudaFree(c->red_dev); }
+      if (c->red_host) { cudaFreeHost(c->red_host); }
+      if (c->ev0) { cudaEventDestroy(c->ev0); }
+      if (c->ev1) { cudaEventDestroy(c->ev1); }
+      if (c->own_stream && c->stream) { cudaStreamDestroy(c->stream); }
+   }
+   delete c;
+   return CDM_OK;
+}
+
+const char *cdm_last_error(const cdm_ctx *c) { return c ? c->err.c_str() : "null context"; }
+void *cdm_stream(cdm_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int64_t cdm_launch_count(const cdm_ctx *c) { return c ? c->launches : 0; }
+
+int cdm_sync(cdm_ctx *c)
+{
+   CDM_REQUIRE_GPU(c);
+   CDM_CUDA(c, cudaStreamSynchronize(c->stream));
+   return CDM_OK;
+}
+
+// ------------------------------------------------------------------ space
+
+static int space_finish(cdm_ctx *ctx, const cdm_mesh *mesh, cdm_space *sp)
+{
+   // per-element vertex coordinates (order-1 mesh nodes)
+   const int nvpe = (sp->dim == 2) ? 4 : 8;
+   sp->elem_x.resize((size_t)sp->ne * nvpe * sp->dim);
+   for (int64_t e = 0; e < sp->ne; e++)
+      for (int k = 0; k < nvpe; k++)
+         for (int c = 0; c < sp->dim; c++)
+            sp->elem_x[((size_t)e * nvpe + k) * sp->dim + c] = mesh->vx[(size_t)mesh->ev[(size_t)e * nvpe + k] * sp->dim + c];
+   cdm_host_restriction(sp->ne, sp->nd, sp->ndof, sp->gather, sp->offsets, sp->indices);
+   if (ctx->device >= 0)
+   {
+      int rc;
+      if ((rc = upload(ctx, sp->gather, &sp->gather_dev))) { return rc; }
+      if ((rc = upload(ctx, sp->offsets, &sp->offsets_dev))) { return rc; }
+      if ((rc = upload(ctx, sp->indices, &sp->indices_dev))) { return rc; }
+      if ((rc = upload(ctx, sp->elem_x, &sp->elem_x_dev))) { return rc; }
+      for (auto &pr : sp->peers)
+      {
+         if ((rc = upload(ctx, pr.own_idx, &pr.own_idx_dev))) { return rc; }
+         if ((rc = upload(ctx, pr.ghost_idx, &pr.ghost_idx_dev))) { return rc; }
+         const size_t nb = std::max(pr.own_idx.size(), pr.ghost_idx.size()) * sizeof(double);
+         CDM_CUDA(ctx, cudaMalloc(&pr.send_dev, nb));
+         CDM_CUDA(ctx, cudaMalloc(&pr.recv_dev, nb));
+      }
+      CDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+   }
+   return CDM_OK;
+}
+
+static cdm_space *space_new(cdm_ctx *ctx, const cdm_mesh *mesh, int order)
+{
+   cdm_space *sp = new (std::nothrow) cdm_space;
+   if (!sp) { return nullptr; }
+   sp->ctx = ctx; sp->dim = mesh->dim; sp->p = order; sp->d1d = order + 1;
+   sp->q1d = cdm_host_q1d(mesh->dim, order);
+   sp->nd = ipow(sp->d1d, sp->dim); sp->nq = ipow(sp->q1d, sp->dim);
+   sp->ne = mesh->ne; sp->nv = mesh->nv; sp->nbe = mesh->nbe;
+   sp->B.resize(sp->q1d * sp->d1d); sp->G.resize(sp->q1d * sp->d1d);
+   sp->qw.resize(sp->q1d); sp->qx.resize(sp->q1d); sp->nodes.resize(sp->d1d);
+   cdm_host_basis(order, sp->q1d, sp->B.data(), sp->G.data(), sp->qw.data(), sp->nodes.data(), sp->qx.data());
+   sp->bdr_attr = mesh->battr;
+   return sp;
+}
+
+// shared-dof plan of a box-partitioned Cartesian space + owned-first renumbering
+static void build_partition(const cdm_mesh *m, cdm_space *sp)
+{
+   const int dim = sp->dim, p = sp->p, d1d = sp->d1d;
+   const int64_t N[3] = {p * m->gn[0] + 1, p * m->gn[1] + 1, dim == 3 ? p * m->gn[2] + 1 : 1};
+   // element index -> rank coordinate along each axis
+   auto axis_rank = [&](int d, int64_t el) -> int
+   {
+      const int64_t q = m->gn[d] / m->parts[d], r = m->gn[d] % m->parts[d];
+      // boxes 0..r-1 have q+1 elements, the rest q
+      if (el < r * (q + 1)) { return (int)(el / (q + 1)); }
+      return (int)(r + (el - r * (q + 1)) / q);
+   };
+   const int64_t ln[3] = {m->n[0], m->n[1], dim == 3 ? m->n[2] : 1};
+   std::vector<int64_t> key(sp->ndof, -1);
+   for (int64_t e = 0; e < sp->ne; e++)
+   {
+      const int64_t ei = e % ln[0], ej = (e / ln[0]) % ln[1], ek = e / (ln[0] * ln[1]);
+      for (int l = 0; l < sp->nd; l++)
+      {
+         const int lx = l % d1d, ly = (l / d1d) % d1d, lz = (dim == 3) ? l / (d1d * d1d) : 0;
+         const int64_t I = p * (m->lo[0] + ei) + lx, J = p * (m->lo[1] + ej) + ly,
+                       K = (dim == 3) ? p * (m->lo[2] + ek) + lz : 0;
+         key[sp->gather[(size_t)e * sp->nd + l]] = I + N[0] * (J + N[1] * K);
+      }
+   }
+   const int me = m->rank;
+   std::vector<int> owner(sp->ndof, me);
+   struct Share { int64_t key; int32_t dof; int peer; bool mine; };
+   std::vector<Share> shares;
+   for (int64_t g = 0; g < sp->ndof; g++)
+   {
+      const int64_t k = key[g];
+      const int64_t c[3] = {k % N[0], (k / N[0]) % N[1], k / (N[0] * N[1])};
+      int rs[3][2], nr[3];
+      for (int d = 0; d < 3; d++)
+      {
+         nr[d] = 1; rs[d][0] = 0;
+         if (d >= dim) { continue; }
+         const int64_t el_hi = std::min<int64_t>(c[d] / p, m->gn[d] - 1);
+         rs[d][0] = axis_rank(d, el_hi);
+         if (c[d] % p == 0 && c[d] > 0 && c[d] < p * m->gn[d])
+         {
+            const int r2 = axis_rank(d, c[d] / p - 1);
+            if (r2 != rs[d][0]) { rs[d][1] = r2; nr[d] = 2; }
+         }
+      }
+      int ranks[8], cnt = 0, own = 1 << 30;
+      for (int a = 0; a < nr[0]; a++)
+         for (int b = 0; b < nr[1]; b++)
+            for (int cc = 0; cc < nr[2]; cc++)
+            {
+               const int r = rs[0][a] + m->parts[0] * (rs[1][b] + m->parts[1] * rs[2][cc]);
+               ranks[cnt++] = r; own = std::min(own, r);
+            }
+      owner[g] = own;
+      if (cnt == 1) { continue; }
+      if (own == me) { for (int i = 0; i < cnt; i++) if (ranks[i] != me) { shares.push_back({k, (int32_t)g, ranks[i], true}); } }
+      else { shares.push_back({k, (int32_t)g, own, false}); }
+   }
+   // owned-first renumbering
+   std::vector<int32_t> newid(sp->ndof);
+   int64_t nown = 0;
+   for (int64_t g = 0; g < sp->ndof; g++) if (owner[g] == me) { newid[g] = (int32_t)nown++; }
+   int64_t ng = nown;
+   for (int64_t g = 0; g < sp->ndof; g++) if (owner[g] != me) { newid[g] = (int32_t)ng++; }
+   sp->ntrue = nown;
+   for (auto &g : sp->gather) { g = newid[g]; }
+   for (auto &g : sp->bdr_dofs_flat) { g = newid[g]; }
+   sp->dof_global.assign(sp->ndof, 0);
+   for (int64_t g = 0; g < sp->ndof; g++) { sp->dof_global[newid[g]] = key[g]; }
+   std::sort(shares.begin(), shares.end(), [](const Share &a, const Share &b)
+   { return a.peer != b.peer ? a.peer < b.peer : a.key < b.key; });
+   for (const Share &s : shares)
+   {
+      if (sp->peers.empty() || sp->peers.back().rank != s.peer) { sp->peers.emplace_back(); sp->peers.back().rank = s.peer; }
+      (s.mine ? sp->peers.back().own_idx : sp->peers.back().ghost_idx).push_back(newid[s.dof]);
+   }
+}
+
+int cdm_space_create_h1(cdm_ctx *ctx, const cdm_mesh *mesh, int order, cdm_space **space)
+{
+   if (!ctx || !mesh || !space) { return cdm_fail(ctx, CDM_EINVAL, "cdm_space_create_h1: bad arguments"); }
+   if (order < 1 || order > 6) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_space_create_h1: order must be 1..6"); }
+   cdm_space *sp = space_new(ctx, mesh, order);
+   if (!sp) { return cdm_fail(ctx, CDM_ENOMEM, "out of memory"); }
+   sp->ndof = cdm_host_h1_numbering(*mesh, order, sp->gather, sp->bdr_dofs_off, sp->bdr_dofs_flat);
+   if (sp->ndof < 0) { delete sp; return cdm_fail(ctx, CDM_EINVAL, "cdm_space_create_h1: boundary element not found in mesh"); }
+   if (sp->ndof > 2147483000LL) { delete sp; return cdm_fail(ctx, CDM_EUNSUP, "cdm_space_create_h1: more than 2^31 dofs on one rank"); }
+   sp->ntrue = sp->ndof;
+   if (mesh->is_part && mesh->parts[0] * mesh->parts[1] * mesh->parts[2] > 1) { build_partition(mesh, sp); }
+   int rc = space_finish(ctx, mesh, sp);
+   if (rc) { cdm_space_destroy(sp); return rc; }
+   *space = sp;
+   return CDM_OK;
+}
+
+int cdm_space_create_from_table(cdm_ctx *ctx, const cdm_mesh *mesh, int order, int64_t ndof,
+                                const int32_t *elem_dof, cdm_space **space)
+{
+   if (!ctx || !mesh || !space || !elem_dof || ndof < 1) { return cdm_fail(ctx, CDM_EINVAL, "cdm_space_create_from_table: bad arguments"); }
+   if (order < 1 || order > 6) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_space_create_from_table: order must be 1..6"); }
+   cdm_space *sp = space_new(ctx, mesh, order);
+   if (!sp) { return cdm_fail(ctx, CDM_ENOMEM, "out of memory"); }
+   sp->ndof = sp->ntrue = ndof;
+   sp->gather.assign(elem_dof, elem_dof + sp->ne * sp->nd);
+   for (int32_t g : sp->gather)
+      if (g < 0 || g >= ndof) { delete sp; return cdm_fail(ctx, CDM_EINVAL, "cdm_space_create_from_table: dof id out of range"); }
+   // boundary dofs: use our own numbering only to locate which lexicographic
+   // nodes lie on each boundary element, then translate through the table
+   {
+      std::vector<int32_t> own_gather, off, flat;
+      const int64_t nd_own = cdm_host_h1_numbering(*mesh, order, own_gather, off, flat);
+      if (nd_own < 0) { delete sp; return cdm_fail(ctx, CDM_EINVAL, "cdm_space_create_from_table: boundary element not found in mesh"); }
+      std::vector<int32_t> tr(nd_own, -1);
+      for (size_t i = 0; i < own_gather.size(); i++) { tr[own_gather[i]] = sp->gather[i]; }
+      for (auto &g : flat) { g = tr[g]; }
+      sp->bdr_dofs_off.swap(off); sp->bdr_dofs_flat.swap(flat);
+   }
+   int rc = space_finish(ctx, mesh, sp);
+   if (rc) { cdm_space_destroy(sp); return rc; }
+   *space = sp;
+   return CDM_OK;
+}
+
+int cdm_space_sizes(const cdm_space *sp, int *dim, int *order, int64_t *ne, int64_t *ndof, int *d1d,
+                    int *q1d, int64_t *ntrue)
+{
+   if (!sp) { return CDM_EINVAL; }
+   if (dim) { *dim = sp->dim; }
+   if (order) { *order = sp->p; }
+   if (ne) { *ne = sp->ne; }
+   if (ndof) { *ndof = sp->ndof; }
+   if (d1d) { *d1d = sp->d1d; }
+   if (q1d) { *q1d = sp->q1d; }
+   if (ntrue) { *ntrue = sp->ntrue; }
+   return CDM_OK;
+}
+
+int cdm_space_get_maps(const cdm_space *sp, int32_t *gather_map, int32_t *offsets, int32_t *indices)
+{
+   if (!sp) { return CDM_EINVAL; }
+   if (gather_map) { std::memcpy(gather_map, sp->gather.data(), sp->gather.size() * sizeof(int32_t)); }
+   if (offsets) { std::memcpy(offsets, sp->offsets.data(), sp->offsets.size() * sizeof(int32_t)); }
+   if (indices) { std::memcpy(indices, sp->indices.data(), sp->indices.size() * sizeof(int32_t)); }
+   return CDM_OK;
+}
+
+int cdm_space_essential_dofs(const cdm_space *sp, const int32_t *bdr_marker, int nattr, int32_t *list, int64_t *count)
+{
+   if (!sp || !bdr_marker || !count) { return CDM_EINVAL; }
+   std::vector<uint8_t> mark(sp->ndof, 0);
+   for (int64_t b = 0; b < sp->nbe; b++)
+   {
+      const int a = sp->bdr_attr[b];
+      if (a < 1 || a > nattr || !bdr_marker[a - 1]) { continue; }
+      for (int32_t j = sp->bdr_dofs_off[b]; j < sp->bdr_dofs_off[b + 1]; j++) { mark[sp->bdr_dofs_flat[j]] = 1; }
+   }
+   int64_t n = 0;
+   for (int64_t g = 0; g < sp->ndof; g++) if (mark[g]) { if (list) { list[n] = (int32_t)g; } n++; }
+   *count = n;
+   return CDM_OK;
+}
+
+int cdm_space_get_basis(const cdm_space *sp, double *B, double *G, double *qw, double *nodes)
+{
+   if (!sp) { return CDM_EINVAL; }
+   if (B) { std::memcpy(B, sp->B.data(), sp->B.size() * sizeof(double)); }
+   if (G) { std::memcpy(G, sp->G.data(), sp->G.size() * sizeof(double)); }
+   if (qw) { std::memcpy(qw, sp->qw.data(), sp->qw.size() * sizeof(double)); }
+   if (nodes) { std::memcpy(nodes, sp->nodes.data(), sp->nodes.size() * sizeof(double)); }
+   return CDM_OK;
+}
+
+// trilinear / bilinear map of reference point xi through element e
+static void map_point(const cdm_space *sp, int64_t e, const double *xi, double *X)
+{
+   const int dim = sp->dim, nvpe = (dim == 2) ? 4 : 8;
+   const double x = xi[0], y = xi[1], z = (dim == 3) ? xi[2] : 0.0;
+   double N[8];
+   if (dim == 2) { N[0] = (1 - x) * (1 - y); N[1] = x * (1 - y); N[2] = x * y; N[3] = (1 - x) * y; }
+   else
+   {
+      N[0] = (1 - x) * (1 - y) * (1 - z); N[1] = x * (1 - y) * (1 - z); N[2] = x * y * (1 - z); N[3] = (1 - x) * y * (1 - z);
+      N[4] = (1 - x) * (1 - y) * z; N[5] = x * (1 - y) * z; N[6] = x * y * z; N[7] = (1 - x) * y * z;
+   }
+   for (int c = 0; c < dim; c++)
+   {
+      double s = 0.0;
+      for (int k = 0; k < nvpe; k++) { s += N[k] * sp->elem_x[((size_t)e * nvpe + k) * dim + c]; }
+      X[c] = s;
+   }
+}
+
+int cdm_space_dof_coords(const cdm_space *sp, double *xyz)
+{
+   if (!sp || !xyz) { return CDM_EINVAL; }
+   const int d1d = sp->d1d, dim = sp->dim;
+   for (int64_t e = 0; e < sp->ne; e++)
+      for (int l = 0; l < sp->nd; l++)
+      {
+         const double xi[3] = {sp->nodes[l % d1d], sp->nodes[(l / d1d) % d1d], dim == 3 ? sp->nodes[l / (d1d * d1d)] : 0.0};
+         map_point(sp, e, xi, xyz + (size_t)sp->gather[(size_t)e * sp->nd + l] * dim);
+      }
+   return CDM_OK;
+}
+
+int cdm_space_qpt_coords(const cdm_space *sp, double *xyz)
+{
+   if (!sp || !xyz) { return CDM_EINVAL; }
+   const int q1d = sp->q1d, dim = sp->dim;
+   for (int64_t e = 0; e < sp->ne; e++)
+      for (int q = 0; q < sp->nq; q++)
+      {
+         const double xi[3] = {sp->qx[q % q1d], sp->qx[(q / q1d) % q1d], dim == 3 ? sp->qx[q / (q1d * q1d)] : 0.0};
+         map_point(sp, e, xi, xyz + ((size_t)e * sp->nq + q) * dim);
+      }
+   return CDM_OK;
+}
+
+int cdm_space_destroy(cdm_space *sp)
+{
+   if (!sp) { return CDM_OK; }
+   if (sp->ctx && sp->ctx->device >= 0)
+   {
+      cudaFree(sp->gather_dev); cudaFree(sp->offsets_dev); cudaFree(sp->indices_dev); cudaFree(sp->elem_x_dev);
+      for (auto &pr : sp->peers) { cudaFree(pr.own_idx_dev); cudaFree(pr.ghost_idx_dev); cudaFree(pr.send_dev); cudaFree(pr.recv_dev); }
+   }
+   delete sp;
+   return CDM_OK;
+}
+
+// --------------------------------------------------------------- operator
+
+static int check_coeff(const cdm_coeff *c, int dim, int which)
+{
+   if (!c || c->kind == CDM_COEFF_NONE) { return 0; }
+   if (c->kind != CDM_COEFF_CONST && c->kind != CDM_COEFF_QPT) { return -1; }
+   if (!c->data) { return -1; }
+   if (which == 0 && c->ncomp != 1 && c->ncomp != dim * (dim + 1) / 2) { return -1; }
+   if (which == 1 && c->ncomp != dim) { return -1; }
+   if (which == 2 && c->ncomp != 1) { return -1; }
+   return 1;
+}
+
+int cdm_operator_create(cdm_space *sp, const cdm_coeff *kappa, const cdm_coeff *vel, double conv_alpha,
+                        const cdm_coeff *mass, const int32_t *ess_dofs, int64_t n_ess, cdm_op **out)
+{
+   if (!sp || !out) { return CDM_EINVAL; }
+   cdm_ctx *ctx = sp->ctx;
+   CDM_REQUIRE_GPU(ctx);
+   const int hk = check_coeff(kappa, sp->dim, 0), hv = check_coeff(vel, sp->dim, 1), hm = check_coeff(mass, sp->dim, 2);
+   if (hk < 0 || hv < 0 || hm < 0) { return cdm_fail(ctx, CDM_EINVAL, "cdm_operator_create: malformed coefficient"); }
+   if (!hk && !hv && !hm) { return cdm_fail(ctx, CDM_EINVAL, "cdm_operator_create: no integrator"); }
+   if (n_ess < 0 || (n_ess > 0 && !ess_dofs)) { return cdm_fail(ctx, CDM_EINVAL, "cdm_operator_create: bad essential dof list"); }
+   cdm_op *op = new (std::nothrow) cdm_op;
+   if (!op) { return cdm_fail(ctx, CDM_ENOMEM, "out of memory"); }
+   op->sp = sp;
+   op->has_diff = hk; op->has_conv = hv; op->has_mass = hm;
+   const int nsym = sp->dim * (sp->dim + 1) / 2, q2 = sp->q1d * sp->q1d;
+   op->ncomp = (hk ? nsym : 0) + (hv ? sp->dim : 0) + (hm ? 1 : 0);
+   op->slab = (op->ncomp * q2 + 1) & ~1;
+   op->D_len = sp->ne * (int64_t)op->slab * (sp->dim == 3 ? sp->q1d : 1);
+   int rc = CDM_OK;
+   do
+   {
+      if (cudaMalloc(&op->D_dev, (size_t)op->D_len * sizeof(double)) != cudaSuccess)
+      { cudaGetLastError(); rc = cdm_fail(ctx, CDM_ENOMEM, "cdm_operator_create: cannot allocate quadrature data"); break; }
+      if (cudaMemsetAsync(op->D_dev, 0, (size_t)op->D_len * sizeof(double), ctx->stream) != cudaSuccess) { rc = CDM_ECUDA; break; }
+      if (n_ess > 0)
+      {
+         std::vector<uint8_t> mark(sp->ndof, 0);
+         for (int64_t i = 0; i < n_ess; i++)
+         {
+            if (ess_dofs[i] < 0 || ess_dofs[i] >= sp->ndof) { rc = cdm_fail(ctx, CDM_EINVAL, "cdm_operator_create: essential dof out of range"); break; }
+            mark[ess_dofs[i]] = 1;
+         }
+         if (rc) { break; }
+         std::vector<int32_t> gc(sp->gather);
+         for (auto &g : gc) if (mark[g]) { g = -1 - g; }
+         for (int64_t g = 0; g < sp->ntrue; g++) if (mark[g]) { op->ess_host.push_back((int32_t)g); }
+         op->n_ess = (int64_t)op->ess_host.size();
+         if ((rc = upload(ctx, gc, &op->gather_c_dev))) { break; }
+         if ((rc = upload(ctx, op->ess_host, &op->ess_dev))) { break; }
+         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = CDM_ECUDA; break; }
+      }
+      rc = cdm_k_setup_qdata(op, kappa, vel, conv_alpha, mass);
+   } while (0);
+   if (rc) { cdm_operator_destroy(op); return rc; }
+   op->kernel_variant = (sp->dim == 3 && sp->p == 3) ? 1 : 0;
+   *out = op;
+   return CDM_OK;
+}
+
+int cdm_operator_update(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel, double conv_alpha, const cdm_coeff *mass)
+{
+   if (!op) { return CDM_EINVAL; }
+   cdm_ctx *ctx = op->sp->ctx;
+   const int hk = check_coeff(kappa, op->sp->dim, 0), hv = check_coeff(vel, op->sp->dim, 1), hm = check_coeff(mass, op->sp->dim, 2);
+   if (hk < 0 || hv < 0 || hm < 0 || (hk > 0) != op->has_diff || (hv > 0) != op->has_conv || (hm > 0) != op->has_mass)
+      return cdm_fail(ctx, CDM_EINVAL, "cdm_operator_update: the set of integrators must not change");
+   if (op->dinv_dev) { cudaFree(op->dinv_dev); op->dinv_dev = nullptr; }
+   return cdm_k_setup_qdata(op, kappa, vel, conv_alpha, mass);
+}
+
+int cdm_operator_destroy(cdm_op *op)
+{
+   if (!op) { return CDM_OK; }
+   if (op->sp && op->sp->ctx && op->sp->ctx->stream) { cudaStreamSynchronize(op->sp->ctx->stream); }
+   cudaFree(op->D_dev); cudaFree(op->gather_c_dev); cudaFree(op->ess_dev); cudaFree(op->yE_dev);
+   cudaFree(op->xL_dev); cudaFree(op->yL_dev); cudaFree(op->dinv_dev); cudaFree(op->kry_dev);
+   delete op;
+   return CDM_OK;
+}
+
+int64_t cdm_operator_size(const cdm_op *op) { return op ? op->sp->ntrue : 0; }
+
+int cdm_operator_set_option(cdm_op *op, const char *name, int value)
+{
+   if (!op || !name) { return CDM_EINVAL; }
+   if (!std::strcmp(name, "scatter")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->scatter_mode = value; return CDM_OK; }
+   if (!std::strcmp(name, "kernel")) { op->kernel_variant = value; return CDM_OK; }
+   return cdm_fail(op->sp->ctx, CDM_EINVAL, std::string("unknown option ") + name);
+}
+
+static int ensure_L(cdm_op *op)
+{
+   cdm_ctx *ctx = op->sp->ctx;
+   if (!op->xL_dev) { CDM_CUDA(ctx, cudaMalloc(&op->xL_dev, sizeof(double) * (size_t)op->sp->ndof)); }
+   if (!op->yL_dev) { CDM_CUDA(ctx, cudaMalloc(&op->yL_dev, sizeof(double) * (size_t)op->sp->ndof)); }
+   return CDM_OK;
+}
+
+// Apply on buffers that have room for the ghost tail (length >= ndof): used by the
+// Krylov drivers so that no T<->L copies are needed.  x's tail is overwritten.
+int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   int rc;
+   const bool par = ctx->nranks > 1 && !sp->peers.empty();
+   if (par && (rc = cdm_halo_P(op, x_buf))) { return rc; }
+   if ((rc = cdm_k_apply(op, x_buf, y_buf, constrained))) { return rc; }
+   if (par && (rc = cdm_halo_PT(op, y_buf))) { return rc; }
+   if (constrained && op->n_ess > 0) { rc = cdm_k_copy_idx(ctx, op->n_ess, op->ess_dev, x_buf, y_buf); }
+   return rc;
+}
+
+static int apply_T(cdm_op *op, const double *x, double *y, bool constrained)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   if (sp->ntrue == sp->ndof) { return cdm_apply_tail(op, const_cast<double *>(x), y, constrained); }
+   int rc = ensure_L(op); if (rc) { return rc; }
+   CDM_CUDA(ctx, cudaMemcpyAsync(op->xL_dev, x, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyDeviceToDevice, ctx->stream));
+   if ((rc = cdm_apply_tail(op, op->xL_dev, op->yL_dev, constrained))) { return rc; }
+   CDM_CUDA(ctx, cudaMemcpyAsync(y, op->yL_dev, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyDeviceToDevice, ctx->stream));
+   return CDM_OK;
+}
+
+int cdm_operator_apply(cdm_op *op, const double *x_dev, double *y_dev)
+{
+   if (!op || !x_dev || !y_dev) { return CDM_EINVAL; }
+   if (x_dev == y_dev) { return cdm_fail(op->sp->ctx, CDM_EINVAL, "cdm_operator_apply: x and y must not alias"); }
+   return apply_T(op, x_dev, y_dev, true);
+}
+
+int cdm_operator_apply_unconstrained(cdm_op *op, const double *x_dev, double *y_dev)
+{
+   if (!op || !x_dev || !y_dev) { return CDM_EINVAL; }
+   if (x_dev == y_dev) { return cdm_fail(op->sp->ctx, CDM_EINVAL, "cdm_operator_apply_unconstrained: x and y must not alias"); }
+   return apply_T(op, x_dev, y_dev, false);
+}
+
+int cdm_operator_mult_host(cdm_op *op, const double *x_host, double *y_host, int constrained)
+{
+   if (!op || !x_host || !y_host) { return CDM_EINVAL; }
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   int rc = ensure_L(op); if (rc) { return rc; }
+   CDM_CUDA(ctx, cudaMemcpyAsync(op->xL_dev, x_host, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyHostToDevice, ctx->stream));
+   if ((rc = cdm_apply_tail(op, op->xL_dev, op->yL_dev, constrained != 0))) { return rc; }
+   CDM_CUDA(ctx, cudaMemcpyAsync(y_host, op->yL_dev, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyDeviceToHost, ctx->stream));
+   CDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+   return CDM_OK;
+}
+
+int cdm_operator_diag(cdm_op *op, double *d_dev)
+{
+   if (!op || !d_dev) { return CDM_EINVAL; }
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   int rc;
+   const bool par = ctx->nranks > 1 && !sp->peers.empty();
+   double *dst = d_dev;
+   if (sp->ntrue != sp->ndof) { if ((rc = ensure_L(op))) { return rc; } dst = op->yL_dev; }
+   if ((rc = cdm_k_diag(op, dst))) { return rc; }
+   if (par && (rc = cdm_halo_PT(op, dst))) { return rc; }
+   if (dst != d_dev) { CDM_CUDA(ctx, cudaMemcpyAsync(d_dev, dst, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyDeviceToDevice, ctx->stream)); }
+   if (op->n_ess > 0) { rc = cdm_k_set_idx(ctx, op->n_ess, op->ess_dev, 1.0, d_dev); }
+   return rc;
+}
+
+int cdm_eliminate_rhs(cdm_op *op, const double *x_dev, double *b_dev)
+{
+   if (!op || !x_dev || !b_dev) { return CDM_EINVAL; }
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   int rc = ensure_L(op); if (rc) { return rc; }
+   // w = 0 ; w[ess] = x[ess]
+   CDM_CUDA(ctx, cudaMemsetAsync(op->xL_dev, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream));
+   if (op->n_ess > 0 && (rc = cdm_k_copy_idx(ctx, op->n_ess, op->ess_dev, x_dev, op->xL_dev))) { return rc; }
+   if ((rc = cdm_apply_tail(op, op->xL_dev, op->yL_dev, false))) { return rc; }
+   if ((rc = cdm_k_axpy(ctx, sp->ntrue, -1.0, op->yL_dev, b_dev))) { return rc; }
+   if (op->n_ess > 0) { rc = cdm_k_copy_idx(ctx, op->n_ess, op->ess_dev, x_dev, b_dev); }
+   return rc;
+}
+
+int cdm_operator_get_qdata(const cdm_op *op, double *Ddiff, double *Dconv, double *Dmass)
+{
+   if (!op) { return CDM_EINVAL; }
+   return cdm_k_get_qdata(op, Ddiff, Dconv, Dmass);
+}
+
+// ---------------------------------------------------------------- vectors
+
+int cdm_vec_alloc(cdm_ctx *c, int64_t n, double **v)
+{
+   CDM_REQUIRE_GPU(c);
+   if (n < 0 || !v) { return CDM_EINVAL; }
+   if (cudaMalloc((void **)v, sizeof(double) * (size_t)(n > 0 ? n : 1)) != cudaSuccess)
+   { cudaGetLastError(); return cdm_fail(c, CDM_ENOMEM, "cdm_vec_alloc: out of device memory"); }
+   return CDM_OK;
+}
+int cdm_vec_free(cdm_ctx *c, double *v) { CDM_REQUIRE_GPU(c); CDM_CUDA(c, cudaFree(v)); return CDM_OK; }
+int cdm_vec_set(cdm_ctx *c, int64_t n, double value, double *v) { CDM_REQUIRE_GPU(c); return cdm_k_set(c, n, value, v); }
+int cdm_vec_upload(cdm_ctx *c, int64_t n, const double *host, double *v)
+{
+   CDM_REQUIRE_GPU(c);
+   CDM_CUDA(c, cudaMemcpyAsync(v, host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+   CDM_CUDA(c, cudaStreamSynchronize(c->stream));
+   return CDM_OK;
+}
+int cdm_vec_download(cdm_ctx *c, int64_t n, const double *v, double *host)
+{
+   CDM_REQUIRE_GPU(c);
+   CDM_CUDA(c, cudaMemcpyAsync(host, v, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+   CDM_CUDA(c, cudaStreamSynchronize(c->stream));
+   return CDM_OK;
+}
+int cdm_axpy(cdm_ctx *c, int64_t n, double a, const double *x, double *y) { CDM_REQUIRE_GPU(c); return cdm_k_axpy(c, n, a, x, y); }
+int cdm_add(cdm_ctx *c, int64_t n, const double *x, double a, const double *y, double *z) { CDM_REQUIRE_GPU(c); return cdm_k_add(c, n, x, a, y, z); }
+int cdm_pointwise_mult(cdm_ctx *c, int64_t n, const double *d, const double *x, double *y) { CDM_REQUIRE_GPU(c); return cdm_k_pmult(c, n, d, x, y); }
+
+static double *red_out(cdm_ctx *c) { return c->red_dev + (size_t)CDM_RED_MAXK * CDM_RED_BLOCKS; }
+
+int cdm_mdot(cdm_ctx *c, int64_t n, int k, const double *w, const double *V, int64_t ldv, double *result_host)
+{
+   CDM_REQUIRE_GPU(c);
+   if (!result_host) { return CDM_EINVAL; }
+   int rc = cdm_k_mdot_dev(c, n, k, w, V, ldv, red_out(c)); if (rc) { return rc; }
+   if ((rc = cdm_allreduce_sum(c, red_out(c), k))) { return rc; }
+   CDM_CUDA(c, cudaMemcpyAsync(c->red_host, red_out(c), sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
+   CDM_CUDA(c, cudaStreamSynchronize(c->stream));
+   for (int i = 0; i < k; i++) { result_host[i] = c->red_host[i]; }
+   return CDM_OK;
+}
+int cdm_dot(cdm_ctx *c, int64_t n, const double *x, const double *y, double *result_host) { return cdm_mdot(c, n, 1, x, y, n, result_host); }
+int cdm_norm2(cdm_ctx *c, int64_t n, const double *x, double *result_host)
+{
+   int rc = cdm_mdot(c, n, 1, x, x, n, result_host);
+   if (!rc) { *result_host = std::sqrt(*result_host); }
+   return rc;
+}
+int cdm_maxpy(cdm_ctx *c, int64_t n, int k, const double *h_host, const double *V, int64_t ldv, double *w)
+{
+   CDM_REQUIRE_GPU(c);
+   if (k < 0 || k > CDM_RED_MAXK || (k > 0 && !h_host)) { return CDM_EINVAL; }
+   double *hd = red_out(c) + CDM_RED_MAXK;
+   for (int i = 0; i < k; i++) { c->red_host[CDM_RED_MAXK + i] = h_host[i]; }
+   CDM_CUDA(c, cudaMemcpyAsync(hd, c->red_host + CDM_RED_MAXK, sizeof(double) * k, cudaMemcpyHostToDevice, c->stream));
+   int rc = cdm_k_maxpy_dev(c, n, k, hd, V, ldv, w, nullptr);
+   if (!rc) { CDM_CUDA(c, cudaStreamSynchronize(c->stream)); }
+   return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// cdm_internal.hpp -- internal types shared by the host and CUDA translation units.
+#pragma once
+#include "cdm_b200.h"
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#define CDM_MAX_D1D 7
+#define CDM_MAX_Q1D 8
+
+struct ncclComm;
+
+struct cdm_ctx
+{
+   int device = -1;                 // -1: host-only context
+   cudaStream_t stream = nullptr;
+   bool own_stream = false;
+   mutable std::string err;
+   int64_t launches = 0;
+   // multi-GPU
+   ncclComm *comm = nullptr;
+   int rank = 0, nranks = 1;
+   // reduction scratch (device) + pinned host mirror
+   double *red_dev = nullptr;       // [RED_BLOCKS * RED_MAXK] partials + [RED_MAXK] results
+   double *red_host = nullptr;      // pinned, RED_MAXK
+   int sm_count = 148;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct cdm_mesh
+{
+   int dim = 0;
+   int64_t nv = 0, ne = 0, nbe = 0;
+   std::vector<double> vx;          // nv*dim, vertex-major
+   std::vector<int32_t> ev;         // ne*2^dim
+   std::vector<int32_t> bv;         // nbe*2^(dim-1)
+   std::vector<int32_t> battr;      // nbe
+   // Cartesian provenance (for box partitioning)
+   bool cartesian = false;
+   int64_t n[3] = {0, 0, 0};
+   // set on submeshes produced by cdm_mesh_partition_box
+   bool is_part = false;
+   int parts[3] = {1, 1, 1};
+   int rank = 0;
+   std::vector<int64_t> vglobal;    // local vertex -> global vertex id of the parent mesh
+   int64_t gn[3] = {0, 0, 0};       // parent mesh element counts
+   int64_t lo[3] = {0, 0, 0};       // first parent element of this box along each axis
+};
+
+// shared-dof exchange plan with one neighbour rank
+struct cdm_halo_peer
+{
+   int rank = -1;
+   // dofs I own that the peer holds as ghosts (peer sends me partial sums / I send values)
+   std::vector<int32_t> own_idx;    // local dof ids (owned, < ntrue)
+   // dofs the peer owns that I hold as ghosts
+   std::vector<int32_t> ghost_idx;  // local dof ids (>= ntrue)
+   int32_t *own_idx_dev = nullptr, *ghost_idx_dev = nullptr;
+   double *send_dev = nullptr, *recv_dev = nullptr;   // max(own, ghost) entries each
+};
+
+struct cdm_space
+{
+   cdm_ctx *ctx = nullptr;
+   int dim = 0, p = 0, d1d = 0, q1d = 0, nd = 0, nq = 0;
+   int64_t ne = 0, ndof = 0, ntrue = 0, nv = 0;
+   // host
+   std::vector<int32_t> gather, offsets, indices;     // ElementRestriction arrays
+   std::vector<double> B, G, qw, nodes, qx;           // 1-D tables (q1d x d1d)
+   std::vector<double> elem_x;                        // ne * nvpe * dim vertex coordinates
+   // entity tables kept for essential-dof marking
+   std::vector<int32_t> bdr_vtx, bdr_attr;
+   std::vector<int32_t> bdr_dofs_flat, bdr_dofs_off;  // per boundary element: its dofs
+   int64_t nbe = 0;
+   // device
+   int32_t *gather_dev = nullptr, *offsets_dev = nullptr, *indices_dev = nullptr;
+   double *elem_x_dev = nullptr;
+   // multi-GPU
+   std::vector<cdm_halo_peer> peers;
+   std::vector<int64_t> dof_global;                    // local dof -> global dof id (partitioned spaces)
+};
+
+struct cdm_op
+{
+   cdm_space *sp = nullptr;
+   bool has_diff = false, has_conv = false, has_mass = false;
+   int ncomp = 0;                  // stored D components per point
+   int slab = 0;                   // doubles per (element, z-slab) [3D] or per element [2D]
+   double *D_dev = nullptr;
+   int64_t D_len = 0;
+   int32_t *gather_c_dev = nullptr; // gather map with essential dofs encoded as -1-g
+   int32_t *ess_dev = nullptr;      // owned essential dofs (y[ess] = x[ess])
+   int64_t n_ess = 0;
+   std::vector<int32_t> ess_host;
+   double *yE_dev = nullptr;       // E-vector scratch (scatter mode 0)
+   double *xL_dev = nullptr, *yL_dev = nullptr;   // L-vector scratch (multi-GPU / host mult)
+   double *dinv_dev = nullptr;     // cached Jacobi inverse diagonal
+   int scatter_mode = 1;           // 0: E-vector + gather transpose, 1: FP64 red.add
+   int kernel_variant = 0;
+   // krylov workspace (lazy)
+   double *kry_dev = nullptr; int64_t kry_len = 0;
+   std::vector<double> coef_scratch;
+};
+
+// ---- error helpers
+int cdm_fail(const cdm_ctx *ctx, int code, const std::string &msg);
+#define CDM_CUDA(ctx, call)                                                              \
+   do { cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+           return cdm_fail(ctx, CDM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+   } while (0)
+#define CDM_REQUIRE_GPU(ctx)                                                             \
+   do { if (!(ctx) || (ctx)->device < 0)                                                 \
+           return cdm_fail(ctx, CDM_ENOGPU, "no CUDA device bound to this context (no CPU fallback)"); \
+   } while (0)
+
+// ---- host-side builders (host_*.cpp)
+void cdm_host_gauss_legendre(int n, double *x, double *w);
+void cdm_host_gauss_lobatto(int n, double *x);
+void cdm_host_basis(int p, int q1d, double *B, double *G, double *qw, double *nodes, double *qx);
+int  cdm_host_q1d(int dim, int p);
+int64_t cdm_host_h1_numbering(const cdm_mesh &m, int p, std::vector<int32_t> &elem_dof,
+                              std::vector<int32_t> &bdr_off, std::vector<int32_t> &bdr_flat);
+void cdm_host_restriction(int64_t ne, int nd, int64_t ndof, const std::vector<int32_t> &gather,
+                          std::vector<int32_t> &offsets, std::vector<int32_t> &indices);
+
+// ---- kernel launchers (kernels_*.cu); all asynchronous on ctx->stream
+int cdm_k_setup_qdata(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel, double alpha,
+                      const cdm_coeff *mass);
+int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained);
+int cdm_k_diag(cdm_op *op, double *dL);
+int cdm_k_get_qdata(const cdm_op *op, double *Ddiff, double *Dconv, double *Dmass);
+int cdm_k_upload_basis(cdm_space *sp);
+
+int cdm_k_set(cdm_ctx *c, int64_t n, double v, double *x);
+int cdm_k_axpy(cdm_ctx *c, int64_t n, double a, const double *x, double *y);
+int cdm_k_add(cdm_ctx *c, int64_t n, const double *x, double a, const double *y, double *z);
+int cdm_k_pmult(cdm_ctx *c, int64_t n, const double *d, const double *x, double *y);
+int cdm_k_copy_idx(cdm_ctx *c, int64_t n, const int32_t *idx, const double *x, double *y);   // y[idx]=x[idx]
+int cdm_k_zero_idx(cdm_ctx *c, int64_t n, const int32_t *idx, double *y);                    // y[idx]=0
+int cdm_k_set_idx(cdm_ctx *c, int64_t n, const int32_t *idx, double v, double *y);           // y[idx]=v
+int cdm_k_pack(cdm_ctx *c, int64_t n, const int32_t *idx, const double *x, double *buf);     // buf[i]=x[idx[i]]
+int cdm_k_unpack(cdm_ctx *c, int64_t n, const int32_t *idx, const double *buf, double *x, int add);
+int cdm_k_recip(cdm_ctx *c, int64_t n, const double *d, double *dinv);
+// k dots of w against V columns -> ctx->red_dev results [k] (device), deterministic
+int cdm_k_mdot_dev(cdm_ctx *c, int64_t n, int k, const double *w, const double *V, int64_t ldv,
+                   double *out_dev);
+// w -= sum_i h_dev[i] V_i ; optionally also out_dev[0] = ||w_new||^2 partial-reduced
+int cdm_k_maxpy_dev(cdm_ctx *c, int64_t n, int k, const double *h_dev, const double *V, int64_t ldv,
+                    double *w, double *norm2_out_dev);
+// v = w * (1/sqrt(*norm2_dev))
+int cdm_k_scale_by_rnorm(cdm_ctx *c, int64_t n, const double *norm2_dev, const double *w, double *v);
+int cdm_k_scale(cdm_ctx *c, int64_t n, double a, const double *w, double *v);
+// fused CG update: x += a d ; r -= a z ; out = (r,r)
+int cdm_k_cg_update(cdm_ctx *c, int64_t n, double a, const double *d, const double *z, double *x,
+                    double *r, double *rr_out_dev);
+
+// ---- halo exchange (comm.cpp)
+int cdm_halo_P(cdm_op *op, double *xL);            // owner -> ghost values
+int cdm_halo_PT(cdm_op *op, double *yL);           // ghost partial sums -> owner (add)
+int cdm_allreduce_sum(cdm_ctx *c, double *buf_dev, int k);

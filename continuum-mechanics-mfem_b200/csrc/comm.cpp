@@ -1,0 +1,138 @@
+// comm.cpp -- mesh-partitioned multi-GPU mode: shared-dof halo exchange (P, P^T)
+// and the Krylov all-reduce, over NCCL.  One rank per GPU.
+//
+// Stands behind ParMesh(MPI_COMM_WORLD, *mesh) / ParFiniteElementSpace
+// (linear_convection_diffusion_2D.cpp:300,312): MFEM's prolongation P (owner ->
+// sharers) and its transpose, and MPI_Allreduce inside InnerProduct
+// (newton_petsc_solver.hpp:82-85).  NCCL is resolved at run time with dlopen so
+// that the single-GPU path has no dependency on it.
+#include "cdm_internal.hpp"
+#include <dlfcn.h>
+#include <cstring>
+
+namespace
+{
+typedef struct { char internal[128]; } nccl_uid;
+typedef int nccl_result;
+struct NcclApi
+{
+   void *h = nullptr;
+   nccl_result (*GetUniqueId)(nccl_uid *) = nullptr;
+   nccl_result (*CommInitRank)(ncclComm **, int, nccl_uid, int) = nullptr;
+   nccl_result (*CommDestroy)(ncclComm *) = nullptr;
+   nccl_result (*AllReduce)(const void *, void *, size_t, int, int, ncclComm *, cudaStream_t) = nullptr;
+   nccl_result (*Send)(const void *, size_t, int, int, ncclComm *, cudaStream_t) = nullptr;
+   nccl_result (*Recv)(void *, size_t, int, int, ncclComm *, cudaStream_t) = nullptr;
+   nccl_result (*GroupStart)() = nullptr;
+   nccl_result (*GroupEnd)() = nullptr;
+   const char *(*GetErrorString)(nccl_result) = nullptr;
+};
+const int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+NcclApi *api()
+{
+   static NcclApi a;
+   static bool tried = false;
+   if (tried) { return a.h ? &a : nullptr; }
+   tried = true;
+   const char *names[] = {"libnccl.so.2", "libnccl.so"};
+   for (const char *nm : names) { a.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (a.h) { break; } }
+   if (!a.h) { return nullptr; }
+#define SYM(field, name) *(void **)(&a.field) = dlsym(a.h, name); if (!a.field) { a.h = nullptr; return nullptr; }
+   SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+   SYM(AllReduce, "ncclAllReduce") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+   SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+   return &a;
+}
+}  // namespace
+
+#define NCCL_CALL(ctx, call)                                                                   \
+   do { nccl_result r_ = (call);                                                               \
+        if (r_ != 0) { return cdm_fail(ctx, CDM_ENCCL, std::string(#call) + ": " + api()->GetErrorString(r_)); } \
+   } while (0)
+
+extern "C" int cdm_comm_unique_id(void *uid128)
+{
+   if (!uid128) { return CDM_EINVAL; }
+   NcclApi *a = api();
+   if (!a) { return CDM_ENCCL; }
+   nccl_uid id;
+   if (a->GetUniqueId(&id) != 0) { return CDM_ENCCL; }
+   std::memcpy(uid128, &id, sizeof(id));
+   return CDM_OK;
+}
+
+extern "C" int cdm_comm_init(cdm_ctx *ctx, int rank, int nranks, const void *uid128)
+{
+   CDM_REQUIRE_GPU(ctx);
+   if (nranks < 1 || rank < 0 || rank >= nranks) { return cdm_fail(ctx, CDM_EINVAL, "cdm_comm_init: bad rank"); }
+   ctx->rank = rank; ctx->nranks = nranks;
+   if (nranks == 1) { return CDM_OK; }
+   if (!uid128) { return cdm_fail(ctx, CDM_EINVAL, "cdm_comm_init: missing unique id"); }
+   NcclApi *a = api();
+   if (!a) { return cdm_fail(ctx, CDM_ENCCL, "cdm_comm_init: libnccl.so.2 not found"); }
+   nccl_uid id;
+   std::memcpy(&id, uid128, sizeof(id));
+   CDM_CUDA(ctx, cudaSetDevice(ctx->device));
+   NCCL_CALL(ctx, a->CommInitRank(&ctx->comm, nranks, id, rank));
+   return CDM_OK;
+}
+
+extern "C" int cdm_comm_rank(const cdm_ctx *ctx, int *rank, int *nranks)
+{
+   if (!ctx) { return CDM_EINVAL; }
+   if (rank) { *rank = ctx->rank; }
+   if (nranks) { *nranks = ctx->nranks; }
+   return CDM_OK;
+}
+
+int cdm_allreduce_sum(cdm_ctx *c, double *buf_dev, int k)
+{
+   if (c->nranks <= 1 || !c->comm) { return CDM_OK; }
+   NCCL_CALL(c, api()->AllReduce(buf_dev, buf_dev, (size_t)k, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+   return CDM_OK;
+}
+
+// x_L ghost entries <- owner values
+int cdm_halo_P(cdm_op *op, double *xL)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *c = sp->ctx;
+   if (!c->comm) { return cdm_fail(c, CDM_ENCCL, "partitioned space used without cdm_comm_init"); }
+   NcclApi *a = api();
+   for (auto &pr : sp->peers)
+      if (!pr.own_idx.empty()) { int rc = cdm_k_pack(c, (int64_t)pr.own_idx.size(), pr.own_idx_dev, xL, pr.send_dev); if (rc) { return rc; } }
+   NCCL_CALL(c, a->GroupStart());
+   for (auto &pr : sp->peers)
+   {
+      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Send(pr.send_dev, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
+      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Recv(pr.recv_dev, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
+   }
+   NCCL_CALL(c, a->GroupEnd());
+   for (auto &pr : sp->peers)
+      if (!pr.ghost_idx.empty()) { int rc = cdm_k_unpack(c, (int64_t)pr.ghost_idx.size(), pr.ghost_idx_dev, pr.recv_dev, xL, 0); if (rc) { return rc; } }
+   return CDM_OK;
+}
+
+// owner entries of y_L += partial sums held in the sharers' ghost entries
+int cdm_halo_PT(cdm_op *op, double *yL)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *c = sp->ctx;
+   if (!c->comm) { return cdm_fail(c, CDM_ENCCL, "partitioned space used without cdm_comm_init"); }
+   NcclApi *a = api();
+   for (auto &pr : sp->peers)
+      if (!pr.ghost_idx.empty()) { int rc = cdm_k_pack(c, (int64_t)pr.ghost_idx.size(), pr.ghost_idx_dev, yL, pr.send_dev); if (rc) { return rc; } }
+   NCCL_CALL(c, a->GroupStart());
+   for (auto &pr : sp->peers)
+   {
+      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Send(pr.send_dev, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
+      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Recv(pr.recv_dev, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
+   }
+   NCCL_CALL(c, a->GroupEnd());
+   // fixed peer order -> deterministic summation
+   for (auto &pr : sp->peers)
+      if (!pr.own_idx.empty()) { int rc = cdm_k_unpack(c, (int64_t)pr.own_idx.size(), pr.own_idx_dev, pr.recv_dev, yL, 1); if (rc) { return rc; } }
+   return CDM_OK;
+}

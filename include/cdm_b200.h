@@ -1,0 +1,222 @@
+/* cdm_b200.h -- C ABI of the B200-native convection-diffusion hot path.
+ *
+ * This is the drop-in boundary of the library: plain pointers and sizes, no
+ * C++/torch types.  Each entry point names the reference interface it stands
+ * behind (file:line relative to
+ * /root/reference/myapps/convection_diffusion/; "MFEM:" = the upstream MFEM
+ * virtual the reference calls through, MFEM itself is not vendored).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative CDM_E* code; it never
+ *     throws across the ABI.  cdm_last_error(ctx) returns a message.
+ *   - a non-converged Krylov solve is NOT an error: it is reported through
+ *     cdm_krylov_result.converged (solver.GetConverged(),
+ *     linear_convection_diffusion_2D.cpp:371).
+ *   - host arrays passed in are copied; the library owns all device memory
+ *     behind the opaque handles.  Pointers named *_dev are device pointers
+ *     owned by the caller (or by cdm_vec_alloc); pointers named *_host are
+ *     host pointers.
+ *   - a context is bound to one CUDA device and one stream; calls on one
+ *     context are not thread-safe, different contexts are independent.
+ *   - there is no CPU fallback: every compute entry point fails with
+ *     CDM_ENOGPU when no CUDA device is usable.
+ */
+#ifndef CDM_B200_H
+#define CDM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDM_OK        0
+#define CDM_EINVAL   -1   /* bad argument */
+#define CDM_ENOGPU   -2   /* no usable CUDA device / CUDA runtime failure at init */
+#define CDM_ECUDA    -3   /* CUDA error during a call */
+#define CDM_ENOMEM   -4
+#define CDM_ENCCL    -5   /* NCCL error */
+#define CDM_EUNSUP   -6   /* unsupported order / dimension */
+
+typedef struct cdm_ctx   cdm_ctx;
+typedef struct cdm_mesh  cdm_mesh;
+typedef struct cdm_space cdm_space;
+typedef struct cdm_op    cdm_op;
+
+/* ---------------------------------------------------------------- context */
+/* Device("cpu") at linear_convection_diffusion_2D.cpp:287 becomes one of these.
+   stream: a cudaStream_t to run on, or NULL to create a private one. */
+int  cdm_init(int device, void *stream, cdm_ctx **ctx);
+int  cdm_finalize(cdm_ctx *ctx);
+const char *cdm_last_error(const cdm_ctx *ctx);
+int  cdm_sync(cdm_ctx *ctx);                       /* cudaStreamSynchronize */
+void *cdm_stream(cdm_ctx *ctx);
+const char *cdm_version(void);
+/* host-only context (mesh / space construction, no device); compute calls fail */
+int  cdm_init_host(cdm_ctx **ctx);
+
+/* multi-GPU: one context per rank; unique_id = 128-byte ncclUniqueId produced
+   by cdm_comm_unique_id on rank 0 and distributed by the caller
+   (MPI_COMM_WORLD at linear_convection_diffusion_2D.cpp:240,300). */
+int  cdm_comm_unique_id(void *unique_id_128);
+int  cdm_comm_init(cdm_ctx *ctx, int rank, int nranks, const void *unique_id_128);
+int  cdm_comm_rank(const cdm_ctx *ctx, int *rank, int *nranks);
+
+/* ------------------------------------------------------------------- mesh */
+/* Mesh(file)+UniformRefinement (linear_convection_diffusion_2D.cpp:290-298)
+   for the Cartesian configs: MFEM Mesh::MakeCartesian2D/3D numbering
+   (sfc_ordering=false), optional smooth interior perturbation (units of h). */
+int  cdm_mesh_cartesian(cdm_ctx *ctx, int dim, const int64_t n[3], const double size[3],
+                        double perturb, cdm_mesh **mesh);
+/* any conforming quad/hex mesh: MFEM vertex order within elements */
+int  cdm_mesh_from_arrays(cdm_ctx *ctx, int dim, int64_t nv, const double *vertices,
+                          int64_t ne, const int32_t *elem_vtx,
+                          int64_t nbe, const int32_t *bdr_vtx, const int32_t *bdr_attr,
+                          cdm_mesh **mesh);
+int  cdm_mesh_sizes(const cdm_mesh *mesh, int *dim, int64_t *nv, int64_t *ne, int64_t *nbe);
+int  cdm_mesh_get(const cdm_mesh *mesh, double *vertices, int32_t *elem_vtx,
+                  int32_t *bdr_vtx, int32_t *bdr_attr);       /* any pointer may be NULL */
+int  cdm_mesh_destroy(cdm_mesh *mesh);
+/* ParMesh(MPI_COMM_WORLD, *mesh) (linear_convection_diffusion_2D.cpp:300): element
+   partition of a Cartesian mesh into px*py*pz boxes; returns this rank's submesh.
+   Shared-dof bookkeeping happens in cdm_space_create_h1 on the returned mesh. */
+int  cdm_mesh_partition_box(cdm_ctx *ctx, const cdm_mesh *global, const int parts[3], int rank,
+                            cdm_mesh **local);
+
+/* ------------------------------------------------------------------ space */
+/* H1_FECollection(order,dim) + (Par)FiniteElementSpace
+   (linear_convection_diffusion_2D.cpp:311-312): MFEM entity-major numbering,
+   GLL nodes, lexicographic ElementRestriction. */
+int  cdm_space_create_h1(cdm_ctx *ctx, const cdm_mesh *mesh, int order, cdm_space **space);
+/* same, but with the element->dof table supplied by the caller (e.g. taken from a
+   live mfem::FiniteElementSpace): elem_dof[ne * (order+1)^dim], lexicographic in
+   element; bit-exact index maps are then derived from MFEM's own numbering. */
+int  cdm_space_create_from_table(cdm_ctx *ctx, const cdm_mesh *mesh, int order, int64_t ndof,
+                                 const int32_t *elem_dof, cdm_space **space);
+int  cdm_space_sizes(const cdm_space *space, int *dim, int *order, int64_t *ne, int64_t *ndof,
+                     int *d1d, int *q1d, int64_t *ntrue);
+/* ElementRestriction index arrays (MFEM fem/restriction.cpp): gather_map[ne*nd],
+   offsets[ndof+1], indices[ne*nd] -- host copies, any pointer may be NULL */
+int  cdm_space_get_maps(const cdm_space *space, int32_t *gather_map, int32_t *offsets,
+                        int32_t *indices);
+/* fespace.GetEssentialTrueDofs(ess_bdr, list) (linear_convection_diffusion_2D.cpp:319-322).
+   bdr_marker[nattr]; call with list=NULL to get the count. Sorted ascending. */
+int  cdm_space_essential_dofs(const cdm_space *space, const int32_t *bdr_marker, int nattr,
+                              int32_t *list, int64_t *count);
+/* 1-D tables used by the kernels: B,G are q1d x d1d row-major, qw[q1d], nodes[d1d] */
+int  cdm_space_get_basis(const cdm_space *space, double *B, double *G, double *qw, double *nodes);
+/* physical coordinates of the dofs (ndof x dim), e.g. to project coefficients
+   (ProjectBdrCoefficient, linear_convection_diffusion_2D.cpp:347) */
+int  cdm_space_dof_coords(const cdm_space *space, double *xyz_host);
+/* physical coordinates of the quadrature points (ne x nq x dim): what
+   Coefficient::Eval(T, ip) sees (linear_convection_diffusion_2D.cpp:165) */
+int  cdm_space_qpt_coords(const cdm_space *space, double *xyz_host);
+int  cdm_space_destroy(cdm_space *space);
+
+/* --------------------------------------------------------------- operator */
+#define CDM_COEFF_NONE  0   /* integrator absent */
+#define CDM_COEFF_CONST 1   /* ConstantCoefficient / VectorConstantCoefficient */
+#define CDM_COEFF_QPT   2   /* values at quadrature points: data[(e*nq+q)*ncomp + c] (host) */
+typedef struct
+{
+   int kind;             /* CDM_COEFF_* */
+   int ncomp;            /* kappa: 1 or dim*(dim+1)/2 (sym. matrix 11,21,31,22,32,33);
+                            velocity: dim; mass: 1 */
+   const double *data;   /* host pointer */
+} cdm_coeff;
+
+/* ParBilinearForm a; a.AddDomainIntegrator(new DiffusionIntegrator(kappa));
+   a.AddDomainIntegrator(new ConvectionIntegrator(vel, conv_alpha));
+   a.AddDomainIntegrator(new MassIntegrator(mass)); a.Assemble();
+   (linear_convection_diffusion_2D.cpp:335-339, linear_convection_diffusion_1D.cpp:391-400)
+   = BilinearFormIntegrator::AssemblePA: geometric factors + D-tensors on the device.
+   ess_dofs: essential dof list used by the constrained apply (may be NULL/0). */
+int  cdm_operator_create(cdm_space *space, const cdm_coeff *kappa, const cdm_coeff *vel,
+                         double conv_alpha, const cdm_coeff *mass,
+                         const int32_t *ess_dofs, int64_t n_ess, cdm_op **op);
+/* re-run the quadrature-data setup with new coefficients (per-step re-assembly,
+   diffusion_mms_ale.cpp:1017-1023) */
+int  cdm_operator_update(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel,
+                         double conv_alpha, const cdm_coeff *mass);
+int  cdm_operator_destroy(cdm_op *op);
+int64_t cdm_operator_size(const cdm_op *op);        /* height = width = true dofs on this rank */
+/* MFEM: Operator::Mult of FormLinearSystem's constrained operator
+   (ConstrainedOperator, DIAG_ONE): y = A z, z = x with z[ess]=0, y[ess]=x[ess].
+   In multi-GPU mode x,y are this rank's T-vectors and the call includes the
+   P / P^T halo exchange. */
+int  cdm_operator_apply(cdm_op *op, const double *x_dev, double *y_dev);
+/* MFEM: BilinearForm::Mult on L-vectors, no constraints
+   (mass_form.Mult(c, rhs), linear_convection_diffusion_1D.cpp:544) */
+int  cdm_operator_apply_unconstrained(cdm_op *op, const double *x_dev, double *y_dev);
+/* same two calls with host vectors (mfem::Vector under Device("cpu")): the
+   host<->device copies are inside the call */
+int  cdm_operator_mult_host(cdm_op *op, const double *x_host, double *y_host, int constrained);
+/* MFEM: BilinearFormIntegrator::AssembleDiagonalPA + OperatorJacobiSmoother
+   (-pc_type jacobi, Input/petsc.opts:6): d = diag(A), d[ess] = 1 */
+int  cdm_operator_diag(cdm_op *op, double *d_dev);
+/* MFEM: ConstrainedOperator::EliminateRHS (a.FormLinearSystem,
+   linear_convection_diffusion_2D.cpp:351): w=0; w[ess]=x[ess]; b -= A w; b[ess]=x[ess] */
+int  cdm_eliminate_rhs(cdm_op *op, const double *x_dev, double *b_dev);
+/* raw quadrature data (tests): host copy in MFEM layout, q fastest:
+   Ddiff[(e*nsym+c)*nq+q], Dconv[(e*dim+c)*nq+q], Dmass[e*nq+q]; pointers may be NULL */
+int  cdm_operator_get_qdata(const cdm_op *op, double *Ddiff, double *Dconv, double *Dmass);
+/* tuning knobs (benchmarks): name in {"scatter" (0 E-vector+gather, 1 atomics), "kernel" (variant id)} */
+int  cdm_operator_set_option(cdm_op *op, const char *name, int value);
+/* number of kernel launches issued by this context so far */
+int64_t cdm_launch_count(const cdm_ctx *ctx);
+
+/* ---------------------------------------------------------------- vectors */
+int  cdm_vec_alloc(cdm_ctx *ctx, int64_t n, double **v_dev);
+int  cdm_vec_free(cdm_ctx *ctx, double *v_dev);
+int  cdm_vec_set(cdm_ctx *ctx, int64_t n, double value, double *v_dev);
+int  cdm_vec_upload(cdm_ctx *ctx, int64_t n, const double *host, double *v_dev);
+int  cdm_vec_download(cdm_ctx *ctx, int64_t n, const double *v_dev, double *host);
+/* MFEM linalg/vector.cpp kernels used by CGSolver/GMRESSolver
+   (mesh_recession_handler.cpp:270-276): y = a*x + y ; z = x + a*y ; dot */
+int  cdm_axpy(cdm_ctx *ctx, int64_t n, double a, const double *x_dev, double *y_dev);
+int  cdm_add(cdm_ctx *ctx, int64_t n, const double *x_dev, double a, const double *y_dev,
+             double *z_dev);
+int  cdm_pointwise_mult(cdm_ctx *ctx, int64_t n, const double *d_dev, const double *x_dev,
+                        double *y_dev);
+/* InnerProduct(comm, x, y) (newton_petsc_solver.hpp:82-85): fixed-order local
+   reduction + all-reduce when a communicator is attached */
+int  cdm_dot(cdm_ctx *ctx, int64_t n, const double *x_dev, const double *y_dev, double *result_host);
+/* k dot products of w against V_0..V_{k-1} (column i at V + i*ldv) in one pass */
+int  cdm_mdot(cdm_ctx *ctx, int64_t n, int k, const double *w_dev, const double *V_dev, int64_t ldv,
+              double *result_host);
+/* w -= sum_i h[i] V_i */
+int  cdm_maxpy(cdm_ctx *ctx, int64_t n, int k, const double *h_host, const double *V_dev,
+               int64_t ldv, double *w_dev);
+int  cdm_norm2(cdm_ctx *ctx, int64_t n, const double *x_dev, double *result_host);
+
+/* ----------------------------------------------------------------- Krylov */
+#define CDM_GMRES_PETSC 0   /* classical Gram-Schmidt, default restart 30 (PETSc KSPGMRES) */
+#define CDM_GMRES_MFEM  1   /* modified Gram-Schmidt, default restart 50 (mfem::GMRESSolver) */
+typedef struct
+{
+   int    variant;     /* CDM_GMRES_* (ignored by CG) */
+   int    restart;     /* 0 = variant default */
+   int    max_it;      /* -ksp_max_it 500 */
+   double rtol, atol;  /* -ksp_rtol 1e-10 -ksp_atol 1e-12 ; CG: rel 1e-12 abs 0 */
+   int    zero_guess;  /* 1: iterative_mode=false (PetscLinearSolver default) */
+   int    jacobi;      /* 1: -pc_type jacobi (diag from cdm_operator_diag) */
+} cdm_krylov_opts;
+typedef struct
+{
+   int    iters, converged;   /* GetNumIterations / GetConverged */
+   double final_norm;         /* GetFinalNorm */
+   int    hist_len;           /* entries written to hist */
+   double seconds;            /* device time of the solve (CUDA events) */
+} cdm_krylov_result;
+/* PetscLinearSolver(A).Mult(B,X) with Input/petsc.opts (linear_convection_diffusion_2D.cpp:368-370):
+   left-preconditioned restarted GMRES on the constrained operator.
+   hist_host: max_it+2 slots for the preconditioned residual history, or NULL. */
+int  cdm_gmres(cdm_op *op, const double *b_dev, double *x_dev, const cdm_krylov_opts *opts,
+               cdm_krylov_result *result, double *hist_host);
+/* mfem::CGSolver::Mult (mesh_recession_handler.cpp:270-276); hist = (r,z) per iteration */
+int  cdm_cg(cdm_op *op, const double *b_dev, double *x_dev, const cdm_krylov_opts *opts,
+            cdm_krylov_result *result, double *hist_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDM_B200_H */
