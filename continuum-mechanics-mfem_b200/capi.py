@@ -86,6 +86,9 @@ SIGNATURES = {
     "cdm_space_get_basis": (_ci, [_vp, _vp, _vp, _vp, _vp]),
     "cdm_space_dof_coords": (_ci, [_vp, _vp]),
     "cdm_space_qpt_coords": (_ci, [_vp, _vp]),
+    "cdm_space_halo_peers": (_ci, [_vp, C.POINTER(_ci)]),
+    "cdm_space_halo_peer": (_ci, [_vp, _ci, C.POINTER(_ci), C.POINTER(_i64), C.POINTER(_i64), _vp, _vp]),
+    "cdm_space_dof_global": (_ci, [_vp, _vp]),
     "cdm_space_destroy": (_ci, [_vp]),
     "cdm_operator_create": (_ci, [_vp, C.POINTER(Coeff), C.POINTER(Coeff), _cd, C.POINTER(Coeff), _vp, _i64, _pp]),
     "cdm_operator_update": (_ci, [_vp, C.POINTER(Coeff), C.POINTER(Coeff), _cd, C.POINTER(Coeff)]),
@@ -98,6 +101,7 @@ SIGNATURES = {
     "cdm_eliminate_rhs": (_ci, [_vp, _vp, _vp]),
     "cdm_operator_get_qdata": (_ci, [_vp, _vp, _vp, _vp]),
     "cdm_operator_set_option": (_ci, [_vp, C.c_char_p, _ci]),
+    "cdm_operator_time_kernel": (_ci, [_vp, _vp, _vp, _ci, _ci, C.POINTER(_cd)]),
     "cdm_launch_count": (_i64, [_vp]),
     "cdm_vec_alloc": (_ci, [_vp, _i64, _pp]),
     "cdm_vec_free": (_ci, [_vp, _vp]),
@@ -226,7 +230,7 @@ class Mesh:
     @classmethod
     def cartesian(cls, ctx, dim, n, size=None, perturb=0.0):
         n = list(n) if not np.isscalar(n) else [n] * dim
-        nn = (C.c_int64 * 3)(*(n + [0] * (3 - len(n))))
+        nn = (C.c_int64 * 3)(*((n + [0] * 3)[:3]))
         ss = (C.c_double * 3)(*((list(size) + [1.0] * 3)[:3] if size is not None else [1.0] * 3))
         h = C.c_void_p()
         ctx.check(lib().cdm_mesh_cartesian(ctx.h, dim, nn, ss, float(perturb), C.byref(h)))
@@ -310,6 +314,24 @@ class H1Space:
         lib().cdm_space_dof_coords(self.h, _ptr(out))
         return out
 
+    def halo(self):
+        """[(peer rank, owned-shared dof ids, ghost dof ids)] of a partitioned space"""
+        n = C.c_int()
+        lib().cdm_space_halo_peers(self.h, C.byref(n))
+        out = []
+        for i in range(n.value):
+            r, no, ng = C.c_int(), C.c_int64(), C.c_int64()
+            lib().cdm_space_halo_peer(self.h, i, C.byref(r), C.byref(no), C.byref(ng), None, None)
+            own, ghost = np.zeros(no.value, np.int32), np.zeros(ng.value, np.int32)
+            lib().cdm_space_halo_peer(self.h, i, C.byref(r), C.byref(no), C.byref(ng), _ptr(own), _ptr(ghost))
+            out.append((r.value, own, ghost))
+        return out
+
+    def dof_global(self):
+        k = np.zeros(self.ndof, np.int64)
+        lib().cdm_space_dof_global(self.h, _ptr(k))
+        return k
+
     def qpt_coords(self):
         out = np.zeros((self.ne, self.nq, self.dim))
         lib().cdm_space_qpt_coords(self.h, _ptr(out))
@@ -376,6 +398,13 @@ class ConvectionDiffusionOperator:
             y = np.zeros(self.height)
         self.ctx.check(lib().cdm_operator_mult_host(self.h, _ptr(x), _ptr(y), 1 if constrained else 0))
         return y
+
+    def time_kernel(self, x, y, reps=10, constrained=True):
+        """mean device time (ms) of the element kernel alone (CUDA events around each launch)"""
+        ms = C.c_double()
+        self.ctx.check(lib().cdm_operator_time_kernel(self.h, _ptr(x), _ptr(y), reps, 1 if constrained else 0,
+                                                      C.byref(ms)))
+        return ms.value
 
     def AssembleDiagonal(self, d):
         self.ctx.check(lib().cdm_operator_diag(self.h, _ptr(d)))

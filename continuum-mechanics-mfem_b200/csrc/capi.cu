@@ -82,6 +82,8 @@ int cdm_finalize(cdm_ctx *c)
       if (c->red_host) { cudaFreeHost(c->red_host); }
       if (c->ev0) { cudaEventDestroy(c->ev0); }
       if (c->ev1) { cudaEventDestroy(c->ev1); }
+      if (c->evk0) { cudaEventDestroy(c->evk0); }
+      if (c->evk1) { cudaEventDestroy(c->evk1); }
       if (c->own_stream && c->stream) { cudaStreamDestroy(c->stream); }
    }
    delete c;
@@ -366,6 +368,34 @@ int cdm_space_qpt_coords(const cdm_space *sp, double *xyz)
    return CDM_OK;
 }
 
+int cdm_space_halo_peers(const cdm_space *sp, int *npeers)
+{
+   if (!sp || !npeers) { return CDM_EINVAL; }
+   *npeers = (int)sp->peers.size();
+   return CDM_OK;
+}
+
+int cdm_space_halo_peer(const cdm_space *sp, int i, int *rank, int64_t *n_own, int64_t *n_ghost,
+                        int32_t *own_idx, int32_t *ghost_idx)
+{
+   if (!sp || i < 0 || i >= (int)sp->peers.size()) { return CDM_EINVAL; }
+   const cdm_halo_peer &pr = sp->peers[i];
+   if (rank) { *rank = pr.rank; }
+   if (n_own) { *n_own = (int64_t)pr.own_idx.size(); }
+   if (n_ghost) { *n_ghost = (int64_t)pr.ghost_idx.size(); }
+   if (own_idx && !pr.own_idx.empty()) { std::memcpy(own_idx, pr.own_idx.data(), pr.own_idx.size() * sizeof(int32_t)); }
+   if (ghost_idx && !pr.ghost_idx.empty()) { std::memcpy(ghost_idx, pr.ghost_idx.data(), pr.ghost_idx.size() * sizeof(int32_t)); }
+   return CDM_OK;
+}
+
+int cdm_space_dof_global(const cdm_space *sp, int64_t *keys)
+{
+   if (!sp || !keys) { return CDM_EINVAL; }
+   if (sp->dof_global.empty()) { for (int64_t g = 0; g < sp->ndof; g++) { keys[g] = g; } }
+   else { std::memcpy(keys, sp->dof_global.data(), sp->dof_global.size() * sizeof(int64_t)); }
+   return CDM_OK;
+}
+
 int cdm_space_destroy(cdm_space *sp)
 {
    if (!sp) { return CDM_OK; }
@@ -435,7 +465,7 @@ int cdm_operator_create(cdm_space *sp, const cdm_coeff *kappa, const cdm_coeff *
       rc = cdm_k_setup_qdata(op, kappa, vel, conv_alpha, mass);
    } while (0);
    if (rc) { cdm_operator_destroy(op); return rc; }
-   op->kernel_variant = (sp->dim == 3 && sp->p == 3) ? 1 : 0;
+   op->kernel_variant = 0;
    *out = op;
    return CDM_OK;
 }
@@ -562,6 +592,29 @@ int cdm_eliminate_rhs(cdm_op *op, const double *x_dev, double *b_dev)
    if ((rc = cdm_k_axpy(ctx, sp->ntrue, -1.0, op->yL_dev, b_dev))) { return rc; }
    if (op->n_ess > 0) { rc = cdm_k_copy_idx(ctx, op->n_ess, op->ess_dev, x_dev, b_dev); }
    return rc;
+}
+
+int cdm_operator_time_kernel(cdm_op *op, const double *x_dev, double *y_dev, int reps, int constrained, double *mean_ms)
+{
+   if (!op || !x_dev || !y_dev || reps < 1 || !mean_ms) { return CDM_EINVAL; }
+   cdm_ctx *ctx = op->sp->ctx;
+   if (!ctx->evk0) { CDM_CUDA(ctx, cudaEventCreate(&ctx->evk0)); CDM_CUDA(ctx, cudaEventCreate(&ctx->evk1)); }
+   double tot = 0.0;
+   ctx->time_main = true;
+   for (int i = 0; i < reps; i++)
+   {
+      int rc = cdm_k_apply(op, x_dev, y_dev, constrained != 0);
+      if (rc) { ctx->time_main = false; return rc; }
+      cudaError_t e = cudaEventSynchronize(ctx->evk1);
+      if (e != cudaSuccess) { ctx->time_main = false; return cdm_fail(ctx, CDM_ECUDA, cudaGetErrorString(e)); }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1);
+      tot += ms;
+   }
+   ctx->time_main = false;
+   CDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+   *mean_ms = tot / reps;
+   return CDM_OK;
 }
 
 int cdm_operator_get_qdata(const cdm_op *op, double *Ddiff, double *Dconv, double *Dmass)

@@ -26,6 +26,9 @@ struct cdm_ctx
    double *red_host = nullptr;      // pinned, RED_MAXK
    int sm_count = 148;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   // kernel-only timing (cdm_operator_time_kernel)
+   bool time_main = false;
+   cudaEvent_t evk0 = nullptr, evk1 = nullptr;
 };
 
 struct cdm_mesh

@@ -543,6 +543,7 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
    if (atomic) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); }
    else { int rc = ensure_yE(op); if (rc) { return rc; } out = op->yE_dev; }
    const BasisTables bt = make_tables(sp);
+   if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }
    if (sp->dim == 3)
    {
       switch (sp->p)
@@ -559,6 +560,7 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
          default: return cdm_fail(ctx, CDM_EUNSUP, "order must be 1..6");
       }
    }
+   if (ctx->time_main) { cudaEventRecord(ctx->evk1, ctx->stream); }
    ctx->launches++;
    if (!atomic)
    {

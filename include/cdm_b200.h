@@ -110,6 +110,14 @@ int  cdm_space_dof_coords(const cdm_space *space, double *xyz_host);
 /* physical coordinates of the quadrature points (ne x nq x dim): what
    Coefficient::Eval(T, ip) sees (linear_convection_diffusion_2D.cpp:165) */
 int  cdm_space_qpt_coords(const cdm_space *space, double *xyz_host);
+/* shared-dof exchange plan of a partitioned space (ParFiniteElementSpace group
+   communicator): number of neighbour ranks; for neighbour i its rank, the owned dofs
+   it shares (sent by P, summed into by P^T) and the ghost dofs it owns.  Index
+   arrays may be NULL to query the counts.  dof_global: lattice key of each local dof. */
+int  cdm_space_halo_peers(const cdm_space *space, int *npeers);
+int  cdm_space_halo_peer(const cdm_space *space, int i, int *rank, int64_t *n_own, int64_t *n_ghost,
+                         int32_t *own_idx, int32_t *ghost_idx);
+int  cdm_space_dof_global(const cdm_space *space, int64_t *keys);
 int  cdm_space_destroy(cdm_space *space);
 
 /* --------------------------------------------------------------- operator */
@@ -161,6 +169,11 @@ int  cdm_eliminate_rhs(cdm_op *op, const double *x_dev, double *b_dev);
 int  cdm_operator_get_qdata(const cdm_op *op, double *Ddiff, double *Dconv, double *Dmass);
 /* tuning knobs (benchmarks): name in {"scatter" (0 E-vector+gather, 1 atomics), "kernel" (variant id)} */
 int  cdm_operator_set_option(cdm_op *op, const char *name, int value);
+/* measurement hook: run the element kernel of the apply `reps` times on this rank's
+   L-vectors and return its mean device time (CUDA events recorded on the context's
+   stream directly around each launch; no halo, no essential fix-up) */
+int  cdm_operator_time_kernel(cdm_op *op, const double *x_dev, double *y_dev, int reps, int constrained,
+                              double *mean_ms);
 /* number of kernel launches issued by this context so far */
 int64_t cdm_launch_count(const cdm_ctx *ctx);
 
