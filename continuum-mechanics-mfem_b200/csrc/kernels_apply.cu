@@ -537,7 +537,11 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
    const int32_t *gmap = (constrained && op->gather_c_dev) ? op->gather_c_dev : sp->gather_dev;
-   if (sp->dim == 3 && sp->p == 3 && op->kernel_variant >= 1) { return cdm_k_apply_p3(op, gmap, xL, yL); }
+   if (sp->dim == 3 && sp->p == 3 && op->kernel_variant >= 1)
+   {
+      const int rc = cdm_k_apply_p3(op, gmap, xL, yL);
+      if (rc != 1) { return rc; }          // 1: integrator combination not instantiated -> generic kernel
+   }
    const int atomic = op->scatter_mode == 1;
    double *out = yL;
    if (atomic) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); }

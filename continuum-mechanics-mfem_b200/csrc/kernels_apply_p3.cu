@@ -1,4 +1,450 @@
-// placeholder until the bulk-async kernel lands
+// kernels_apply_p3.cu -- the headline kernel: fused 3D apply for orders whose
+// quadrature slab fits one warp (Q1D^2 <= 32: p = 1, 2, 3), written for sm_100a.
+//
+//   y_L += G^T B^T D B G x_L      (Operator::Mult inside the Krylov loop,
+//                                  linear_convection_diffusion_2D.cpp:368-370)
+//
+// Design (see DESIGN.md "apply kernel"):
+//   * persistent grid, one warp owns one element at a time; all exchange between
+//     the lanes of an element goes through warp-private shared memory guarded by
+//     __syncwarp only -- no block barriers in the steady state.
+//   * the quadrature data (10 doubles per point, the dominant HBM stream) is
+//     pulled by the bulk-async copy engine (cp.async.bulk -> SASS UBLKCP) into a
+//     per-warp ring of Q1D z-slabs, each guarded by an mbarrier; the slab of the
+//     NEXT element is requested as soon as the current one has been consumed, so
+//     ~10 KB per warp are always in flight regardless of occupancy.
+//   * gradients are taken with the collocation derivative matrix at the Gauss
+//     points (u -> B u, then Dq along each direction), which needs one
+//     interpolation instead of four; G = Dq B holds exactly because Q1D > p.
+//   * x is gathered with the (essential-dof-encoding) int32 map one element ahead;
+//     results are scattered with fp64 red.add (or stored as an E-vector).
 #include "cdm_internal.hpp"
-int cdm_k_apply_p3(cdm_op *op, const int32_t *, const double *, double *)
-{ return cdm_fail(op->sp->ctx, CDM_EUNSUP, "p3 kernel not built"); }
+#include "kernels_common.cuh"
+
+namespace
+{
+struct WarpTables
+{
+   double B[CDM_MAX_Q1D * CDM_MAX_D1D];    // B[q*D + d]
+   double Dq[CDM_MAX_Q1D * CDM_MAX_Q1D];   // collocation derivative, Dq[i*Q + k] = l_k'(x_i) on the Gauss points
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (TMA engine)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void red_add_f64(double *addr, double v)
+{
+   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+// per-lane coefficient table in shared memory: row r, lane l -> sCo[r*32 + l]
+// rows: [0,D) bx = B[qx][d] ; [D,2D) by = B[qy][d] ; [2D,2D+Q) B[q][dyA] ; [2D+Q,2D+2Q) B[q][dxB]
+template <int D, int Q> struct CoefRows { static constexpr int BX = 0, BY = D, CY = 2 * D, CX = 2 * D + Q, N = 2 * D + 2 * Q; };
+
+template <int D, int Q, int NW, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
+__global__ void __launch_bounds__(NW * 32)
+k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict__ gmap,
+               const double *__restrict__ x, const double *__restrict__ Dg, const int slab,
+               double *__restrict__ y)
+{
+   constexpr int Q2 = Q * Q, ND = D * D * D, QP = Q + 1;
+   constexpr int NPL = (ND + 31) / 32;                       // gathered values per lane
+   constexpr int SU = Q * Q * QP;                            // u at quadrature points, rows padded
+   constexpr int SF = 2 * 2 * Q * QP;                        // double-buffered fx, fy slabs
+   using CR = CoefRows<D, Q>;
+   static_assert(Q2 <= 32 && ND <= 64 && D * D * QP <= SF && D * Q * QP <= SU, "tile does not fit one warp");
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+   const int warp_doubles = Q * slab + ND + SU + SF;
+   double *sCo = reinterpret_cast<double *>(smraw);                          // CR::N * 32
+   double *wbase = sCo + CR::N * 32 + wib * warp_doubles;
+   uint64_t *bars = reinterpret_cast<uint64_t *>(sCo + CR::N * 32 + NW * warp_doubles) + wib * Q;
+   double *ring = wbase, *sX = ring + Q * slab, *sU = sX + ND, *sF = sU + SU;
+   const bool act = lane < Q2;
+   const int qx = act ? lane % Q : 0, qy = act ? lane / Q : 0;
+   const bool actA = lane < Q * D;                          // (qx, dy) lanes of the two-stage x/y contractions
+   const int dxB = lane % D, dyB = (lane / D) % D, dzB = lane / (D * D);    // output mapping: pos = lane + 32 j
+
+   // ---- one-time setup
+   if (wib == 0)
+   {
+      for (int d = 0; d < D; d++)
+      {
+         sCo[(CR::BX + d) * 32 + lane] = tb.B[qx * D + d];
+         sCo[(CR::BY + d) * 32 + lane] = tb.B[qy * D + d];
+      }
+      for (int q = 0; q < Q; q++)
+      {
+         sCo[(CR::CY + q) * 32 + lane] = tb.B[q * D + (qy < D ? qy : 0)];
+         sCo[(CR::CX + q) * 32 + lane] = tb.B[q * D + dxB];
+      }
+   }
+   if (lane == 0)
+   {
+      for (int q = 0; q < Q; q++) { mbar_init(&bars[q], 1); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncthreads();
+   double dqx_row[Q], dqy_row[Q], dqx_col[Q], dqy_col[Q];
+   #pragma unroll
+   for (int k = 0; k < Q; k++)
+   {
+      dqx_row[k] = tb.Dq[qx * Q + k]; dqy_row[k] = tb.Dq[qy * Q + k];
+      dqx_col[k] = tb.Dq[k * Q + qx]; dqy_col[k] = tb.Dq[k * Q + qy];
+   }
+
+   const int64_t gw = (int64_t)blockIdx.x * NW + wib, tw = (int64_t)gridDim.x * NW;
+   const uint32_t slab_bytes = (uint32_t)slab * 8u;
+   // prologue: request the first element's slabs and gather its x values
+   int32_t pg[NPL];
+   double px[NPL];
+   if (gw < ne)
+   {
+      if (lane == 0)
+      {
+         #pragma unroll
+         for (int q = 0; q < Q; q++)
+         {
+            mbar_expect_tx(&bars[q], slab_bytes);
+            bulk_g2s(ring + q * slab, Dg + (gw * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+         }
+      }
+      #pragma unroll
+      for (int j = 0; j < NPL; j++)
+      {
+         const int pos = lane + 32 * j;
+         pg[j] = (pos < ND) ? gmap[gw * ND + pos] : -1;
+         px[j] = (pg[j] >= 0) ? x[pg[j]] : 0.0;
+      }
+   }
+
+   uint32_t parity = 0;
+   for (int64_t e = gw; e < ne; e += tw, parity ^= 1u)
+   {
+      const int64_t en = e + tw;
+      const bool more = en < ne;
+      int32_t g[NPL];
+      // ---- S0: x tile to shared memory; prefetch the next element's gather
+      #pragma unroll
+      for (int j = 0; j < NPL; j++)
+      {
+         g[j] = pg[j];
+         if (lane + 32 * j < ND) { sX[lane + 32 * j] = px[j]; }
+      }
+      if (more)
+      {
+         #pragma unroll
+         for (int j = 0; j < NPL; j++)
+         {
+            const int pos = lane + 32 * j;
+            pg[j] = (pos < ND) ? __ldg(gmap + en * ND + pos) : -1;
+         }
+         #pragma unroll
+         for (int j = 0; j < NPL; j++) { px[j] = (pg[j] >= 0) ? __ldg(x + pg[j]) : 0.0; }
+      }
+      __syncwarp();
+      // ---- S1a: contract x: lane (qx, dy)
+      double *sT = sU;                                       // [dz][dy][qx] rows padded to QP
+      if (actA)
+      {
+         double bx[D];
+         #pragma unroll
+         for (int d = 0; d < D; d++) { bx[d] = sCo[(CR::BX + d) * 32 + lane]; }
+         #pragma unroll
+         for (int dz = 0; dz < D; dz++)
+         {
+            double t = 0.0;
+            #pragma unroll
+            for (int dx = 0; dx < D; dx++) { t += bx[dx] * sX[dx + D * (qy + D * dz)]; }
+            sT[(dz * D + qy) * QP + qx] = t;
+         }
+      }
+      __syncwarp();
+      // ---- S1b: contract y: lane (qx, qy); S2: contract z in registers
+      double u[Q];
+      {
+         double by[D], v[D];
+         #pragma unroll
+         for (int d = 0; d < D; d++) { by[d] = sCo[(CR::BY + d) * 32 + lane]; }
+         #pragma unroll
+         for (int dz = 0; dz < D; dz++)
+         {
+            double t = 0.0;
+            #pragma unroll
+            for (int dy = 0; dy < D; dy++) { t += by[dy] * sT[(dz * D + dy) * QP + qx]; }
+            v[dz] = t;
+         }
+         #pragma unroll
+         for (int qz = 0; qz < Q; qz++)
+         {
+            double t = 0.0;
+            #pragma unroll
+            for (int dz = 0; dz < D; dz++) { t += tb.B[qz * D + dz] * v[dz]; }
+            u[qz] = t;
+         }
+      }
+      __syncwarp();                                          // sT (aliases sU) fully consumed
+      if (act)
+      {
+         #pragma unroll
+         for (int qz = 0; qz < Q; qz++) { sU[(qz * Q + qy) * QP + qx] = u[qz]; }
+      }
+      __syncwarp();
+      // ---- S4: slab loop: gradients, point-wise D, transposed gradients
+      double out[Q];
+      #pragma unroll
+      for (int qz = 0; qz < Q; qz++) { out[qz] = 0.0; }
+      #pragma unroll
+      for (int qz = 0; qz < Q; qz++)
+      {
+         double gx = 0.0, gy = 0.0, gz = 0.0;
+         if (DIFF || CONV)
+         {
+            #pragma unroll
+            for (int k = 0; k < Q; k++)
+            {
+               gx += dqx_row[k] * sU[(qz * Q + qy) * QP + k];
+               gy += dqy_row[k] * sU[(qz * Q + k) * QP + qx];
+               gz += tb.Dq[qz * Q + k] * u[k];
+            }
+         }
+         mbar_wait(&bars[qz], parity);
+         const double *dp = ring + qz * slab + (act ? lane : 0);
+         double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;
+         int c = 0;
+         if (DIFF)
+         {
+            const double d0 = dp[0], d1 = dp[Q2], d2 = dp[2 * Q2], d3 = dp[3 * Q2], d4 = dp[4 * Q2], d5 = dp[5 * Q2];
+            fx = d0 * gx + d1 * gy + d2 * gz;
+            fy = d1 * gx + d3 * gy + d4 * gz;
+            fz = d2 * gx + d4 * gy + d5 * gz;
+            c = 6;
+         }
+         if (CONV) { s = dp[c * Q2] * gx + dp[(c + 1) * Q2] * gy + dp[(c + 2) * Q2] * gz; c += 3; }
+         if (MASS) { s += dp[c * Q2] * u[qz]; }
+         double r = s;
+         if (DIFF)
+         {
+            double *sFx = sF + (qz & 1) * (2 * Q * QP), *sFy = sFx + Q * QP;
+            if (act) { sFx[qy * QP + qx] = fx; sFy[qy * QP + qx] = fy; }
+            __syncwarp();
+            // slab qz of this element is consumed by every lane: request it for the next element
+            if (lane == 0 && more)
+            {
+               mbar_expect_tx(&bars[qz], slab_bytes);
+               bulk_g2s(ring + qz * slab, Dg + (en * Q + qz) * (int64_t)slab, slab_bytes, &bars[qz]);
+            }
+            #pragma unroll
+            for (int k = 0; k < Q; k++)
+            {
+               r += dqx_col[k] * sFx[qy * QP + k] + dqy_col[k] * sFy[k * QP + qx];
+               out[k] += tb.Dq[qz * Q + k] * fz;
+            }
+         }
+         else
+         {
+            __syncwarp();
+            if (lane == 0 && more)
+            {
+               mbar_expect_tx(&bars[qz], slab_bytes);
+               bulk_g2s(ring + qz * slab, Dg + (en * Q + qz) * (int64_t)slab, slab_bytes, &bars[qz]);
+            }
+         }
+         out[qz] += r;
+      }
+      // ---- S5: transposed interpolation z (registers), y and x (shared memory)
+      double *sW = sU;                                       // [dz][qy][qx]
+      {
+         double w[D];
+         #pragma unroll
+         for (int dz = 0; dz < D; dz++)
+         {
+            double t = 0.0;
+            #pragma unroll
+            for (int qz = 0; qz < Q; qz++) { t += tb.B[qz * D + dz] * out[qz]; }
+            w[dz] = t;
+         }
+         __syncwarp();                                       // all sU reads of the slab loop are done
+         if (act)
+         {
+            #pragma unroll
+            for (int dz = 0; dz < D; dz++) { sW[(dz * Q + qy) * QP + qx] = w[dz]; }
+         }
+      }
+      __syncwarp();
+      double *sA = sF;                                       // [dz][dy][qx]
+      if (actA)
+      {
+         double cy[Q];
+         #pragma unroll
+         for (int q = 0; q < Q; q++) { cy[q] = sCo[(CR::CY + q) * 32 + lane]; }
+         #pragma unroll
+         for (int dz = 0; dz < D; dz++)
+         {
+            double t = 0.0;
+            #pragma unroll
+            for (int q = 0; q < Q; q++) { t += cy[q] * sW[(dz * Q + q) * QP + qx]; }
+            sA[(dz * D + qy) * QP + qx] = t;
+         }
+      }
+      __syncwarp();
+      {
+         double cx[Q];
+         #pragma unroll
+         for (int q = 0; q < Q; q++) { cx[q] = sCo[(CR::CX + q) * 32 + lane]; }
+         #pragma unroll
+         for (int j = 0; j < NPL; j++)
+         {
+            const int pos = lane + 32 * j;
+            if (pos < ND)
+            {
+               const int dz = dzB + j * (32 / (D * D));
+               double t = 0.0;
+               #pragma unroll
+               for (int q = 0; q < Q; q++) { t += cx[q] * sA[(dz * D + dyB) * QP + q]; }
+               if (ATOMIC) { if (g[j] >= 0) { red_add_f64(y + g[j], t); } }
+               else { y[e * ND + pos] = t; }
+            }
+         }
+      }
+      __syncwarp();                                          // sA / sX reuse by the next element
+   }
+}
+
+// collocation derivative matrix on the Gauss points: Dq[i][k] = l_k'(x_i)
+void collocation_matrix(int q1d, const double *xq, double *Dq)
+{
+   std::vector<double> bw(q1d);
+   for (int j = 0; j < q1d; j++)
+   {
+      double c = 1.0;
+      for (int k = 0; k < q1d; k++) if (k != j) { c *= xq[j] - xq[k]; }
+      bw[j] = 1.0 / c;
+   }
+   for (int i = 0; i < q1d; i++)
+   {
+      double diag = 0.0;
+      for (int k = 0; k < q1d; k++)
+      {
+         if (k == i) { continue; }
+         Dq[i * q1d + k] = (bw[k] / bw[i]) / (xq[i] - xq[k]);
+         diag -= Dq[i * q1d + k];
+      }
+      Dq[i * q1d + i] = diag;
+   }
+}
+
+template <int D, int Q, int NW, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
+int launch(cdm_op *op, const WarpTables &tb, const int32_t *gmap, const double *xL, double *out)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   auto kern = k_apply3d_warp<D, Q, NW, DIFF, CONV, MASS, ATOMIC>;
+   constexpr int QP = Q + 1, ND = D * D * D;
+   const int warp_doubles = Q * op->slab + ND + Q * Q * QP + 2 * 2 * Q * QP;
+   const size_t smem = (size_t)(CoefRows<D, Q>::N * 32 + NW * warp_doubles) * sizeof(double) + (size_t)NW * Q * sizeof(uint64_t);
+   static size_t configured = 0;
+   static int blocks_per_sm = 0;
+   if (configured != smem)
+   {
+      CDM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CDM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NW * 32, smem));
+      if (blocks_per_sm < 1) { return cdm_fail(ctx, CDM_ECUDA, "k_apply3d_warp does not fit on an SM"); }
+      configured = smem;
+   }
+   int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
+   const int64_t need = (sp->ne + NW - 1) / NW;
+   if (grid > need) { grid = need; }
+   if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }
+   kern<<<(unsigned)grid, NW * 32, smem, ctx->stream>>>(tb, sp->ne, gmap, xL, op->D_dev, op->slab, out);
+   if (ctx->time_main) { cudaEventRecord(ctx->evk1, ctx->stream); }
+   ctx->launches++;
+   CDM_CUDA(ctx, cudaGetLastError());
+   return CDM_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_restrict_transpose_p3(int64_t ndof, const int32_t *__restrict__ offsets, const int32_t *__restrict__ indices,
+                        const double *__restrict__ yE, double *__restrict__ yL)
+{
+   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (g >= ndof) { return; }
+   double s = 0.0;
+   for (int32_t j = offsets[g]; j < offsets[g + 1]; j++) { s += yE[indices[j]]; }
+   yL[g] = s;
+}
+}  // namespace
+
+#define NWARPS 4
+#define DISPATCH_FLAGS(D_, Q_)                                                                            \
+   if (op->has_diff && op->has_conv && op->has_mass)                                                      \
+      rc = atomic ? launch<D_, Q_, NWARPS, true, true, true, true>(op, tb, gmap, xL, out)                 \
+                  : launch<D_, Q_, NWARPS, true, true, true, false>(op, tb, gmap, xL, out);               \
+   else if (op->has_diff && !op->has_conv && op->has_mass)                                                \
+      rc = atomic ? launch<D_, Q_, NWARPS, true, false, true, true>(op, tb, gmap, xL, out)                \
+                  : launch<D_, Q_, NWARPS, true, false, true, false>(op, tb, gmap, xL, out);              \
+   else if (!op->has_diff && !op->has_conv && op->has_mass)                                               \
+      rc = atomic ? launch<D_, Q_, NWARPS, false, false, true, true>(op, tb, gmap, xL, out)               \
+                  : launch<D_, Q_, NWARPS, false, false, true, false>(op, tb, gmap, xL, out);             \
+   else if (op->has_diff && !op->has_conv && !op->has_mass)                                               \
+      rc = atomic ? launch<D_, Q_, NWARPS, true, false, false, true>(op, tb, gmap, xL, out)               \
+                  : launch<D_, Q_, NWARPS, true, false, false, false>(op, tb, gmap, xL, out);             \
+   else { rc = 1; }
+
+// returns 1 when this operator is not covered (caller falls back to the generic kernel)
+int cdm_k_apply_p3(cdm_op *op, const int32_t *gmap, const double *xL, double *yL)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   if (sp->dim != 3 || sp->p != 3) { return 1; }
+   if (!((op->has_diff && op->has_mass) || (!op->has_conv && (op->has_diff || op->has_mass)))) { return 1; }
+   if (op->has_conv && !(op->has_diff && op->has_mass)) { return 1; }
+   WarpTables tb;
+   memset(&tb, 0, sizeof(tb));
+   for (int i = 0; i < sp->q1d * sp->d1d; i++) { tb.B[i] = sp->B[i]; }
+   collocation_matrix(sp->q1d, sp->qx.data(), tb.Dq);
+   const bool atomic = op->scatter_mode == 1;
+   double *out = yL;
+   if (atomic) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); }
+   else
+   {
+      if (!op->yE_dev) { CDM_CUDA(ctx, cudaMalloc(&op->yE_dev, sizeof(double) * (size_t)sp->ne * sp->nd)); }
+      out = op->yE_dev;
+   }
+   int rc = 0;
+   DISPATCH_FLAGS(4, 5)
+   if (rc) { return rc; }
+   if (!atomic)
+   {
+      const unsigned nb = (unsigned)((sp->ndof + 255) / 256);
+      k_restrict_transpose_p3<<<nb, 256, 0, ctx->stream>>>(sp->ndof, sp->offsets_dev, sp->indices_dev, op->yE_dev, yL);
+      ctx->launches++;
+      CDM_CUDA(ctx, cudaGetLastError());
+   }
+   return CDM_OK;
+}
