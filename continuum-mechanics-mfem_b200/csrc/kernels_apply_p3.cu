@@ -62,54 +62,43 @@ __device__ __forceinline__ void red_add_f64(double *addr, double v)
    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
 
-// per-lane coefficient table in shared memory: row r, lane l -> sCo[r*32 + l]
-// rows: [0,D) bx = B[qx][d] ; [D,2D) by = B[qy][d] ; [2D,2D+Q) B[q][dyA] ; [2D+Q,2D+2Q) B[q][dxB]
-template <int D, int Q> struct CoefRows { static constexpr int BX = 0, BY = D, CY = 2 * D, CX = 2 * D + Q, N = 2 * D + 2 * Q; };
-
+// Lane roles (D1D = 4, Q1D = 5):
+//   L1 lanes (dy,dz)  l < 16 : own one x-line of nodal values (gather / scatter, x contraction)
+//   L2 lanes (qx,dz)  l < 20 : y contraction                   qx = l>>2, dz = l&3
+//   L3 lanes (qx,qy)  l < 25 : z contraction and the quadrature-point work   qx = l%5, qy = l/5
+// In every interpolation stage the coefficient index is a compile-time constant, so
+// B comes from the constant bank (kernel parameter) and costs no registers or loads.
+// Exchange layouts (doubles), chosen so that both the writer and the reader of each
+// buffer hit 16 distinct 8-byte bank pairs per half warp:
+//   P(qx,dy,dz) = qx + 5 dy + 20 dz        (L1 <-> L2)
+//   R(qx,qy,dz) = qx + 5 qy + 28 dz        (L2 <-> L3)
 template <int D, int Q, int NW, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
 __global__ void __launch_bounds__(NW * 32)
 k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict__ gmap,
                const double *__restrict__ x, const double *__restrict__ Dg, const int slab,
                double *__restrict__ y)
 {
-   constexpr int Q2 = Q * Q, ND = D * D * D, QP = Q + 1;
-   constexpr int NPL = (ND + 31) / 32;                       // gathered values per lane
-   constexpr int SU = Q * Q * QP;                            // u at quadrature points, rows padded
-   constexpr int SF = 2 * 2 * Q * QP;                        // double-buffered fx, fy slabs
-   using CR = CoefRows<D, Q>;
-   static_assert(Q2 <= 32 && ND <= 64 && D * D * QP <= SF && D * Q * QP <= SU, "tile does not fit one warp");
+   static_assert(D == 4 && Q == 5, "lane roles and exchange layouts are written for order 3");
+   constexpr int Q2 = Q * Q, ND = D * D * D;
+   constexpr int SU = Q * Q2;                                // u at the quadrature points [qz][qy][qx]
+   constexpr int SF = 2 * 2 * Q2;                            // double-buffered fx, fy slabs; aliases the P buffer
+   constexpr int SR = 28 * (D - 1) + Q2 + 3;                 // R buffer (112)
    extern __shared__ __align__(128) unsigned char smraw[];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-   const int warp_doubles = Q * slab + ND + SU + SF;
-   double *sCo = reinterpret_cast<double *>(smraw);                          // CR::N * 32
-   double *wbase = sCo + CR::N * 32 + wib * warp_doubles;
-   uint64_t *bars = reinterpret_cast<uint64_t *>(sCo + CR::N * 32 + NW * warp_doubles) + wib * Q;
-   double *ring = wbase, *sX = ring + Q * slab, *sU = sX + ND, *sF = sU + SU;
-   const bool act = lane < Q2;
-   const int qx = act ? lane % Q : 0, qy = act ? lane / Q : 0;
-   const bool actA = lane < Q * D;                          // (qx, dy) lanes of the two-stage x/y contractions
-   const int dxB = lane % D, dyB = (lane / D) % D, dzB = lane / (D * D);    // output mapping: pos = lane + 32 j
+   const int warp_doubles = (Q * slab + SU + SF + SR + 15) & ~15;      // keeps every ring slab 16-byte aligned
+   double *wbase = reinterpret_cast<double *>(smraw) + wib * warp_doubles;
+   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smraw) + NW * warp_doubles) + wib * Q;
+   double *ring = wbase, *sU = ring + Q * slab, *sF = sU + SU, *sP = sF, *sR = sF + SF;
+   const bool l1 = lane < D * D, l2 = lane < Q * D, l3 = lane < Q2;
+   const int qx = l3 ? lane % Q : 0, qy = l3 ? lane / Q : 0;             // L3 role
+   const int qx2 = l2 ? (lane >> 2) : 0, dz2 = lane & 3;                 // L2 role
 
-   // ---- one-time setup
-   if (wib == 0)
-   {
-      for (int d = 0; d < D; d++)
-      {
-         sCo[(CR::BX + d) * 32 + lane] = tb.B[qx * D + d];
-         sCo[(CR::BY + d) * 32 + lane] = tb.B[qy * D + d];
-      }
-      for (int q = 0; q < Q; q++)
-      {
-         sCo[(CR::CY + q) * 32 + lane] = tb.B[q * D + (qy < D ? qy : 0)];
-         sCo[(CR::CX + q) * 32 + lane] = tb.B[q * D + dxB];
-      }
-   }
    if (lane == 0)
    {
       for (int q = 0; q < Q; q++) { mbar_init(&bars[q], 1); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
-   __syncthreads();
+   __syncwarp();
    double dqx_row[Q], dqy_row[Q], dqx_col[Q], dqy_col[Q];
    #pragma unroll
    for (int k = 0; k < Q; k++)
@@ -120,9 +109,9 @@ k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict_
 
    const int64_t gw = (int64_t)blockIdx.x * NW + wib, tw = (int64_t)gridDim.x * NW;
    const uint32_t slab_bytes = (uint32_t)slab * 8u;
-   // prologue: request the first element's slabs and gather its x values
-   int32_t pg[NPL];
-   double px[NPL];
+   // prologue: request the first element's slabs and gather its x-lines
+   int4 pg = make_int4(-1, -1, -1, -1);
+   double px0 = 0.0, px1 = 0.0, px2 = 0.0, px3 = 0.0;
    if (gw < ne)
    {
       if (lane == 0)
@@ -134,12 +123,11 @@ k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict_
             bulk_g2s(ring + q * slab, Dg + (gw * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
          }
       }
-      #pragma unroll
-      for (int j = 0; j < NPL; j++)
+      if (l1)
       {
-         const int pos = lane + 32 * j;
-         pg[j] = (pos < ND) ? gmap[gw * ND + pos] : -1;
-         px[j] = (pg[j] >= 0) ? x[pg[j]] : 0.0;
+         pg = __ldg(reinterpret_cast<const int4 *>(gmap + gw * ND) + lane);
+         px0 = (pg.x >= 0) ? __ldg(x + pg.x) : 0.0; px1 = (pg.y >= 0) ? __ldg(x + pg.y) : 0.0;
+         px2 = (pg.z >= 0) ? __ldg(x + pg.z) : 0.0; px3 = (pg.w >= 0) ? __ldg(x + pg.w) : 0.0;
       }
    }
 
@@ -148,74 +136,56 @@ k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict_
    {
       const int64_t en = e + tw;
       const bool more = en < ne;
-      int32_t g[NPL];
-      // ---- S0: x tile to shared memory; prefetch the next element's gather
-      #pragma unroll
-      for (int j = 0; j < NPL; j++)
-      {
-         g[j] = pg[j];
-         if (lane + 32 * j < ND) { sX[lane + 32 * j] = px[j]; }
-      }
-      if (more)
+      const int4 g = pg;
+      // ---- F1 (L1 lanes): x contraction of the own x-line, constant-bank coefficients
+      if (l1)
       {
          #pragma unroll
-         for (int j = 0; j < NPL; j++)
+         for (int q = 0; q < Q; q++)
          {
-            const int pos = lane + 32 * j;
-            pg[j] = (pos < ND) ? __ldg(gmap + en * ND + pos) : -1;
+            sP[q + Q * lane] = tb.B[q * D + 0] * px0 + tb.B[q * D + 1] * px1 + tb.B[q * D + 2] * px2 + tb.B[q * D + 3] * px3;
          }
-         #pragma unroll
-         for (int j = 0; j < NPL; j++) { px[j] = (pg[j] >= 0) ? __ldg(x + pg[j]) : 0.0; }
+      }
+      // prefetch the next element's gather (consumed one element later)
+      if (more && l1)
+      {
+         pg = __ldg(reinterpret_cast<const int4 *>(gmap + en * ND) + lane);
+         px0 = (pg.x >= 0) ? __ldg(x + pg.x) : 0.0; px1 = (pg.y >= 0) ? __ldg(x + pg.y) : 0.0;
+         px2 = (pg.z >= 0) ? __ldg(x + pg.z) : 0.0; px3 = (pg.w >= 0) ? __ldg(x + pg.w) : 0.0;
       }
       __syncwarp();
-      // ---- S1a: contract x: lane (qx, dy)
-      double *sT = sU;                                       // [dz][dy][qx] rows padded to QP
-      if (actA)
+      // ---- F2 (L2 lanes): y contraction
+      if (l2)
       {
-         double bx[D];
+         double t[D];
          #pragma unroll
-         for (int d = 0; d < D; d++) { bx[d] = sCo[(CR::BX + d) * 32 + lane]; }
+         for (int dy = 0; dy < D; dy++) { t[dy] = sP[qx2 + Q * dy + Q * D * dz2]; }
          #pragma unroll
-         for (int dz = 0; dz < D; dz++)
+         for (int q = 0; q < Q; q++)
          {
-            double t = 0.0;
-            #pragma unroll
-            for (int dx = 0; dx < D; dx++) { t += bx[dx] * sX[dx + D * (qy + D * dz)]; }
-            sT[(dz * D + qy) * QP + qx] = t;
+            sR[qx2 + Q * q + 28 * dz2] = tb.B[q * D + 0] * t[0] + tb.B[q * D + 1] * t[1] + tb.B[q * D + 2] * t[2] + tb.B[q * D + 3] * t[3];
          }
       }
       __syncwarp();
-      // ---- S1b: contract y: lane (qx, qy); S2: contract z in registers
+      // ---- F3 (L3 lanes): z contraction in registers, publish u
       double u[Q];
       {
-         double by[D], v[D];
+         double v[D];
          #pragma unroll
-         for (int d = 0; d < D; d++) { by[d] = sCo[(CR::BY + d) * 32 + lane]; }
-         #pragma unroll
-         for (int dz = 0; dz < D; dz++)
-         {
-            double t = 0.0;
-            #pragma unroll
-            for (int dy = 0; dy < D; dy++) { t += by[dy] * sT[(dz * D + dy) * QP + qx]; }
-            v[dz] = t;
-         }
+         for (int dz = 0; dz < D; dz++) { v[dz] = sR[lane % Q2 + 28 * dz]; }
          #pragma unroll
          for (int qz = 0; qz < Q; qz++)
          {
-            double t = 0.0;
-            #pragma unroll
-            for (int dz = 0; dz < D; dz++) { t += tb.B[qz * D + dz] * v[dz]; }
-            u[qz] = t;
+            u[qz] = tb.B[qz * D + 0] * v[0] + tb.B[qz * D + 1] * v[1] + tb.B[qz * D + 2] * v[2] + tb.B[qz * D + 3] * v[3];
          }
       }
-      __syncwarp();                                          // sT (aliases sU) fully consumed
-      if (act)
+      if (l3)
       {
          #pragma unroll
-         for (int qz = 0; qz < Q; qz++) { sU[(qz * Q + qy) * QP + qx] = u[qz]; }
+         for (int qz = 0; qz < Q; qz++) { sU[qz * Q2 + lane] = u[qz]; }
       }
       __syncwarp();
-      // ---- S4: slab loop: gradients, point-wise D, transposed gradients
+      // ---- slab loop: gradients, point-wise D, transposed gradients
       double out[Q];
       #pragma unroll
       for (int qz = 0; qz < Q; qz++) { out[qz] = 0.0; }
@@ -228,13 +198,13 @@ k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict_
             #pragma unroll
             for (int k = 0; k < Q; k++)
             {
-               gx += dqx_row[k] * sU[(qz * Q + qy) * QP + k];
-               gy += dqy_row[k] * sU[(qz * Q + k) * QP + qx];
+               gx += dqx_row[k] * sU[qz * Q2 + qy * Q + k];
+               gy += dqy_row[k] * sU[qz * Q2 + k * Q + qx];
                gz += tb.Dq[qz * Q + k] * u[k];
             }
          }
          mbar_wait(&bars[qz], parity);
-         const double *dp = ring + qz * slab + (act ? lane : 0);
+         const double *dp = ring + qz * slab + (l3 ? lane : 0);
          double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;
          int c = 0;
          if (DIFF)
@@ -250,89 +220,86 @@ k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict_
          double r = s;
          if (DIFF)
          {
-            double *sFx = sF + (qz & 1) * (2 * Q * QP), *sFy = sFx + Q * QP;
-            if (act) { sFx[qy * QP + qx] = fx; sFy[qy * QP + qx] = fy; }
-            __syncwarp();
-            // slab qz of this element is consumed by every lane: request it for the next element
-            if (lane == 0 && more)
-            {
-               mbar_expect_tx(&bars[qz], slab_bytes);
-               bulk_g2s(ring + qz * slab, Dg + (en * Q + qz) * (int64_t)slab, slab_bytes, &bars[qz]);
-            }
+            double *sFx = sF + (qz & 1) * (2 * Q2), *sFy = sFx + Q2;
+            if (l3) { sFx[lane] = fx; sFy[lane] = fy; }
+         }
+         __syncwarp();
+         // slab qz of this element is consumed by every lane: request it for the next element
+         if (lane == 0 && more)
+         {
+            mbar_expect_tx(&bars[qz], slab_bytes);
+            bulk_g2s(ring + qz * slab, Dg + (en * Q + qz) * (int64_t)slab, slab_bytes, &bars[qz]);
+         }
+         if (DIFF)
+         {
+            const double *sFx = sF + (qz & 1) * (2 * Q2), *sFy = sFx + Q2;
             #pragma unroll
             for (int k = 0; k < Q; k++)
             {
-               r += dqx_col[k] * sFx[qy * QP + k] + dqy_col[k] * sFy[k * QP + qx];
+               r += dqx_col[k] * sFx[qy * Q + k] + dqy_col[k] * sFy[k * Q + qx];
                out[k] += tb.Dq[qz * Q + k] * fz;
-            }
-         }
-         else
-         {
-            __syncwarp();
-            if (lane == 0 && more)
-            {
-               mbar_expect_tx(&bars[qz], slab_bytes);
-               bulk_g2s(ring + qz * slab, Dg + (en * Q + qz) * (int64_t)slab, slab_bytes, &bars[qz]);
             }
          }
          out[qz] += r;
       }
-      // ---- S5: transposed interpolation z (registers), y and x (shared memory)
-      double *sW = sU;                                       // [dz][qy][qx]
+      // ---- B1 (L3 lanes): transposed z contraction in registers, publish w(qx,qy,dz)
+      if (l3)
       {
-         double w[D];
          #pragma unroll
          for (int dz = 0; dz < D; dz++)
          {
             double t = 0.0;
             #pragma unroll
             for (int qz = 0; qz < Q; qz++) { t += tb.B[qz * D + dz] * out[qz]; }
-            w[dz] = t;
-         }
-         __syncwarp();                                       // all sU reads of the slab loop are done
-         if (act)
-         {
-            #pragma unroll
-            for (int dz = 0; dz < D; dz++) { sW[(dz * Q + qy) * QP + qx] = w[dz]; }
+            sR[lane + 28 * dz] = t;
          }
       }
       __syncwarp();
-      double *sA = sF;                                       // [dz][dy][qx]
-      if (actA)
+      // ---- B2 (L2 lanes): transposed y contraction
+      if (l2)
       {
-         double cy[Q];
+         double t[Q];
          #pragma unroll
-         for (int q = 0; q < Q; q++) { cy[q] = sCo[(CR::CY + q) * 32 + lane]; }
+         for (int q = 0; q < Q; q++) { t[q] = sR[qx2 + Q * q + 28 * dz2]; }
          #pragma unroll
-         for (int dz = 0; dz < D; dz++)
+         for (int dy = 0; dy < D; dy++)
          {
-            double t = 0.0;
+            double a = 0.0;
             #pragma unroll
-            for (int q = 0; q < Q; q++) { t += cy[q] * sW[(dz * Q + q) * QP + qx]; }
-            sA[(dz * D + qy) * QP + qx] = t;
+            for (int q = 0; q < Q; q++) { a += tb.B[q * D + dy] * t[q]; }
+            sP[qx2 + Q * dy + Q * D * dz2] = a;
          }
       }
       __syncwarp();
+      // ---- B3 (L1 lanes): transposed x contraction of the own x-line, scatter
+      if (l1)
       {
-         double cx[Q];
+         double t[Q], yv[D];
          #pragma unroll
-         for (int q = 0; q < Q; q++) { cx[q] = sCo[(CR::CX + q) * 32 + lane]; }
+         for (int q = 0; q < Q; q++) { t[q] = sP[q + Q * lane]; }
          #pragma unroll
-         for (int j = 0; j < NPL; j++)
+         for (int dx = 0; dx < D; dx++)
          {
-            const int pos = lane + 32 * j;
-            if (pos < ND)
-            {
-               const int dz = dzB + j * (32 / (D * D));
-               double t = 0.0;
-               #pragma unroll
-               for (int q = 0; q < Q; q++) { t += cx[q] * sA[(dz * D + dyB) * QP + q]; }
-               if (ATOMIC) { if (g[j] >= 0) { red_add_f64(y + g[j], t); } }
-               else { y[e * ND + pos] = t; }
-            }
+            double a = 0.0;
+            #pragma unroll
+            for (int q = 0; q < Q; q++) { a += tb.B[q * D + dx] * t[q]; }
+            yv[dx] = a;
+         }
+         if (ATOMIC)
+         {
+            if (g.x >= 0) { red_add_f64(y + g.x, yv[0]); }
+            if (g.y >= 0) { red_add_f64(y + g.y, yv[1]); }
+            if (g.z >= 0) { red_add_f64(y + g.z, yv[2]); }
+            if (g.w >= 0) { red_add_f64(y + g.w, yv[3]); }
+         }
+         else
+         {
+            double2 *dst = reinterpret_cast<double2 *>(y + e * ND + D * lane);
+            dst[0] = make_double2(yv[0], yv[1]);
+            dst[1] = make_double2(yv[2], yv[3]);
          }
       }
-      __syncwarp();                                          // sA / sX reuse by the next element
+      __syncwarp();                                          // sP / sR reuse by the next element
    }
 }
 
@@ -365,9 +332,8 @@ int launch(cdm_op *op, const WarpTables &tb, const int32_t *gmap, const double *
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
    auto kern = k_apply3d_warp<D, Q, NW, DIFF, CONV, MASS, ATOMIC>;
-   constexpr int QP = Q + 1, ND = D * D * D;
-   const int warp_doubles = Q * op->slab + ND + Q * Q * QP + 2 * 2 * Q * QP;
-   const size_t smem = (size_t)(CoefRows<D, Q>::N * 32 + NW * warp_doubles) * sizeof(double) + (size_t)NW * Q * sizeof(uint64_t);
+   const int warp_doubles = (Q * op->slab + Q * Q * Q + 2 * 2 * Q * Q + (28 * (D - 1) + Q * Q + 3) + 15) & ~15;
+   const size_t smem = (size_t)(NW * warp_doubles) * sizeof(double) + (size_t)NW * Q * sizeof(uint64_t);
    static size_t configured = 0;
    static int blocks_per_sm = 0;
    if (configured != smem)
