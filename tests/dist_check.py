@@ -1,0 +1,181 @@
+"""Distributed parity check of the mesh-partitioned mode, run with one process per rank:
+
+  CPU / gloo  (host logic only: partition plan + P / P^T semantics; local element work is
+               done by the ORACLE, so this runs without a GPU):
+      python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port P \
+             tests/dist_check.py --mode cpu
+  GPU / NCCL  (the product path: CUDA apply + NCCL halo exchange + all-reduced Krylov dots):
+      python -m torch.distributed.run --nproc-per-node N ... tests/dist_check.py --mode gpu
+
+Every rank compares its owned part of  y = A x  (and of the GMRES solution / residual
+history) with the oracle's result on the un-partitioned mesh.  Exit code 0 = parity.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import cdm_b200 as cdm  # noqa: E402
+from oracle import pyoracle as orc  # noqa: E402
+
+PARTS = {1: (1, 1, 1), 2: (2, 1, 1), 3: (3, 1, 1), 4: (2, 2, 1), 6: (3, 2, 1), 8: (2, 2, 2)}
+
+
+def lattice_keys(P):
+    """global lattice key of every dof of an un-partitioned oracle problem (Cartesian, lexicographic elements)"""
+    p, d1d, dim = P.p, P.p + 1, P.dim
+    n = list(P.n) + [0] * (3 - dim)
+    N0, N1 = p * n[0] + 1, p * n[1] + 1
+    keys = np.zeros(P.ndof, np.int64)
+    e = np.arange(P.ne)
+    ei, ej, ek = e % n[0], (e // n[0]) % n[1], (e // (n[0] * n[1]) if dim == 3 else 0 * e)
+    for l in range(P.nd):
+        lx, ly, lz = l % d1d, (l // d1d) % d1d, (l // (d1d * d1d) if dim == 3 else 0)
+        keys[P.elem_dof[:, l]] = (p * ei + lx) + N0 * ((p * ej + ly) + N1 * (p * ek + lz))
+    return keys
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="cpu", choices=["cpu", "gpu"])
+    ap.add_argument("--order", type=int, default=3)
+    ap.add_argument("--n", type=int, nargs=3, default=[6, 5, 4])
+    args = ap.parse_args()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    gpu = args.mode == "gpu"
+    if gpu:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        ctx = cdm.Context(local_rank)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(cdm.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init(rank, world, uid.cpu().numpy().tobytes())
+    else:
+        dist.init_process_group("gloo")
+        ctx = cdm.Context(host_only=True)
+    p, parts = args.order, PARTS[world]
+    kap, vel, mass = 0.1, (1.0, -2.0, 0.5), 1.0
+
+    # ---- oracle on the un-partitioned mesh
+    P = orc.Problem(3, p, args.n, perturb=0.1, kappa=kap, vel=vel, mass=mass)
+    gkeys = lattice_keys(P)
+    inv = np.zeros(gkeys.max() + 1, np.int64)
+    inv[gkeys] = np.arange(P.ndof)
+    xg = np.sin(1.0 + 0.37 * gkeys)
+    yg = P.pa_op(True).mult(xg)                                   # constrained apply, all-Dirichlet
+    rng = np.random.default_rng(5)
+    bg = rng.uniform(-1, 1, P.ndof)[np.argsort(np.argsort(gkeys))]  # any fixed vector keyed by lattice position
+    bg = np.where(P.ess_mark, 0.0, bg)
+    dg = np.where(P.ess_mark, 1.0, P.pa_diag())
+    xs_g, info = P.pa_op(True).gmres(bg, dinv=1 / dg, variant=0, rtol=1e-10, atol=1e-12, max_it=500)
+
+    # ---- this rank's part
+    gm = cdm.Mesh.cartesian(ctx, 3, args.n, perturb=0.1)
+    lm = gm.partition_box(parts, rank)
+    sp = cdm.H1Space(lm, p)
+    keys = sp.dof_global()
+    nt = sp.ntrue
+    mine = inv[keys]                                             # local dof -> global oracle dof
+    assert np.abs(sp.dof_coords() - P.coords()[mine]).max() < 1e-13
+    tot = torch.tensor([nt], dtype=torch.int64, device="cuda" if gpu else "cpu")
+    dist.all_reduce(tot)
+    assert int(tot[0]) == P.ndof, (int(tot[0]), P.ndof)
+    ess = sp.essential_dofs(np.ones(6, np.int32))
+    assert np.all(P.ess_mark[mine[ess]] == 1) and P.ess_mark[mine].sum() == len(ess)
+
+    ok = True
+    if gpu:
+        op = cdm.ConvectionDiffusionOperator(sp, kappa=kap, vel=vel, mass=mass, ess_dofs=ess)
+        xd = torch.from_numpy(xg[mine[:nt]]).cuda()
+        yd = torch.zeros(nt, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        for kernel in (0, 1):
+            for scatter in (0, 1):
+                op.set_option("kernel", kernel)
+                op.set_option("scatter", scatter)
+                op.Mult(xd, yd)
+                ctx.sync()
+                err = np.linalg.norm(yd.cpu().numpy() - yg[mine[:nt]]) / np.linalg.norm(yg)
+                ok &= err < 1e-12
+                print(f"[rank {rank}] apply kernel={kernel} scatter={scatter} rel err {err:.2e}", flush=True)
+        # Jacobi diagonal (P^T-summed) and distributed GMRES
+        dd = torch.zeros(nt, dtype=torch.float64, device="cuda")
+        op.AssembleDiagonal(dd)
+        ctx.sync()
+        err = np.linalg.norm(dd.cpu().numpy() - dg[mine[:nt]]) / np.linalg.norm(dg)
+        ok &= err < 1e-12
+        bd = torch.from_numpy(bg[mine[:nt]]).cuda()
+        xs = torch.zeros(nt, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        s = cdm.GMRESSolver(cdm.GMRES_PETSC, 0, 500, 1e-10, 1e-12, jacobi=True)
+        s.SetOperator(op)
+        s.Mult(bd, xs)
+        ctx.sync()
+        herr = np.max(np.abs(s.history - info["hist"][:len(s.history)]) / info["hist"][0]) if len(s.history) == len(info["hist"]) else 1.0
+        serr = np.linalg.norm(xs.cpu().numpy() - xs_g[mine[:nt]]) / np.linalg.norm(xs_g)
+        ok &= s.GetConverged() and s.GetNumIterations() == info["iters"] and herr < 1e-10 and serr < 1e-9
+        print(f"[rank {rank}] diag err {err:.2e} gmres iters {s.GetNumIterations()}/{info['iters']} hist err {herr:.2e} sol err {serr:.2e}", flush=True)
+        nrm = ctx.norm2(xd)
+        ok &= abs(nrm - np.linalg.norm(xg)) < 1e-12 * np.linalg.norm(xg)      # all-reduced dot over T-dofs
+    else:
+        # host emulation of cdm_halo_P / cdm_halo_PT with gloo, element work by the oracle
+        lvx, lev, lbv, lba = lm.arrays()
+        g, o, i = sp.maps()
+        L = orc.lib()
+        nsym = 6
+        Dd = np.zeros((sp.ne, nsym, sp.nq)); Dc = np.zeros((sp.ne, 3, sp.nq)); Dm = np.zeros((sp.ne, sp.nq))
+        ck, cv, cm = np.array([kap]), np.array(vel), np.array([mass])
+        L.orc_qdata(3, p, sp.ne, lev, lvx, 1, 1, orc._opt(ck), 1, orc._opt(cv), 1.0, 1, orc._opt(cm),
+                    orc._opt(Dd), orc._opt(Dc), orc._opt(Dm))
+        plan = sp.halo()
+
+        def exchange(vec, forward):
+            reqs, bufs = [], []
+            for peer, own, ghost in plan:
+                snd, rcv = (own, ghost) if forward else (ghost, own)
+                if len(snd):
+                    reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(vec[snd])), peer))
+                if len(rcv):
+                    t = torch.zeros(len(rcv), dtype=torch.float64)
+                    reqs.append(dist.irecv(t, peer))
+                    bufs.append((rcv, t))
+            for r in reqs:
+                r.wait()
+            for idx, t in bufs:
+                if forward:
+                    vec[idx] = t.numpy()
+                else:
+                    vec[idx] += t.numpy()
+
+        essm = np.zeros(sp.ndof, bool)
+        essm[ess] = True
+        xL = np.zeros(sp.ndof)
+        xL[:nt] = xg[mine[:nt]]
+        exchange(xL, True)                                        # P
+        assert np.array_equal(xL, xg[mine])                       # ghosts received the owners' values
+        z = np.where(essm, 0.0, xL)
+        yL = np.zeros(sp.ndof)
+        L.orc_pa_apply(3, p, sp.ne, sp.ndof, g, o, i, orc._opt(Dd), orc._opt(Dc), orc._opt(Dm), z, yL)
+        exchange(yL, False)                                       # P^T
+        yL[essm] = xL[essm]
+        err = np.linalg.norm(yL[:nt] - yg[mine[:nt]]) / np.linalg.norm(yg)
+        ok &= err < 1e-12
+        print(f"[rank {rank}] host-emulated partitioned apply rel err {err:.2e} (ntrue {nt}, ghosts {sp.ndof - nt})", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda" if gpu else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag[0]) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

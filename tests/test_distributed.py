@@ -1,0 +1,43 @@
+"""Multi-rank tests of the mesh-partitioned mode (ParMesh / ParFiniteElementSpace semantics,
+linear_convection_diffusion_2D.cpp:300,312).  CPU: world_size 2 and 4 over gloo (partition plan,
+P / P^T semantics; element work by the oracle).  GPU: NCCL, when >= 2 devices are visible."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(nproc, mode, order, n=(6, 5, 4)):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "dist_check.py"), "--mode", mode, "--order", str(order), "--n", *map(str, n)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("nproc,order", [(2, 3), (4, 2)])
+def test_partitioned_apply_gloo(nproc, order):
+    out = _run(nproc, "cpu", order)
+    assert out.count("host-emulated partitioned apply") == nproc
+
+
+@pytest.mark.gpu
+def test_partitioned_apply_and_gmres_nccl():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run through gpurun --gpus 2)")
+    nproc = 8 if n >= 8 else (4 if n >= 4 else 2)
+    out = _run(nproc, "gpu", 3, n=(8, 6, 6))
+    assert out.count("gmres iters") == nproc
