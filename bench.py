@@ -175,6 +175,7 @@ def main():
         op.set_option("kernel", args.kernel)
     if args.scatter >= 0:
         op.set_option("scatter", args.scatter)
+    op.set_option("tail", 1)        # x, y are allocated with the local (L-vector) size: no T<->L copies
     n_true = sp.ntrue
     tot = torch.tensor([n_true, sp.ne], dtype=torch.int64, device="cuda")
     if world > 1:

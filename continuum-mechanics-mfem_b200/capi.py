@@ -94,6 +94,7 @@ SIGNATURES = {
     "cdm_operator_update": (_ci, [_vp, C.POINTER(Coeff), C.POINTER(Coeff), _cd, C.POINTER(Coeff)]),
     "cdm_operator_destroy": (_ci, [_vp]),
     "cdm_operator_size": (_i64, [_vp]),
+    "cdm_operator_local_size": (_i64, [_vp]),
     "cdm_operator_apply": (_ci, [_vp, _vp, _vp]),
     "cdm_operator_apply_unconstrained": (_ci, [_vp, _vp, _vp]),
     "cdm_operator_mult_host": (_ci, [_vp, _vp, _vp, _ci]),
@@ -373,6 +374,7 @@ class ConvectionDiffusionOperator:
         self.ctx.check(lib().cdm_operator_create(space.h, C.byref(ck), C.byref(cv), float(alpha), C.byref(cm),
                                                  _ptr(ess), 0 if ess is None else len(ess), C.byref(self.h)))
         self.height = self.width = int(lib().cdm_operator_size(self.h))
+        self.local_size = int(lib().cdm_operator_local_size(self.h))
         self.flags = (kappa is not None, vel is not None, mass is not None)
 
     def update(self, kappa=None, vel=None, alpha=1.0, mass=None):

@@ -492,12 +492,14 @@ int cdm_operator_destroy(cdm_op *op)
 }
 
 int64_t cdm_operator_size(const cdm_op *op) { return op ? op->sp->ntrue : 0; }
+int64_t cdm_operator_local_size(const cdm_op *op) { return op ? op->sp->ndof : 0; }
 
 int cdm_operator_set_option(cdm_op *op, const char *name, int value)
 {
    if (!op || !name) { return CDM_EINVAL; }
    if (!std::strcmp(name, "scatter")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->scatter_mode = value; return CDM_OK; }
    if (!std::strcmp(name, "kernel")) { op->kernel_variant = value; return CDM_OK; }
+   if (!std::strcmp(name, "tail")) { op->tail = value != 0; return CDM_OK; }
    return cdm_fail(op->sp->ctx, CDM_EINVAL, std::string("unknown option ") + name);
 }
 
@@ -528,7 +530,7 @@ static int apply_T(cdm_op *op, const double *x, double *y, bool constrained)
 {
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
-   if (sp->ntrue == sp->ndof) { return cdm_apply_tail(op, const_cast<double *>(x), y, constrained); }
+   if (sp->ntrue == sp->ndof || op->tail) { return cdm_apply_tail(op, const_cast<double *>(x), y, constrained); }
    int rc = ensure_L(op); if (rc) { return rc; }
    CDM_CUDA(ctx, cudaMemcpyAsync(op->xL_dev, x, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyDeviceToDevice, ctx->stream));
    if ((rc = cdm_apply_tail(op, op->xL_dev, op->yL_dev, constrained))) { return rc; }

@@ -99,6 +99,7 @@ struct cdm_op
    double *yE_dev = nullptr;       // E-vector scratch (scatter mode 0)
    double *xL_dev = nullptr, *yL_dev = nullptr;   // L-vector scratch (multi-GPU / host mult)
    double *dinv_dev = nullptr;     // cached Jacobi inverse diagonal
+   bool tail = false;              // caller vectors have room for the ghost tail (length >= ndof)
    int scatter_mode = 1;           // 0: E-vector + gather transpose, 1: FP64 red.add
    int kernel_variant = 0;
    // krylov workspace (lazy)

@@ -147,6 +147,10 @@ int  cdm_operator_update(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *ve
                          double conv_alpha, const cdm_coeff *mass);
 int  cdm_operator_destroy(cdm_op *op);
 int64_t cdm_operator_size(const cdm_op *op);        /* height = width = true dofs on this rank */
+/* local (L-vector) size = true dofs + ghost dofs of this rank.  Vectors allocated with this
+   length may be passed to cdm_operator_apply after cdm_operator_set_option(op, "tail", 1):
+   the entries past the true size are scratch for the halo exchange and no T<->L copy is made. */
+int64_t cdm_operator_local_size(const cdm_op *op);
 /* MFEM: Operator::Mult of FormLinearSystem's constrained operator
    (ConstrainedOperator, DIAG_ONE): y = A z, z = x with z[ess]=0, y[ess]=x[ess].
    In multi-GPU mode x,y are this rank's T-vectors and the call includes the
@@ -167,7 +171,7 @@ int  cdm_eliminate_rhs(cdm_op *op, const double *x_dev, double *b_dev);
 /* raw quadrature data (tests): host copy in MFEM layout, q fastest:
    Ddiff[(e*nsym+c)*nq+q], Dconv[(e*dim+c)*nq+q], Dmass[e*nq+q]; pointers may be NULL */
 int  cdm_operator_get_qdata(const cdm_op *op, double *Ddiff, double *Dconv, double *Dmass);
-/* tuning knobs (benchmarks): name in {"scatter" (0 E-vector+gather, 1 atomics), "kernel" (variant id)} */
+/* tuning knobs (benchmarks): name in {"scatter" (0 E-vector+gather, 1 atomics), "kernel" (variant id), "tail" (0/1)} */
 int  cdm_operator_set_option(cdm_op *op, const char *name, int value);
 /* measurement hook: run the element kernel of the apply `reps` times on this rank's
    L-vectors and return its mean device time (CUDA events recorded on the context's

@@ -46,7 +46,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", default="cpu", choices=["cpu", "gpu"])
     ap.add_argument("--order", type=int, default=3)
-    ap.add_argument("--n", type=int, nargs=3, default=[6, 5, 4])
+    ap.add_argument("--mesh", type=int, nargs=3, default=[6, 5, 4])
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
@@ -67,7 +67,7 @@ def main():
     kap, vel, mass = 0.1, (1.0, -2.0, 0.5), 1.0
 
     # ---- oracle on the un-partitioned mesh
-    P = orc.Problem(3, p, args.n, perturb=0.1, kappa=kap, vel=vel, mass=mass)
+    P = orc.Problem(3, p, args.mesh, perturb=0.1, kappa=kap, vel=vel, mass=mass)
     gkeys = lattice_keys(P)
     inv = np.zeros(gkeys.max() + 1, np.int64)
     inv[gkeys] = np.arange(P.ndof)
@@ -80,7 +80,7 @@ def main():
     xs_g, info = P.pa_op(True).gmres(bg, dinv=1 / dg, variant=0, rtol=1e-10, atol=1e-12, max_it=500)
 
     # ---- this rank's part
-    gm = cdm.Mesh.cartesian(ctx, 3, args.n, perturb=0.1)
+    gm = cdm.Mesh.cartesian(ctx, 3, args.mesh, perturb=0.1)
     lm = gm.partition_box(parts, rank)
     sp = cdm.H1Space(lm, p)
     keys = sp.dof_global()

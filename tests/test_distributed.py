@@ -20,7 +20,7 @@ def _free_port():
 def _run(nproc, mode, order, n=(6, 5, 4)):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "dist_check.py"), "--mode", mode, "--order", str(order), "--n", *map(str, n)]
+           os.path.join(ROOT, "tests", "dist_check.py"), "--mode", mode, "--order", str(order), "--mesh", *map(str, n)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
