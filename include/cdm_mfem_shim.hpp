@@ -1,0 +1,267 @@
+// cdm_mfem_shim.hpp -- header-only C++ layer over the C ABI (cdm_b200.h) with the MFEM
+// surface that myapps/convection_diffusion calls on this path, so the app's main() keeps
+// its shape (same names, argument meaning and error behaviour):
+//
+//   mfem::Vector                      -> cdm::Vector          (device-resident, host mirror on demand)
+//   mfem::Operator::Mult              -> cdm::Operator::Mult  (linear_convection_diffusion_1D.cpp:544)
+//   ParBilinearForm + integrators     -> cdm::ConvectionDiffusionForm
+//        AddDomainIntegrator / Assemble / FormLinearSystem / RecoverFEMSolution
+//        (linear_convection_diffusion_2D.cpp:335-351, :377)
+//   PetscLinearSolver / GMRESSolver   -> cdm::GMRESSolver     (:368-374, Input/petsc.opts:2-6)
+//   mfem::CGSolver                    -> cdm::CGSolver        (mesh_recession_handler.cpp:270-276)
+//
+// Errors: every non-zero C-ABI return becomes std::runtime_error, matching the app's
+// try/catch -> exit code 3 (linear_convection_diffusion_2D.cpp:435-442).  A solve that does
+// not converge is NOT an exception: query GetConverged() like the app does (:371).
+#pragma once
+#include "cdm_b200.h"
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace cdm
+{
+inline void check(cdm_ctx *ctx, int rc, const char *what)
+{
+   if (rc != CDM_OK)
+   {
+      throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " +
+                               (ctx ? cdm_last_error(ctx) : "no context"));
+   }
+}
+
+// Device("cuda") analogue (linear_convection_diffusion_2D.cpp:287 uses Device("cpu"))
+class Device
+{
+public:
+   explicit Device(int device = 0, void *stream = nullptr)
+   {
+      const int rc = cdm_init(device, stream, &ctx_);
+      if (rc != CDM_OK) { throw std::runtime_error("cdm_init failed: no usable CUDA device (no CPU fallback)"); }
+   }
+   ~Device() { cdm_finalize(ctx_); }
+   Device(const Device &) = delete;
+   Device &operator=(const Device &) = delete;
+   cdm_ctx *ctx() const { return ctx_; }
+   void Sync() const { check(ctx_, cdm_sync(ctx_), "cdm_sync"); }
+private:
+   cdm_ctx *ctx_ = nullptr;
+};
+
+class Vector
+{
+public:
+   Vector() = default;
+   Vector(const Device &dev, int64_t n) { SetSize(dev, n); }
+   ~Vector() { Destroy(); }
+   Vector(const Vector &) = delete;
+   Vector &operator=(const Vector &) = delete;
+   void SetSize(const Device &dev, int64_t n)
+   {
+      Destroy();
+      ctx_ = dev.ctx(); n_ = n;
+      check(ctx_, cdm_vec_alloc(ctx_, n, &d_), "cdm_vec_alloc");
+      check(ctx_, cdm_vec_set(ctx_, n, 0.0, d_), "cdm_vec_set");
+   }
+   int64_t Size() const { return n_; }
+   double *Read() const { return d_; }             // device pointer (mfem::Vector::Read with a device backend)
+   double *ReadWrite() { return d_; }
+   Vector &operator=(double v) { check(ctx_, cdm_vec_set(ctx_, n_, v, d_), "cdm_vec_set"); return *this; }
+   void SetFromHost(const double *h) { check(ctx_, cdm_vec_upload(ctx_, n_, h, d_), "cdm_vec_upload"); }
+   void GetToHost(double *h) const { check(ctx_, cdm_vec_download(ctx_, n_, d_, h), "cdm_vec_download"); }
+   std::vector<double> HostCopy() const { std::vector<double> h(n_); GetToHost(h.data()); return h; }
+   void Add(double a, const Vector &x) { check(ctx_, cdm_axpy(ctx_, n_, a, x.d_, d_), "cdm_axpy"); }   // *this += a x
+   double operator*(const Vector &y) const { double r; check(ctx_, cdm_dot(ctx_, n_, d_, y.d_, &r), "cdm_dot"); return r; }
+   double Norml2() const { double r; check(ctx_, cdm_norm2(ctx_, n_, d_, &r), "cdm_norm2"); return r; }
+private:
+   void Destroy() { if (d_) { cdm_vec_free(ctx_, d_); d_ = nullptr; } }
+   cdm_ctx *ctx_ = nullptr;
+   double *d_ = nullptr;
+   int64_t n_ = 0;
+};
+
+// mfem::Operator
+class Operator
+{
+public:
+   explicit Operator(int64_t s = 0) : height(s), width(s) {}
+   virtual ~Operator() = default;
+   int64_t Height() const { return height; }
+   int64_t Width() const { return width; }
+   virtual void Mult(const Vector &x, Vector &y) const = 0;
+protected:
+   int64_t height, width;
+};
+
+class Mesh
+{
+public:
+   static Mesh MakeCartesian3D(const Device &dev, int64_t nx, int64_t ny, int64_t nz, double perturb = 0.0)
+   {
+      Mesh m; m.ctx_ = dev.ctx();
+      const int64_t n[3] = {nx, ny, nz};
+      check(m.ctx_, cdm_mesh_cartesian(m.ctx_, 3, n, nullptr, perturb, &m.h_), "cdm_mesh_cartesian");
+      return m;
+   }
+   static Mesh MakeCartesian2D(const Device &dev, int64_t nx, int64_t ny, double perturb = 0.0)
+   {
+      Mesh m; m.ctx_ = dev.ctx();
+      const int64_t n[3] = {nx, ny, 0};
+      check(m.ctx_, cdm_mesh_cartesian(m.ctx_, 2, n, nullptr, perturb, &m.h_), "cdm_mesh_cartesian");
+      return m;
+   }
+   Mesh(Mesh &&o) noexcept : ctx_(o.ctx_), h_(o.h_) { o.h_ = nullptr; }
+   ~Mesh() { if (h_) { cdm_mesh_destroy(h_); } }
+   int Dimension() const { int d; cdm_mesh_sizes(h_, &d, nullptr, nullptr, nullptr); return d; }
+   cdm_mesh *handle() const { return h_; }
+   cdm_ctx *ctx() const { return ctx_; }
+private:
+   Mesh() = default;
+   cdm_ctx *ctx_ = nullptr;
+   cdm_mesh *h_ = nullptr;
+};
+
+// H1_FECollection(order, dim) + FiniteElementSpace
+class H1Space
+{
+public:
+   H1Space(const Mesh &mesh, int order) : ctx_(mesh.ctx())
+   {
+      check(ctx_, cdm_space_create_h1(ctx_, mesh.handle(), order, &h_), "cdm_space_create_h1");
+      cdm_space_sizes(h_, &dim_, &order_, &ne_, &ndof_, &d1d_, &q1d_, &ntrue_);
+   }
+   ~H1Space() { cdm_space_destroy(h_); }
+   H1Space(const H1Space &) = delete;
+   int64_t GetTrueVSize() const { return ntrue_; }
+   int64_t GetNE() const { return ne_; }
+   int GetNQ() const { int nq = 1; for (int d = 0; d < dim_; d++) { nq *= q1d_; } return nq; }
+   int Dimension() const { return dim_; }
+   // fespace.GetEssentialTrueDofs(ess_bdr, ess_tdof_list)
+   void GetEssentialTrueDofs(const std::vector<int> &ess_bdr, std::vector<int32_t> &list) const
+   {
+      std::vector<int32_t> marker(ess_bdr.begin(), ess_bdr.end());
+      int64_t n = 0;
+      check(ctx_, cdm_space_essential_dofs(h_, marker.data(), (int)marker.size(), nullptr, &n), "cdm_space_essential_dofs");
+      list.resize(n);
+      check(ctx_, cdm_space_essential_dofs(h_, marker.data(), (int)marker.size(), list.data(), &n), "cdm_space_essential_dofs");
+   }
+   std::vector<double> DofCoordinates() const
+   {
+      std::vector<double> x((size_t)ndof_ * dim_);
+      cdm_space_dof_coords(h_, x.data());
+      return x;
+   }
+   std::vector<double> QuadraturePointCoordinates() const
+   {
+      std::vector<double> x((size_t)ne_ * GetNQ() * dim_);
+      cdm_space_qpt_coords(h_, x.data());
+      return x;
+   }
+   cdm_space *handle() const { return h_; }
+   cdm_ctx *ctx() const { return ctx_; }
+private:
+   cdm_ctx *ctx_;
+   cdm_space *h_ = nullptr;
+   int dim_ = 0, order_ = 0, d1d_ = 0, q1d_ = 0;
+   int64_t ne_ = 0, ndof_ = 0, ntrue_ = 0;
+};
+
+// ParBilinearForm with {Diffusion, Convection, Mass}Integrator under AssemblyLevel::PARTIAL
+class ConvectionDiffusionForm : public Operator
+{
+public:
+   explicit ConvectionDiffusionForm(H1Space &fes) : Operator(fes.GetTrueVSize()), fes_(fes) {}
+   ~ConvectionDiffusionForm() override { cdm_operator_destroy(op_); }
+   // a.AddDomainIntegrator(new DiffusionIntegrator(kappa))
+   void AddDiffusionIntegrator(double kappa) { kappa_c_ = {kappa}; kap_ = {CDM_COEFF_CONST, 1, kappa_c_.data()}; }
+   void AddDiffusionIntegrator(const std::vector<double> &per_qpt, int ncomp = 1)
+   { kappa_c_ = per_qpt; kap_ = {CDM_COEFF_QPT, ncomp, kappa_c_.data()}; }
+   // a.AddDomainIntegrator(new ConvectionIntegrator(velocity, alpha))
+   void AddConvectionIntegrator(const std::vector<double> &velocity, double alpha = 1.0)
+   { vel_c_ = velocity; vel_ = {CDM_COEFF_CONST, (int)velocity.size(), vel_c_.data()}; alpha_ = alpha; }
+   void AddConvectionIntegratorQpt(const std::vector<double> &per_qpt, double alpha = 1.0)
+   { vel_c_ = per_qpt; vel_ = {CDM_COEFF_QPT, fes_.Dimension(), vel_c_.data()}; alpha_ = alpha; }
+   // a.AddDomainIntegrator(new MassIntegrator(s))
+   void AddMassIntegrator(double s) { mass_c_ = {s}; mass_ = {CDM_COEFF_CONST, 1, mass_c_.data()}; }
+   void AddMassIntegrator(const std::vector<double> &per_qpt) { mass_c_ = per_qpt; mass_ = {CDM_COEFF_QPT, 1, mass_c_.data()}; }
+   void SetEssentialTrueDofs(const std::vector<int32_t> &ess) { ess_ = ess; }
+   // a.Assemble(): quadrature data on the device
+   void Assemble()
+   {
+      if (op_) { cdm_operator_destroy(op_); op_ = nullptr; }
+      check(fes_.ctx(), cdm_operator_create(fes_.handle(), &kap_, &vel_, alpha_, &mass_, ess_.data(), (int64_t)ess_.size(), &op_),
+            "cdm_operator_create");
+   }
+   // Operator::Mult of the constrained system operator
+   void Mult(const Vector &x, Vector &y) const override
+   { check(fes_.ctx(), cdm_operator_apply(op_, x.Read(), y.ReadWrite()), "cdm_operator_apply"); }
+   // BilinearForm::Mult on L-vectors, no constraints (mass_form.Mult(c, rhs))
+   void MultUnconstrained(const Vector &x, Vector &y) const
+   { check(fes_.ctx(), cdm_operator_apply_unconstrained(op_, x.Read(), y.ReadWrite()), "cdm_operator_apply_unconstrained"); }
+   // a.FormLinearSystem(ess_tdof_list, u, b, A, X, B): X = u, B = b - A u_ess, B[ess] = u[ess]
+   void FormLinearSystem(const Vector &u, Vector &b) const
+   { check(fes_.ctx(), cdm_eliminate_rhs(op_, u.Read(), b.ReadWrite()), "cdm_eliminate_rhs"); }
+   void AssembleDiagonal(Vector &d) const { check(fes_.ctx(), cdm_operator_diag(op_, d.ReadWrite()), "cdm_operator_diag"); }
+   cdm_op *handle() const { return op_; }
+   cdm_ctx *ctx() const { return fes_.ctx(); }
+private:
+   H1Space &fes_;
+   cdm_op *op_ = nullptr;
+   std::vector<double> kappa_c_, vel_c_, mass_c_;
+   cdm_coeff kap_{CDM_COEFF_NONE, 0, nullptr}, vel_{CDM_COEFF_NONE, 0, nullptr}, mass_{CDM_COEFF_NONE, 0, nullptr};
+   double alpha_ = 1.0;
+   std::vector<int32_t> ess_;
+};
+
+// mfem::IterativeSolver surface
+class IterativeSolver
+{
+public:
+   virtual ~IterativeSolver() = default;
+   void SetRelTol(double v) { o_.rtol = v; }
+   void SetAbsTol(double v) { o_.atol = v; }
+   void SetMaxIter(int v) { o_.max_it = v; }
+   void SetPrintLevel(int) {}
+   void SetJacobi(bool on) { o_.jacobi = on ? 1 : 0; }          // -pc_type jacobi
+   void SetOperator(const ConvectionDiffusionForm &op) { op_ = &op; }
+   bool iterative_mode = false;                                  // PetscLinearSolver default
+   int GetNumIterations() const { return r_.iters; }
+   bool GetConverged() const { return r_.converged != 0; }
+   double GetFinalNorm() const { return r_.final_norm; }
+   double GetSolveSeconds() const { return r_.seconds; }
+   const std::vector<double> &ResidualHistory() const { return hist_; }
+   virtual void Mult(const Vector &b, Vector &x) = 0;
+protected:
+   template <typename F> void Run(F fn, const Vector &b, Vector &x, const char *what)
+   {
+      if (!op_) { throw std::runtime_error("SetOperator has not been called"); }
+      o_.zero_guess = iterative_mode ? 0 : 1;
+      hist_.assign((size_t)o_.max_it + 2, 0.0);
+      check(op_->ctx(), fn(op_->handle(), b.Read(), x.ReadWrite(), &o_, &r_, hist_.data()), what);
+      hist_.resize(r_.hist_len);
+   }
+   cdm_krylov_opts o_{CDM_GMRES_PETSC, 0, 500, 1e-10, 1e-12, 1, 1};
+   cdm_krylov_result r_{0, 0, 0.0, 0, 0.0};
+   const ConvectionDiffusionForm *op_ = nullptr;
+   std::vector<double> hist_;
+};
+
+// GMRES as configured by Input/petsc.opts (variant CDM_GMRES_PETSC) or mfem::GMRESSolver (CDM_GMRES_MFEM)
+class GMRESSolver : public IterativeSolver
+{
+public:
+   explicit GMRESSolver(int variant = CDM_GMRES_PETSC) { o_.variant = variant; }
+   void SetKDim(int m) { o_.restart = m; }
+   void Mult(const Vector &b, Vector &x) override { Run(cdm_gmres, b, x, "cdm_gmres"); }
+};
+
+// mfem::CGSolver (rel 1e-12, abs 0, max 500 at mesh_recession_handler.cpp:271-273)
+class CGSolver : public IterativeSolver
+{
+public:
+   CGSolver() { o_.rtol = 1e-12; o_.atol = 0.0; o_.jacobi = 0; }
+   void Mult(const Vector &b, Vector &x) override { Run(cdm_cg, b, x, "cdm_cg"); }
+};
+}  // namespace cdm
