@@ -120,13 +120,39 @@ static int space_finish(cdm_ctx *ctx, const cdm_mesh *mesh, cdm_space *sp)
       if ((rc = upload(ctx, sp->offsets, &sp->offsets_dev))) { return rc; }
       if ((rc = upload(ctx, sp->indices, &sp->indices_dev))) { return rc; }
       if ((rc = upload(ctx, sp->elem_x, &sp->elem_x_dev))) { return rc; }
-      for (auto &pr : sp->peers)
+      if (!sp->peers.empty())
       {
-         if ((rc = upload(ctx, pr.own_idx, &pr.own_idx_dev))) { return rc; }
-         if ((rc = upload(ctx, pr.ghost_idx, &pr.ghost_idx_dev))) { return rc; }
-         const size_t nb = std::max(pr.own_idx.size(), pr.ghost_idx.size()) * sizeof(double);
-         CDM_CUDA(ctx, cudaMalloc(&pr.send_dev, nb));
-         CDM_CUDA(ctx, cudaMalloc(&pr.recv_dev, nb));
+         // fused exchange plan: one pack and one unpack kernel per phase, whatever the peer count.
+         // own_all / ghost_all = per-peer lists concatenated in peer order; P^T adds are done per
+         // owned-shared dof in peer order (CSR), so the summation order is fixed.
+         cdm_halo_plan &hp = sp->halo;
+         for (auto &pr : sp->peers)
+         {
+            pr.own_off = (int64_t)hp.own_all.size(); pr.ghost_off = (int64_t)hp.ghost_all.size();
+            hp.own_all.insert(hp.own_all.end(), pr.own_idx.begin(), pr.own_idx.end());
+            hp.ghost_all.insert(hp.ghost_all.end(), pr.ghost_idx.begin(), pr.ghost_idx.end());
+         }
+         std::vector<int32_t> order(hp.own_all.size());
+         for (size_t i = 0; i < order.size(); i++) { order[i] = (int32_t)i; }
+         std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hp.own_all[a] < hp.own_all[b]; });
+         for (size_t i = 0; i < order.size(); i++)
+         {
+            if (i == 0 || hp.own_all[order[i]] != hp.own_all[order[i - 1]])
+            {
+               hp.pt_dof.push_back(hp.own_all[order[i]]);
+               hp.pt_off.push_back((int32_t)i);
+            }
+         }
+         hp.pt_off.push_back((int32_t)order.size());
+         hp.pt_src = order;
+         if ((rc = upload(ctx, hp.own_all, &hp.own_all_dev))) { return rc; }
+         if ((rc = upload(ctx, hp.ghost_all, &hp.ghost_all_dev))) { return rc; }
+         if ((rc = upload(ctx, hp.pt_dof, &hp.pt_dof_dev))) { return rc; }
+         if ((rc = upload(ctx, hp.pt_off, &hp.pt_off_dev))) { return rc; }
+         if ((rc = upload(ctx, hp.pt_src, &hp.pt_src_dev))) { return rc; }
+         const size_t nb = (std::max(hp.own_all.size(), hp.ghost_all.size()) + 1) * sizeof(double);
+         CDM_CUDA(ctx, cudaMalloc(&hp.send_dev, nb));
+         CDM_CUDA(ctx, cudaMalloc(&hp.recv_dev, nb));
       }
       CDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
    }
@@ -402,7 +428,9 @@ int cdm_space_destroy(cdm_space *sp)
    if (sp->ctx && sp->ctx->device >= 0)
    {
       cudaFree(sp->gather_dev); cudaFree(sp->offsets_dev); cudaFree(sp->indices_dev); cudaFree(sp->elem_x_dev);
-      for (auto &pr : sp->peers) { cudaFree(pr.own_idx_dev); cudaFree(pr.ghost_idx_dev); cudaFree(pr.send_dev); cudaFree(pr.recv_dev); }
+      cdm_halo_plan &hp = sp->halo;
+      cudaFree(hp.own_all_dev); cudaFree(hp.ghost_all_dev); cudaFree(hp.pt_dof_dev); cudaFree(hp.pt_off_dev);
+      cudaFree(hp.pt_src_dev); cudaFree(hp.send_dev); cudaFree(hp.recv_dev);
    }
    delete sp;
    return CDM_OK;

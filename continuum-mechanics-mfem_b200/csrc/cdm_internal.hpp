@@ -59,8 +59,17 @@ struct cdm_halo_peer
    std::vector<int32_t> own_idx;    // local dof ids (owned, < ntrue)
    // dofs the peer owns that I hold as ghosts
    std::vector<int32_t> ghost_idx;  // local dof ids (>= ntrue)
-   int32_t *own_idx_dev = nullptr, *ghost_idx_dev = nullptr;
-   double *send_dev = nullptr, *recv_dev = nullptr;   // max(own, ghost) entries each
+   int64_t own_off = 0, ghost_off = 0;   // offsets of this peer's lists in the fused plan
+};
+
+// fused exchange plan over all peers (one pack + one unpack kernel per phase)
+struct cdm_halo_plan
+{
+   std::vector<int32_t> own_all, ghost_all;          // per-peer lists concatenated in peer order
+   std::vector<int32_t> pt_dof, pt_off, pt_src;      // P^T: distinct owned-shared dofs, CSR into the receive buffer
+   int32_t *own_all_dev = nullptr, *ghost_all_dev = nullptr;
+   int32_t *pt_dof_dev = nullptr, *pt_off_dev = nullptr, *pt_src_dev = nullptr;
+   double *send_dev = nullptr, *recv_dev = nullptr;
 };
 
 struct cdm_space
@@ -81,6 +90,7 @@ struct cdm_space
    double *elem_x_dev = nullptr;
    // multi-GPU
    std::vector<cdm_halo_peer> peers;
+   cdm_halo_plan halo;
    std::vector<int64_t> dof_global;                    // local dof -> global dof id (partitioned spaces)
 };
 
@@ -147,6 +157,9 @@ int cdm_k_set_idx(cdm_ctx *c, int64_t n, const int32_t *idx, double v, double *y
 int cdm_k_pack(cdm_ctx *c, int64_t n, const int32_t *idx, const double *x, double *buf);     // buf[i]=x[idx[i]]
 int cdm_k_unpack(cdm_ctx *c, int64_t n, const int32_t *idx, const double *buf, double *x, int add);
 int cdm_k_recip(cdm_ctx *c, int64_t n, const double *d, double *dinv);
+// x[dof[k]] += sum_{j in [off[k],off[k+1])} buf[src[j]]  (fixed order)
+int cdm_k_unpack_add_csr(cdm_ctx *c, int64_t n, const int32_t *dof, const int32_t *off, const int32_t *src,
+                         const double *buf, double *x);
 // k dots of w against V columns -> ctx->red_dev results [k] (device), deterministic
 int cdm_k_mdot_dev(cdm_ctx *c, int64_t n, int k, const double *w, const double *V, int64_t ldv,
                    double *out_dev);

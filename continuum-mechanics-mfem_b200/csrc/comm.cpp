@@ -101,38 +101,35 @@ int cdm_halo_P(cdm_op *op, double *xL)
    cdm_ctx *c = sp->ctx;
    if (!c->comm) { return cdm_fail(c, CDM_ENCCL, "partitioned space used without cdm_comm_init"); }
    NcclApi *a = api();
-   for (auto &pr : sp->peers)
-      if (!pr.own_idx.empty()) { int rc = cdm_k_pack(c, (int64_t)pr.own_idx.size(), pr.own_idx_dev, xL, pr.send_dev); if (rc) { return rc; } }
+   cdm_halo_plan &hp = sp->halo;
+   int rc = cdm_k_pack(c, (int64_t)hp.own_all.size(), hp.own_all_dev, xL, hp.send_dev);
+   if (rc) { return rc; }
    NCCL_CALL(c, a->GroupStart());
    for (auto &pr : sp->peers)
    {
-      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Send(pr.send_dev, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
-      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Recv(pr.recv_dev, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
+      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Send(hp.send_dev + pr.own_off, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
+      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Recv(hp.recv_dev + pr.ghost_off, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
    }
    NCCL_CALL(c, a->GroupEnd());
-   for (auto &pr : sp->peers)
-      if (!pr.ghost_idx.empty()) { int rc = cdm_k_unpack(c, (int64_t)pr.ghost_idx.size(), pr.ghost_idx_dev, pr.recv_dev, xL, 0); if (rc) { return rc; } }
-   return CDM_OK;
+   return cdm_k_unpack(c, (int64_t)hp.ghost_all.size(), hp.ghost_all_dev, hp.recv_dev, xL, 0);
 }
 
-// owner entries of y_L += partial sums held in the sharers' ghost entries
+// owner entries of y_L += partial sums held in the sharers' ghost entries (fixed peer order)
 int cdm_halo_PT(cdm_op *op, double *yL)
 {
    cdm_space *sp = op->sp;
    cdm_ctx *c = sp->ctx;
    if (!c->comm) { return cdm_fail(c, CDM_ENCCL, "partitioned space used without cdm_comm_init"); }
    NcclApi *a = api();
-   for (auto &pr : sp->peers)
-      if (!pr.ghost_idx.empty()) { int rc = cdm_k_pack(c, (int64_t)pr.ghost_idx.size(), pr.ghost_idx_dev, yL, pr.send_dev); if (rc) { return rc; } }
+   cdm_halo_plan &hp = sp->halo;
+   int rc = cdm_k_pack(c, (int64_t)hp.ghost_all.size(), hp.ghost_all_dev, yL, hp.send_dev);
+   if (rc) { return rc; }
    NCCL_CALL(c, a->GroupStart());
    for (auto &pr : sp->peers)
    {
-      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Send(pr.send_dev, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
-      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Recv(pr.recv_dev, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
+      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Send(hp.send_dev + pr.ghost_off, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
+      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Recv(hp.recv_dev + pr.own_off, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
    }
    NCCL_CALL(c, a->GroupEnd());
-   // fixed peer order -> deterministic summation
-   for (auto &pr : sp->peers)
-      if (!pr.own_idx.empty()) { int rc = cdm_k_unpack(c, (int64_t)pr.own_idx.size(), pr.own_idx_dev, pr.recv_dev, yL, 1); if (rc) { return rc; } }
-   return CDM_OK;
+   return cdm_k_unpack_add_csr(c, (int64_t)hp.pt_dof.size(), hp.pt_dof_dev, hp.pt_off_dev, hp.pt_src_dev, hp.recv_dev, yL);
 }

@@ -77,6 +77,19 @@ __global__ void k_unpack(int64_t n, const int32_t *__restrict__ idx, const doubl
    if (i < n) { if (add) { x[idx[i]] += buf[i]; } else { x[idx[i]] = buf[i]; } }
 }
 
+__global__ void k_unpack_add_csr(int64_t n, const int32_t *__restrict__ dof, const int32_t *__restrict__ off,
+                                 const int32_t *__restrict__ src, const double *__restrict__ buf, double *__restrict__ x)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) { return; }
+   double s = x[dof[i]];
+   for (int32_t j = off[i]; j < off[i + 1]; j++) { s += buf[src[j]]; }
+   x[dof[i]] = s;
+}
+int cdm_k_unpack_add_csr(cdm_ctx *c, int64_t n, const int32_t *dof, const int32_t *off, const int32_t *src,
+                         const double *buf, double *x)
+{ if (n > 0) { k_unpack_add_csr<<<vec_grid(n), VEC_BLOCK, 0, c->stream>>>(n, dof, off, src, buf, x); } VEC_CHECK(c); }
+
 int cdm_k_set(cdm_ctx *c, int64_t n, double v, double *x)
 { if (n > 0) { k_set<<<vec_grid(n), VEC_BLOCK, 0, c->stream>>>(n, v, x); } VEC_CHECK(c); }
 int cdm_k_axpy(cdm_ctx *c, int64_t n, double a, const double *x, double *y)
