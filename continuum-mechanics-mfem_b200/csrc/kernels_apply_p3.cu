@@ -72,7 +72,10 @@ __device__ __forceinline__ void red_add_f64(double *addr, double v)
 // buffer hit 16 distinct 8-byte bank pairs per half warp:
 //   P(qx,dy,dz) = qx + 5 dy + 20 dz        (L1 <-> L2)
 //   R(qx,qy,dz) = qx + 5 qy + 28 dz        (L2 <-> L3)
-template <int D, int Q, int NW, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
+// PH = true ("phased"): the quadrature-point work is split into two sync-free phases -- (A) gradients,
+// D, point-wise products for all five slabs, (B) all transposed gradient contractions -- so the loads
+// of different slabs overlap; fx, fy of the whole element are exchanged at once.
+template <int D, int Q, int NW, bool DIFF, bool CONV, bool MASS, bool ATOMIC, bool PH>
 __global__ void __launch_bounds__(NW * 32)
 k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict__ gmap,
                const double *__restrict__ x, const double *__restrict__ Dg, const int slab,
@@ -81,14 +84,15 @@ k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict_
    static_assert(D == 4 && Q == 5, "lane roles and exchange layouts are written for order 3");
    constexpr int Q2 = Q * Q, ND = D * D * D;
    constexpr int SU = Q * Q2;                                // u at the quadrature points [qz][qy][qx]
-   constexpr int SF = 2 * 2 * Q2;                            // double-buffered fx, fy slabs; aliases the P buffer
-   constexpr int SR = 28 * (D - 1) + Q2 + 3;                 // R buffer (112)
+   constexpr int SRW = 28 * (D - 1) + Q2 + 3;                // R buffer (112)
+   constexpr int SF = PH ? 2 * Q * Q2 : 2 * 2 * Q2;          // fx, fy: whole element (PH) or double-buffered slabs
+   constexpr int SR = PH ? 0 : SRW;                          // PH: the R buffer lives inside the fx/fy region
    extern __shared__ __align__(128) unsigned char smraw[];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    const int warp_doubles = (Q * slab + SU + SF + SR + 15) & ~15;      // keeps every ring slab 16-byte aligned
    double *wbase = reinterpret_cast<double *>(smraw) + wib * warp_doubles;
    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smraw) + NW * warp_doubles) + wib * Q;
-   double *ring = wbase, *sU = ring + Q * slab, *sF = sU + SU, *sP = sF, *sR = sF + SF;
+   double *ring = wbase, *sU = ring + Q * slab, *sF = sU + SU, *sP = sF, *sR = PH ? sF + 100 : sF + SF;
    const bool l1 = lane < D * D, l2 = lane < Q * D, l3 = lane < Q2;
    const int qx = l3 ? lane % Q : 0, qy = l3 ? lane / Q : 0;             // L3 role
    const int qx2 = l2 ? (lane >> 2) : 0, dz2 = lane & 3;                 // L2 role
@@ -185,8 +189,74 @@ k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict_
          for (int qz = 0; qz < Q; qz++) { sU[qz * Q2 + lane] = u[qz]; }
       }
       __syncwarp();
-      // ---- slab loop: gradients, point-wise D, transposed gradients
       double out[Q];
+      if (PH)
+      {
+         // ---- phase A: gradients, point-wise D for all slabs (no synchronisation inside)
+         double fzv[Q], sv[Q];
+         #pragma unroll
+         for (int qz = 0; qz < Q; qz++)
+         {
+            double gx = 0.0, gy = 0.0, gz = 0.0;
+            if (DIFF || CONV)
+            {
+               #pragma unroll
+               for (int k = 0; k < Q; k++)
+               {
+                  gx += dqx_row[k] * sU[qz * Q2 + qy * Q + k];
+                  gy += dqy_row[k] * sU[qz * Q2 + k * Q + qx];
+                  gz += tb.Dq[qz * Q + k] * u[k];
+               }
+            }
+            mbar_wait(&bars[qz], parity);
+            const double *dp = ring + qz * slab + (l3 ? lane : 0);
+            double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;
+            int c = 0;
+            if (DIFF)
+            {
+               const double d0 = dp[0], d1 = dp[Q2], d2 = dp[2 * Q2], d3 = dp[3 * Q2], d4 = dp[4 * Q2], d5 = dp[5 * Q2];
+               fx = d0 * gx + d1 * gy + d2 * gz;
+               fy = d1 * gx + d3 * gy + d4 * gz;
+               fz = d2 * gx + d4 * gy + d5 * gz;
+               c = 6;
+            }
+            if (CONV) { s = dp[c * Q2] * gx + dp[(c + 1) * Q2] * gy + dp[(c + 2) * Q2] * gz; c += 3; }
+            if (MASS) { s += dp[c * Q2] * u[qz]; }
+            fzv[qz] = fz; sv[qz] = s;
+            if (DIFF && l3) { sF[qz * Q2 + lane] = fx; sF[Q * Q2 + qz * Q2 + lane] = fy; }
+         }
+         __syncwarp();
+         // the whole D tile of this element is consumed: request the next element's tile
+         if (lane == 0 && more)
+         {
+            #pragma unroll
+            for (int q = 0; q < Q; q++)
+            {
+               mbar_expect_tx(&bars[q], slab_bytes);
+               bulk_g2s(ring + q * slab, Dg + (en * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+            }
+         }
+         // ---- phase B: transposed gradient contractions
+         #pragma unroll
+         for (int qz = 0; qz < Q; qz++)
+         {
+            double r = sv[qz];
+            if (DIFF)
+            {
+               #pragma unroll
+               for (int k = 0; k < Q; k++)
+               {
+                  r += dqx_col[k] * sF[qz * Q2 + qy * Q + k] + dqy_col[k] * sF[Q * Q2 + qz * Q2 + k * Q + qx];
+                  r += tb.Dq[k * Q + qz] * fzv[k];
+               }
+            }
+            out[qz] = r;
+         }
+         __syncwarp();                                       // fx/fy region is reused by the R buffer
+      }
+      else
+      {
+      // ---- slab loop: gradients, point-wise D, transposed gradients
       #pragma unroll
       for (int qz = 0; qz < Q; qz++) { out[qz] = 0.0; }
       #pragma unroll
@@ -241,6 +311,7 @@ k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict_
             }
          }
          out[qz] += r;
+      }
       }
       // ---- B1 (L3 lanes): transposed z contraction in registers, publish w(qx,qy,dz)
       if (l3)
@@ -303,6 +374,275 @@ k_apply3d_warp(const WarpTables tb, const int64_t ne, const int32_t *__restrict_
    }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_apply3d_warp_bg -- "register-z" variant (kernel option 3, the default for order 3).
+// u, du/dx, du/dy, du/dz are produced by separate B / G contractions: x and y in two exchange
+// stages with constant-bank coefficients, z in registers, so every lane ends up holding the four
+// fields on its own z-column of quadrature points.  The point-wise D product and the transposed
+// z contraction then run entirely in registers: no gradient exchange through shared memory, no
+// per-lane coefficient registers, 6 warp syncs per element.  Shared-memory instructions per
+// element: 45 (forward) + 50 (D) + 45 (backward), against ~200 in the collocated variants.
+struct WarpTablesBG
+{
+   double B[CDM_MAX_Q1D * CDM_MAX_D1D];    // B[q*D + d]
+   double G[CDM_MAX_Q1D * CDM_MAX_D1D];    // G[q*D + d]
+};
+
+template <int NW, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
+__global__ void __launch_bounds__(NW * 32)
+k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__restrict__ gmap,
+                  const double *__restrict__ x, const double *__restrict__ Dg, const int slab,
+                  double *__restrict__ y)
+{
+   constexpr int D = 4, Q = 5, Q2 = Q * Q, ND = D * D * D;
+   constexpr bool GRAD = DIFF || CONV;
+   constexpr int PS = 80, RS = 112;                          // one P-layout / R-layout array (doubles)
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+   const int warp_doubles = (Q * slab + 3 * RS + 2 * PS + 15) & ~15;
+   double *wbase = reinterpret_cast<double *>(smraw) + wib * warp_doubles;
+   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smraw) + NW * warp_doubles) + wib * Q;
+   double *ring = wbase, *sR0 = ring + Q * slab, *sR1 = sR0 + RS, *sR2 = sR1 + RS, *sP0 = sR2 + RS, *sP1 = sP0 + PS;
+   const bool l1 = lane < D * D, l2 = lane < Q * D, l3 = lane < Q2;
+   const int l3i = l3 ? lane : 0;                                        // L3 role: (qx,qy) = lane
+   const int qx2 = l2 ? (lane >> 2) : 0, dz2 = lane & 3;                 // L2 role
+
+   if (lane == 0)
+   {
+      for (int q = 0; q < Q; q++) { mbar_init(&bars[q], 1); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   __syncwarp();
+   const int64_t gw = (int64_t)blockIdx.x * NW + wib, tw = (int64_t)gridDim.x * NW;
+   const uint32_t slab_bytes = (uint32_t)slab * 8u;
+   int4 pg = make_int4(-1, -1, -1, -1);
+   double px[D] = {0.0, 0.0, 0.0, 0.0};
+   if (gw < ne)
+   {
+      if (lane == 0)
+      {
+         #pragma unroll
+         for (int q = 0; q < Q; q++)
+         {
+            mbar_expect_tx(&bars[q], slab_bytes);
+            bulk_g2s(ring + q * slab, Dg + (gw * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+         }
+      }
+      if (l1)
+      {
+         pg = __ldg(reinterpret_cast<const int4 *>(gmap + gw * ND) + lane);
+         px[0] = (pg.x >= 0) ? __ldg(x + pg.x) : 0.0; px[1] = (pg.y >= 0) ? __ldg(x + pg.y) : 0.0;
+         px[2] = (pg.z >= 0) ? __ldg(x + pg.z) : 0.0; px[3] = (pg.w >= 0) ? __ldg(x + pg.w) : 0.0;
+      }
+   }
+
+   uint32_t parity = 0;
+   for (int64_t e = gw; e < ne; e += tw, parity ^= 1u)
+   {
+      const int64_t en = e + tw;
+      const bool more = en < ne;
+      const int4 g = pg;
+      // ---- F1 (L1 lanes): x contraction of the own x-line with B and G
+      if (l1)
+      {
+         #pragma unroll
+         for (int q = 0; q < Q; q++)
+         {
+            double tB = 0.0, tG = 0.0;
+            #pragma unroll
+            for (int d = 0; d < D; d++) { tB += tb.B[q * D + d] * px[d]; if (GRAD) { tG += tb.G[q * D + d] * px[d]; } }
+            sP0[q + Q * lane] = tB;
+            if (GRAD) { sP1[q + Q * lane] = tG; }
+         }
+      }
+      if (more && l1)
+      {
+         pg = __ldg(reinterpret_cast<const int4 *>(gmap + en * ND) + lane);
+         px[0] = (pg.x >= 0) ? __ldg(x + pg.x) : 0.0; px[1] = (pg.y >= 0) ? __ldg(x + pg.y) : 0.0;
+         px[2] = (pg.z >= 0) ? __ldg(x + pg.z) : 0.0; px[3] = (pg.w >= 0) ? __ldg(x + pg.w) : 0.0;
+      }
+      __syncwarp();
+      // ---- F2 (L2 lanes): y contraction -> (B B), (G B), (B G)
+      if (l2)
+      {
+         double tB[D], tG[D];
+         #pragma unroll
+         for (int dy = 0; dy < D; dy++)
+         {
+            tB[dy] = sP0[qx2 + Q * dy + Q * D * dz2];
+            if (GRAD) { tG[dy] = sP1[qx2 + Q * dy + Q * D * dz2]; }
+         }
+         #pragma unroll
+         for (int q = 0; q < Q; q++)
+         {
+            double vbb = 0.0, vgb = 0.0, vbg = 0.0;
+            #pragma unroll
+            for (int dy = 0; dy < D; dy++)
+            {
+               vbb += tb.B[q * D + dy] * tB[dy];
+               if (GRAD) { vgb += tb.B[q * D + dy] * tG[dy]; vbg += tb.G[q * D + dy] * tB[dy]; }
+            }
+            sR0[qx2 + Q * q + 28 * dz2] = vbb;
+            if (GRAD) { sR1[qx2 + Q * q + 28 * dz2] = vgb; sR2[qx2 + Q * q + 28 * dz2] = vbg; }
+         }
+      }
+      __syncwarp();
+      // ---- F3 (L3 lanes): z contraction in registers: u, ux, uy, uz on the lane's z-column
+      double u[Q], ux[Q], uy[Q], uz[Q];
+      {
+         double vbb[D], vgb[D], vbg[D];
+         #pragma unroll
+         for (int dz = 0; dz < D; dz++)
+         {
+            vbb[dz] = sR0[l3i + 28 * dz];
+            if (GRAD) { vgb[dz] = sR1[l3i + 28 * dz]; vbg[dz] = sR2[l3i + 28 * dz]; }
+         }
+         #pragma unroll
+         for (int qz = 0; qz < Q; qz++)
+         {
+            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+            #pragma unroll
+            for (int dz = 0; dz < D; dz++)
+            {
+               a += tb.B[qz * D + dz] * vbb[dz];
+               if (GRAD) { b += tb.B[qz * D + dz] * vgb[dz]; c += tb.B[qz * D + dz] * vbg[dz]; d += tb.G[qz * D + dz] * vbb[dz]; }
+            }
+            u[qz] = a; ux[qz] = b; uy[qz] = c; uz[qz] = d;
+         }
+      }
+      // ---- point-wise D at the lane's five quadrature points (registers only)
+      #pragma unroll
+      for (int qz = 0; qz < Q; qz++)
+      {
+         mbar_wait(&bars[qz], parity);
+         const double *dp = ring + qz * slab + l3i;
+         double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;
+         int c = 0;
+         if (DIFF)
+         {
+            const double d0 = dp[0], d1 = dp[Q2], d2 = dp[2 * Q2], d3 = dp[3 * Q2], d4 = dp[4 * Q2], d5 = dp[5 * Q2];
+            fx = d0 * ux[qz] + d1 * uy[qz] + d2 * uz[qz];
+            fy = d1 * ux[qz] + d3 * uy[qz] + d4 * uz[qz];
+            fz = d2 * ux[qz] + d4 * uy[qz] + d5 * uz[qz];
+            c = 6;
+         }
+         if (CONV) { s = dp[c * Q2] * ux[qz] + dp[(c + 1) * Q2] * uy[qz] + dp[(c + 2) * Q2] * uz[qz]; c += 3; }
+         if (MASS) { s += dp[c * Q2] * u[qz]; }
+         ux[qz] = fx; uy[qz] = fy; uz[qz] = fz; u[qz] = s;
+      }
+      __syncwarp();                                          // D tile and the R buffers are consumed by every lane
+      if (lane == 0 && more)
+      {
+         #pragma unroll
+         for (int q = 0; q < Q; q++)
+         {
+            mbar_expect_tx(&bars[q], slab_bytes);
+            bulk_g2s(ring + q * slab, Dg + (en * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+         }
+      }
+      // ---- B1 (L3 lanes): transposed z contraction in registers
+      if (l3)
+      {
+         #pragma unroll
+         for (int dz = 0; dz < D; dz++)
+         {
+            double wx = 0.0, wy = 0.0, wb = 0.0;
+            #pragma unroll
+            for (int qz = 0; qz < Q; qz++)
+            {
+               wb += tb.B[qz * D + dz] * u[qz];
+               if (DIFF) { wx += tb.B[qz * D + dz] * ux[qz]; wy += tb.B[qz * D + dz] * uy[qz]; wb += tb.G[qz * D + dz] * uz[qz]; }
+            }
+            sR2[lane + 28 * dz] = wb;
+            if (DIFF) { sR0[lane + 28 * dz] = wx; sR1[lane + 28 * dz] = wy; }
+         }
+      }
+      __syncwarp();
+      // ---- B2 (L2 lanes): transposed y contraction
+      if (l2)
+      {
+         double wx[Q], wy[Q], wb[Q];
+         #pragma unroll
+         for (int q = 0; q < Q; q++)
+         {
+            wb[q] = sR2[qx2 + Q * q + 28 * dz2];
+            if (DIFF) { wx[q] = sR0[qx2 + Q * q + 28 * dz2]; wy[q] = sR1[qx2 + Q * q + 28 * dz2]; }
+         }
+         #pragma unroll
+         for (int dy = 0; dy < D; dy++)
+         {
+            double a1 = 0.0, a2 = 0.0;
+            #pragma unroll
+            for (int q = 0; q < Q; q++)
+            {
+               a2 += tb.B[q * D + dy] * wb[q];
+               if (DIFF) { a1 += tb.B[q * D + dy] * wx[q]; a2 += tb.G[q * D + dy] * wy[q]; }
+            }
+            sP1[qx2 + Q * dy + Q * D * dz2] = a2;
+            if (DIFF) { sP0[qx2 + Q * dy + Q * D * dz2] = a1; }
+         }
+      }
+      __syncwarp();
+      // ---- B3 (L1 lanes): transposed x contraction of the own x-line, scatter
+      if (l1)
+      {
+         double a1[Q], a2[Q], yv[D];
+         #pragma unroll
+         for (int q = 0; q < Q; q++) { a2[q] = sP1[q + Q * lane]; if (DIFF) { a1[q] = sP0[q + Q * lane]; } }
+         #pragma unroll
+         for (int dx = 0; dx < D; dx++)
+         {
+            double a = 0.0;
+            #pragma unroll
+            for (int q = 0; q < Q; q++) { a += tb.B[q * D + dx] * a2[q]; if (DIFF) { a += tb.G[q * D + dx] * a1[q]; } }
+            yv[dx] = a;
+         }
+         if (ATOMIC)
+         {
+            if (g.x >= 0) { red_add_f64(y + g.x, yv[0]); }
+            if (g.y >= 0) { red_add_f64(y + g.y, yv[1]); }
+            if (g.z >= 0) { red_add_f64(y + g.z, yv[2]); }
+            if (g.w >= 0) { red_add_f64(y + g.w, yv[3]); }
+         }
+         else
+         {
+            double2 *dst = reinterpret_cast<double2 *>(y + e * ND + D * lane);
+            dst[0] = make_double2(yv[0], yv[1]);
+            dst[1] = make_double2(yv[2], yv[3]);
+         }
+      }
+      __syncwarp();                                          // P buffers are rewritten by the next element's F1
+   }
+}
+
+template <int NW, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
+int launch_bg(cdm_op *op, const WarpTablesBG &tb, const int32_t *gmap, const double *xL, double *out)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   auto kern = k_apply3d_warp_bg<NW, DIFF, CONV, MASS, ATOMIC>;
+   const int warp_doubles = (5 * op->slab + 3 * 112 + 2 * 80 + 15) & ~15;
+   const size_t smem = (size_t)(NW * warp_doubles) * sizeof(double) + (size_t)NW * 5 * sizeof(uint64_t);
+   static size_t configured = 0;
+   static int blocks_per_sm = 0;
+   if (configured != smem)
+   {
+      CDM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CDM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NW * 32, smem));
+      if (blocks_per_sm < 1) { return cdm_fail(ctx, CDM_ECUDA, "k_apply3d_warp_bg does not fit on an SM"); }
+      configured = smem;
+   }
+   int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
+   const int64_t need = (sp->ne + NW - 1) / NW;
+   if (grid > need) { grid = need; }
+   if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }
+   kern<<<(unsigned)grid, NW * 32, smem, ctx->stream>>>(tb, sp->ne, gmap, xL, op->D_dev, op->slab, out);
+   if (ctx->time_main) { cudaEventRecord(ctx->evk1, ctx->stream); }
+   ctx->launches++;
+   CDM_CUDA(ctx, cudaGetLastError());
+   return CDM_OK;
+}
+
 // collocation derivative matrix on the Gauss points: Dq[i][k] = l_k'(x_i)
 void collocation_matrix(int q1d, const double *xq, double *Dq)
 {
@@ -326,13 +666,14 @@ void collocation_matrix(int q1d, const double *xq, double *Dq)
    }
 }
 
-template <int D, int Q, int NW, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
+template <int D, int Q, int NW, bool DIFF, bool CONV, bool MASS, bool ATOMIC, bool PH>
 int launch(cdm_op *op, const WarpTables &tb, const int32_t *gmap, const double *xL, double *out)
 {
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
-   auto kern = k_apply3d_warp<D, Q, NW, DIFF, CONV, MASS, ATOMIC>;
-   const int warp_doubles = (Q * op->slab + Q * Q * Q + 2 * 2 * Q * Q + (28 * (D - 1) + Q * Q + 3) + 15) & ~15;
+   auto kern = k_apply3d_warp<D, Q, NW, DIFF, CONV, MASS, ATOMIC, PH>;
+   const int warp_doubles = PH ? ((Q * op->slab + Q * Q * Q + 2 * Q * Q * Q + 15) & ~15)
+                               : ((Q * op->slab + Q * Q * Q + 2 * 2 * Q * Q + (28 * (D - 1) + Q * Q + 3) + 15) & ~15);
    const size_t smem = (size_t)(NW * warp_doubles) * sizeof(double) + (size_t)NW * Q * sizeof(uint64_t);
    static size_t configured = 0;
    static int blocks_per_sm = 0;
@@ -367,19 +708,16 @@ k_restrict_transpose_p3(int64_t ndof, const int32_t *__restrict__ offsets, const
 }  // namespace
 
 #define NWARPS 4
+#define DISPATCH_ONE(D_, Q_, DF, CV, MS)                                                                   \
+   rc = ph ? (atomic ? launch<D_, Q_, NWARPS, DF, CV, MS, true, true>(op, tb, gmap, xL, out)              \
+                     : launch<D_, Q_, NWARPS, DF, CV, MS, false, true>(op, tb, gmap, xL, out))            \
+           : (atomic ? launch<D_, Q_, NWARPS, DF, CV, MS, true, false>(op, tb, gmap, xL, out)             \
+                     : launch<D_, Q_, NWARPS, DF, CV, MS, false, false>(op, tb, gmap, xL, out))
 #define DISPATCH_FLAGS(D_, Q_)                                                                            \
-   if (op->has_diff && op->has_conv && op->has_mass)                                                      \
-      rc = atomic ? launch<D_, Q_, NWARPS, true, true, true, true>(op, tb, gmap, xL, out)                 \
-                  : launch<D_, Q_, NWARPS, true, true, true, false>(op, tb, gmap, xL, out);               \
-   else if (op->has_diff && !op->has_conv && op->has_mass)                                                \
-      rc = atomic ? launch<D_, Q_, NWARPS, true, false, true, true>(op, tb, gmap, xL, out)                \
-                  : launch<D_, Q_, NWARPS, true, false, true, false>(op, tb, gmap, xL, out);              \
-   else if (!op->has_diff && !op->has_conv && op->has_mass)                                               \
-      rc = atomic ? launch<D_, Q_, NWARPS, false, false, true, true>(op, tb, gmap, xL, out)               \
-                  : launch<D_, Q_, NWARPS, false, false, true, false>(op, tb, gmap, xL, out);             \
-   else if (op->has_diff && !op->has_conv && !op->has_mass)                                               \
-      rc = atomic ? launch<D_, Q_, NWARPS, true, false, false, true>(op, tb, gmap, xL, out)               \
-                  : launch<D_, Q_, NWARPS, true, false, false, false>(op, tb, gmap, xL, out);             \
+   if (op->has_diff && op->has_conv && op->has_mass) { DISPATCH_ONE(D_, Q_, true, true, true); }          \
+   else if (op->has_diff && !op->has_conv && op->has_mass) { DISPATCH_ONE(D_, Q_, true, false, true); }   \
+   else if (!op->has_diff && !op->has_conv && op->has_mass) { DISPATCH_ONE(D_, Q_, false, false, true); } \
+   else if (op->has_diff && !op->has_conv && !op->has_mass) { DISPATCH_ONE(D_, Q_, true, false, false); } \
    else { rc = 1; }
 
 // returns 1 when this operator is not covered (caller falls back to the generic kernel)
@@ -395,6 +733,7 @@ int cdm_k_apply_p3(cdm_op *op, const int32_t *gmap, const double *xL, double *yL
    for (int i = 0; i < sp->q1d * sp->d1d; i++) { tb.B[i] = sp->B[i]; }
    collocation_matrix(sp->q1d, sp->qx.data(), tb.Dq);
    const bool atomic = op->scatter_mode == 1;
+   const bool ph = op->kernel_variant >= 2;
    double *out = yL;
    if (atomic) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); }
    else
@@ -403,7 +742,25 @@ int cdm_k_apply_p3(cdm_op *op, const int32_t *gmap, const double *xL, double *yL
       out = op->yE_dev;
    }
    int rc = 0;
-   DISPATCH_FLAGS(4, 5)
+   if (op->kernel_variant >= 3)
+   {
+      WarpTablesBG tg;
+      memset(&tg, 0, sizeof(tg));
+      for (int i = 0; i < sp->q1d * sp->d1d; i++) { tg.B[i] = sp->B[i]; tg.G[i] = sp->G[i]; }
+#define BG_ONE(DF, CV, MS)                                                              \
+      rc = atomic ? launch_bg<NWARPS, DF, CV, MS, true>(op, tg, gmap, xL, out)          \
+                  : launch_bg<NWARPS, DF, CV, MS, false>(op, tg, gmap, xL, out)
+      if (op->has_diff && op->has_conv && op->has_mass) { BG_ONE(true, true, true); }
+      else if (op->has_diff && !op->has_conv && op->has_mass) { BG_ONE(true, false, true); }
+      else if (!op->has_diff && !op->has_conv && op->has_mass) { BG_ONE(false, false, true); }
+      else if (op->has_diff && !op->has_conv && !op->has_mass) { BG_ONE(true, false, false); }
+      else { rc = 1; }
+#undef BG_ONE
+   }
+   else
+   {
+      DISPATCH_FLAGS(4, 5)
+   }
    if (rc) { return rc; }
    if (!atomic)
    {

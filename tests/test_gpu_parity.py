@@ -108,7 +108,7 @@ def test_apply_matches_oracle(torch, ctx, orc, dim, p, n, scatter):
     assert rel(op.mult_host(x), yc) < 1e-13
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_p3_kernel_variants(torch, ctx, orc, variant):
     """3D order 3 (the headline configuration): generic kernel and the bulk-async kernel"""
     P, mesh, sp = make(ctx, orc, 3, 3, 5, perturb=0.12)
@@ -353,7 +353,7 @@ def test_golden_fixture(torch, ctx, orc):
         assert abs(D.down(dd).sum() - case["diag_sum"]) <= 1e-12 * abs(case["diag_sum"])
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3])
 def test_full_size_properties_config2(torch, ctx, kernel):
     """BASELINE config 2 size (66^3 hexes, order 3, 7 880 599 dofs): size-independent properties,
     no oracle needed: K 1 = 0, C 1 = 0, 1^T M 1 = volume, symmetry of K + M, linearity."""
