@@ -415,7 +415,9 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
    __syncwarp();
    const int64_t gw = (int64_t)blockIdx.x * NW + wib, tw = (int64_t)gridDim.x * NW;
    const uint32_t slab_bytes = (uint32_t)slab * 8u;
-   int4 pg = make_int4(-1, -1, -1, -1);
+   // gather pipeline: indices are fetched two elements ahead, values one element ahead, so that no
+   // load is consumed in the element that issued it
+   int4 pg = make_int4(-1, -1, -1, -1), pgn = make_int4(-1, -1, -1, -1);
    double px[D] = {0.0, 0.0, 0.0, 0.0};
    if (gw < ne)
    {
@@ -431,6 +433,7 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
       if (l1)
       {
          pg = __ldg(reinterpret_cast<const int4 *>(gmap + gw * ND) + lane);
+         if (gw + tw < ne) { pgn = __ldg(reinterpret_cast<const int4 *>(gmap + (gw + tw) * ND) + lane); }
          px[0] = (pg.x >= 0) ? __ldg(x + pg.x) : 0.0; px[1] = (pg.y >= 0) ? __ldg(x + pg.y) : 0.0;
          px[2] = (pg.z >= 0) ? __ldg(x + pg.z) : 0.0; px[3] = (pg.w >= 0) ? __ldg(x + pg.w) : 0.0;
       }
@@ -457,7 +460,8 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
       }
       if (more && l1)
       {
-         pg = __ldg(reinterpret_cast<const int4 *>(gmap + en * ND) + lane);
+         pg = pgn;                                           // indices of element en, loaded one element ago
+         if (en + tw < ne) { pgn = __ldg(reinterpret_cast<const int4 *>(gmap + (en + tw) * ND) + lane); }
          px[0] = (pg.x >= 0) ? __ldg(x + pg.x) : 0.0; px[1] = (pg.y >= 0) ? __ldg(x + pg.y) : 0.0;
          px[2] = (pg.z >= 0) ? __ldg(x + pg.z) : 0.0; px[3] = (pg.w >= 0) ? __ldg(x + pg.w) : 0.0;
       }
