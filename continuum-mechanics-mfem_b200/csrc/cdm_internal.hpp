@@ -163,6 +163,9 @@ int cdm_k_unpack_add_csr(cdm_ctx *c, int64_t n, const int32_t *dof, const int32_
 // k dots of w against V columns -> ctx->red_dev results [k] (device), deterministic
 int cdm_k_mdot_dev(cdm_ctx *c, int64_t n, int k, const double *w, const double *V, int64_t ldv,
                    double *out_dev);
+// w_out = dinv .* t fused with the k dots of w_out against V
+int cdm_k_mdot_pc_dev(cdm_ctx *c, int64_t n, int k, const double *t, const double *dinv, double *w_out,
+                      const double *V, int64_t ldv, double *out_dev);
 // w -= sum_i h_dev[i] V_i ; optionally also out_dev[0] = ||w_new||^2 partial-reduced
 int cdm_k_maxpy_dev(cdm_ctx *c, int64_t n, int k, const double *h_dev, const double *V, int64_t ldv,
                     double *w, double *norm2_out_dev);

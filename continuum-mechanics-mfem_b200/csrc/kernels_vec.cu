@@ -117,31 +117,90 @@ int cdm_k_unpack(cdm_ctx *c, int64_t n, const int32_t *idx, const double *buf, d
 // ------------------------------------------------------------ reductions
 // stage 1: per-block partials, partial[j * CDM_RED_BLOCKS + block]
 // stage 2: one block per result sums its CDM_RED_BLOCKS partials in a fixed order
+// Streaming kernels use 128-bit loads and keep KB+1 (or more) independent loads in flight per
+// thread; the launch shape is fixed, so every result is bit-reproducible.
 
-template <int KB>
+__device__ __forceinline__ double2 ld2(const double *p, int64_t i2) { return reinterpret_cast<const double2 *>(p)[i2]; }
+__device__ __forceinline__ void st2(double *p, int64_t i2, double2 v) { reinterpret_cast<double2 *>(p)[i2] = v; }
+
+// KB dot products of w against V_0..V_{KB-1} (KB is exact: no predicates in the steady state).
+// PC: w = dinv .* t is formed on the fly (Jacobi preconditioner fused into the first pass) and
+// written to w_out.  VEC: all pointers 16-byte aligned and ldv even -> double2 path, where a block
+// walks over tiles of 2*UNROLL*blockDim consecutive doubles of every vector.
+template <int KB, int UNROLL, bool PC, bool VEC>
 __global__ void __launch_bounds__(CDM_RED_THREADS)
-k_mdot_partial(int64_t n, int kb, const double *__restrict__ w, const double *__restrict__ V, int64_t ldv,
+k_mdot_partial(int64_t n, const double *__restrict__ w, const double *__restrict__ dinv,
+               double *__restrict__ w_out, const double *__restrict__ V, int64_t ldv,
                double *__restrict__ partial)
 {
    __shared__ double red[8];
    double acc[KB];
    #pragma unroll
    for (int j = 0; j < KB; j++) { acc[j] = 0.0; }
-   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+   if (VEC)
    {
-      const double wv = w[i];
-      #pragma unroll
-      for (int j = 0; j < KB; j++) if (j < kb) { acc[j] += wv * V[j * ldv + i]; }
+      const int64_t n2 = n >> 1;
+      const int64_t tile = (int64_t)UNROLL * blockDim.x;               // in double2 units
+      const int64_t nfull = n2 / tile;
+      for (int64_t t = blockIdx.x; t < nfull; t += gridDim.x)
+      {
+         const int64_t base = t * tile + threadIdx.x;
+         double2 wv[UNROLL];
+         #pragma unroll
+         for (int u = 0; u < UNROLL; u++)
+         {
+            wv[u] = ld2(w, base + u * blockDim.x);
+            if (PC) { const double2 d = ld2(dinv, base + u * blockDim.x); wv[u].x *= d.x; wv[u].y *= d.y; st2(w_out, base + u * blockDim.x, wv[u]); }
+         }
+         double2 v[KB][UNROLL];
+         #pragma unroll
+         for (int j = 0; j < KB; j++)
+         {
+            #pragma unroll
+            for (int u = 0; u < UNROLL; u++) { v[j][u] = ld2(V + j * ldv, base + u * blockDim.x); }
+         }
+         #pragma unroll
+         for (int j = 0; j < KB; j++)
+         {
+            #pragma unroll
+            for (int u = 0; u < UNROLL; u++) { acc[j] += wv[u].x * v[j][u].x + wv[u].y * v[j][u].y; }
+         }
+      }
+      // tail (fewer than one tile of double2 plus possibly one odd double): last block only
+      if (blockIdx.x == gridDim.x - 1)
+      {
+         for (int64_t i = nfull * tile + threadIdx.x; i < n2; i += blockDim.x)
+         {
+            double2 wv = ld2(w, i);
+            if (PC) { const double2 d = ld2(dinv, i); wv.x *= d.x; wv.y *= d.y; st2(w_out, i, wv); }
+            #pragma unroll
+            for (int j = 0; j < KB; j++) { const double2 vv = ld2(V + j * ldv, i); acc[j] += wv.x * vv.x + wv.y * vv.y; }
+         }
+         if ((n & 1) && threadIdx.x == 0)
+         {
+            double wl = w[n - 1];
+            if (PC) { wl *= dinv[n - 1]; w_out[n - 1] = wl; }
+            #pragma unroll
+            for (int j = 0; j < KB; j++) { acc[j] += wl * V[j * ldv + n - 1]; }
+         }
+      }
+   }
+   else
+   {
+      const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+      for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      {
+         double wv = w[i];
+         if (PC) { wv *= dinv[i]; w_out[i] = wv; }
+         #pragma unroll
+         for (int j = 0; j < KB; j++) { acc[j] += wv * V[j * ldv + i]; }
+      }
    }
    #pragma unroll
    for (int j = 0; j < KB; j++)
    {
-      if (j < kb)
-      {
-         const double s = block_sum(acc[j], red);
-         if (threadIdx.x == 0) { partial[(int64_t)j * CDM_RED_BLOCKS + blockIdx.x] = s; }
-      }
+      const double s = block_sum(acc[j], red);
+      if (threadIdx.x == 0) { partial[(int64_t)j * CDM_RED_BLOCKS + blockIdx.x] = s; }
    }
 }
 
@@ -156,22 +215,51 @@ k_reduce_final(const double *__restrict__ partial, double *__restrict__ out)
    if (threadIdx.x == 0) { out[blockIdx.x] = s; }
 }
 
-int cdm_k_mdot_dev(cdm_ctx *c, int64_t n, int k, const double *w, const double *V, int64_t ldv, double *out_dev)
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int KB, bool PC>
+static void mdot_one(cdm_ctx *c, bool vec, int64_t n, const double *win, const double *dinv, double *w_out,
+                     const double *Vj, int64_t ldv, double *pj)
+{
+   if (vec) { k_mdot_partial<KB, (KB <= 4 ? 4 : 2), PC, true><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, win, dinv, w_out, Vj, ldv, pj); }
+   else { k_mdot_partial<KB, 1, PC, false><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, win, dinv, w_out, Vj, ldv, pj); }
+}
+
+template <bool PC>
+static int mdot_launch(cdm_ctx *c, int64_t n, int k, const double *w, const double *dinv, double *w_out,
+                       const double *V, int64_t ldv, double *out_dev)
 {
    if (k < 1 || k > CDM_RED_MAXK) { return cdm_fail(c, CDM_EINVAL, "mdot: k out of range"); }
    double *partial = c->red_dev;
+   const bool vec = aligned16(w) && aligned16(V) && (ldv % 2 == 0) && (!PC || (aligned16(dinv) && aligned16(w_out)));
    for (int j0 = 0; j0 < k; j0 += 8)
    {
       const int kb = (k - j0 < 8) ? k - j0 : 8;
-      k_mdot_partial<8><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(
-         n, kb, w, V + (int64_t)j0 * ldv, ldv, partial + (int64_t)j0 * CDM_RED_BLOCKS);
+      const double *Vj = V + (int64_t)j0 * ldv;
+      double *pj = partial + (int64_t)j0 * CDM_RED_BLOCKS;
+      // the preconditioner is applied (and w_out written) by the first pass only
+      const bool first = PC && j0 == 0;
+      const double *win = (PC && !first) ? w_out : w;
+#define MDOT_CASE(KB) case KB: if (first) { mdot_one<KB, true>(c, vec, n, win, dinv, w_out, Vj, ldv, pj); } \
+                               else { mdot_one<KB, false>(c, vec, n, win, dinv, w_out, Vj, ldv, pj); } break
+      switch (kb) { MDOT_CASE(1); MDOT_CASE(2); MDOT_CASE(3); MDOT_CASE(4); MDOT_CASE(5); MDOT_CASE(6); MDOT_CASE(7); MDOT_CASE(8); }
+#undef MDOT_CASE
       c->launches++;
    }
    k_reduce_final<<<k, CDM_RED_THREADS, 0, c->stream>>>(partial, out_dev);
    VEC_CHECK(c);
 }
 
+int cdm_k_mdot_dev(cdm_ctx *c, int64_t n, int k, const double *w, const double *V, int64_t ldv, double *out_dev)
+{ return mdot_launch<false>(c, n, k, w, nullptr, nullptr, V, ldv, out_dev); }
+
+// w_out = dinv .* t, then k dots of w_out against V (one pass over t, dinv and the first 16 basis vectors)
+int cdm_k_mdot_pc_dev(cdm_ctx *c, int64_t n, int k, const double *t, const double *dinv, double *w_out,
+                      const double *V, int64_t ldv, double *out_dev)
+{ return mdot_launch<true>(c, n, k, t, dinv, w_out, V, ldv, out_dev); }
+
 // w -= sum_j h[j] V_j, and the partial sums of ||w_new||^2
+template <bool VEC>
 __global__ void __launch_bounds__(CDM_RED_THREADS)
 k_maxpy_norm(int64_t n, int k, const double *__restrict__ h, const double *__restrict__ V, int64_t ldv,
              double *__restrict__ w, double *__restrict__ partial)
@@ -182,12 +270,52 @@ k_maxpy_norm(int64_t n, int k, const double *__restrict__ h, const double *__res
    __syncthreads();
    double acc = 0.0;
    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (VEC)
    {
-      double v = w[i];
-      for (int j = 0; j < k; j++) { v -= sh[j] * V[j * ldv + i]; }
-      w[i] = v;
-      acc += v * v;
+      const int64_t n2 = n >> 1;
+      for (int64_t i = gid; i < n2; i += stride)
+      {
+         double2 v = ld2(w, i);
+         int j0 = 0;
+         for (; j0 + 8 <= k; j0 += 8)                         // full groups: 8 independent loads in flight
+         {
+            double2 t[8];
+            #pragma unroll
+            for (int j = 0; j < 8; j++) { t[j] = ld2(V + (j0 + j) * ldv, i); }
+            #pragma unroll
+            for (int j = 0; j < 8; j++) { v.x -= sh[j0 + j] * t[j].x; v.y -= sh[j0 + j] * t[j].y; }
+         }
+         if (j0 + 4 <= k)
+         {
+            double2 t[4];
+            #pragma unroll
+            for (int j = 0; j < 4; j++) { t[j] = ld2(V + (j0 + j) * ldv, i); }
+            #pragma unroll
+            for (int j = 0; j < 4; j++) { v.x -= sh[j0 + j] * t[j].x; v.y -= sh[j0 + j] * t[j].y; }
+            j0 += 4;
+         }
+         for (; j0 < k; j0++) { const double2 t = ld2(V + j0 * ldv, i); v.x -= sh[j0] * t.x; v.y -= sh[j0] * t.y; }
+         st2(w, i, v);
+         acc += v.x * v.x + v.y * v.y;
+      }
+      if ((n & 1) && gid == 0)
+      {
+         double v = w[n - 1];
+         for (int j = 0; j < k; j++) { v -= sh[j] * V[j * ldv + n - 1]; }
+         w[n - 1] = v;
+         acc += v * v;
+      }
+   }
+   else
+   {
+      for (int64_t i = gid; i < n; i += stride)
+      {
+         double v = w[i];
+         for (int j = 0; j < k; j++) { v -= sh[j] * V[j * ldv + i]; }
+         w[i] = v;
+         acc += v * v;
+      }
    }
    if (partial)
    {
@@ -200,8 +328,11 @@ int cdm_k_maxpy_dev(cdm_ctx *c, int64_t n, int k, const double *h_dev, const dou
                     double *w, double *norm2_out_dev)
 {
    if (k < 0 || k > CDM_RED_MAXK) { return cdm_fail(c, CDM_EINVAL, "maxpy: k out of range"); }
-   k_maxpy_norm<<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, k, h_dev, V, ldv, w,
-                                                                  norm2_out_dev ? c->red_dev : nullptr);
+   double *partial = norm2_out_dev ? c->red_dev : nullptr;
+   if (aligned16(w) && aligned16(V) && (ldv % 2 == 0))
+      k_maxpy_norm<true><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, k, h_dev, V, ldv, w, partial);
+   else
+      k_maxpy_norm<false><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, k, h_dev, V, ldv, w, partial);
    c->launches++;
    if (norm2_out_dev)
    {

@@ -109,11 +109,13 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
       {
          double *vj = V + (int64_t)j * ld, *vn = V + (int64_t)(j + 1) * ld;
          RC(cdm_apply_tail(op, vj, dinv ? t : w, true));
-         if (dinv) { RC(cdm_k_pmult(c, n, dinv, t, w)); }
+         if (dinv && o->variant != CDM_GMRES_PETSC) { RC(cdm_k_pmult(c, n, dinv, t, w)); }
          if (o->variant == CDM_GMRES_PETSC)
          {
-            // classical Gram-Schmidt: all j+1 dots against the same w, one all-reduce
-            RC(cdm_k_mdot_dev(c, n, j + 1, w, V, ld, h_dev));
+            // classical Gram-Schmidt: all j+1 dots against the same w, one all-reduce; the Jacobi
+            // scaling w = dinv .* (A v_j) is fused into the first pass of the multi-dot
+            if (dinv) { RC(cdm_k_mdot_pc_dev(c, n, j + 1, t, dinv, w, V, ld, h_dev)); }
+            else { RC(cdm_k_mdot_dev(c, n, j + 1, w, V, ld, h_dev)); }
             RC(cdm_allreduce_sum(c, h_dev, j + 1));
             RC(cdm_k_maxpy_dev(c, n, j + 1, h_dev, V, ld, w, h_dev + (j + 1)));
          }
