@@ -493,7 +493,9 @@ int cdm_operator_create(cdm_space *sp, const cdm_coeff *kappa, const cdm_coeff *
       rc = cdm_k_setup_qdata(op, kappa, vel, conv_alpha, mass);
    } while (0);
    if (rc) { cdm_operator_destroy(op); return rc; }
-   op->kernel_variant = (sp->dim == 3 && sp->p == 3) ? 3 : 0;
+   // default kernel per order (measured, profiles/): p=3 hand-specialised register-z kernel,
+   // p>=4 the generic group kernel, p<=2 and 2D the block kernel
+   op->kernel_variant = (sp->dim == 3 && sp->p == 3) ? 3 : ((sp->dim == 3 && sp->p >= 4) ? 4 : 0);
    *out = op;
    return CDM_OK;
 }

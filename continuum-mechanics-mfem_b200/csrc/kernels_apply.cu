@@ -515,6 +515,7 @@ static int ensure_yE(cdm_op *op)
 }
 
 int cdm_k_apply_p3(cdm_op *op, const int32_t *gmap, const double *xL, double *yL);   // kernels_apply_p3.cu
+int cdm_k_apply_group(cdm_op *op, const int32_t *gmap, const double *xL, double *yL);   // kernels_apply_warp.cu
 
 #define LAUNCH3D(P, NBZ)                                                                              \
    case P: {                                                                                          \
@@ -537,7 +538,12 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
    const int32_t *gmap = (constrained && op->gather_c_dev) ? op->gather_c_dev : sp->gather_dev;
-   if (sp->dim == 3 && sp->p == 3 && op->kernel_variant >= 1)
+   if (sp->dim == 3 && op->kernel_variant == 4)
+   {
+      const int rc = cdm_k_apply_group(op, gmap, xL, yL);
+      if (rc != 1) { return rc; }
+   }
+   else if (sp->dim == 3 && sp->p == 3 && op->kernel_variant >= 1)
    {
       const int rc = cdm_k_apply_p3(op, gmap, xL, yL);
       if (rc != 1) { return rc; }          // 1: integrator combination not instantiated -> generic kernel

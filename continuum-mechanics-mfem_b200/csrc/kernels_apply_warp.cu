@@ -1,0 +1,413 @@
+// kernels_apply_warp.cu -- the register-z / bulk-async apply kernel of kernels_apply_p3.cu
+// generalised to every order p = 1..6 in 3D (kernel option 4).
+//
+// One *group* of T = Q1D^2 threads owns one element at a time:
+//   p = 1 : T =  9, three groups per warp        p = 4 : T = 36, two warps per group
+//   p = 2 : T = 16, two groups per warp          p = 5 : T = 49, two warps per group
+//   p = 3 : T = 25, one group per warp           p = 6 : T = 64, two warps per group
+// Sub-warp groups synchronise with __syncwarp, two-warp groups with a named barrier
+// (bar.sync id, 64).  Everything else is the design documented in kernels_apply_p3.cu:
+// quadrature data streamed by cp.async.bulk into a per-group ring of Q1D z-slabs guarded by
+// mbarriers, x / y contractions through two conflict-aware exchange buffers with constant-bank
+// coefficients, z contraction + point-wise D + transposed z contraction in registers,
+// two-level gather prefetch, fp64 red.add scatter (or E-vector stores).
+#include "cdm_internal.hpp"
+#include "kernels_common.cuh"
+
+namespace
+{
+struct GroupTables
+{
+   double B[CDM_MAX_Q1D * CDM_MAX_D1D];
+   double G[CDM_MAX_Q1D * CDM_MAX_D1D];
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_init(uint64_t *bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void g_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void g_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+   asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra GDONE_%=;\n"
+      "bra GWAIT_%=;\n"
+      "GDONE_%=:\n"
+      "}\n" ::"r"(s_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void g_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void g_red_add(double *addr, double v)
+{ asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory"); }
+
+template <int P> struct GroupCfg
+{
+   static constexpr int D = P + 1, Q = P + 2, T = Q * Q, ND = D * D * D;
+   static constexpr int EPW = (T <= 10) ? 3 : (T <= 16 ? 2 : 1);   // groups per warp
+   static constexpr int WPG = (T <= 32) ? 1 : 2;                   // warps per group
+   static constexpr int GPB = (P <= 3) ? 4 * EPW : (P == 4 ? 2 : 1);   // groups per block
+   static constexpr int THREADS = (WPG == 1) ? 32 * (GPB / EPW) : 64 * GPB;
+   static constexpr int MINB = (P <= 4) ? 4 : (P == 5 ? 5 : 3);        // resident blocks per SM the register budget is sized for
+   static constexpr int RSTR = (P == 3) ? 28 : (Q * Q + ((Q * Q) % 2 == 0 ? 1 : 2));   // dz stride of the R layout
+   static constexpr int RS = ((D - 1) * RSTR + Q * Q + 1) & ~1;
+   static constexpr int PS = (Q * D * D + 1) & ~1;
+};
+
+template <int P, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
+__global__ void __launch_bounds__(GroupCfg<P>::THREADS, GroupCfg<P>::MINB)
+k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restrict__ gmap,
+                const double *__restrict__ x, const double *__restrict__ Dg, const int slab,
+                double *__restrict__ y)
+{
+   using C = GroupCfg<P>;
+   constexpr int D = C::D, Q = C::Q, T = C::T, ND = C::ND, Q2 = Q * Q;
+   constexpr int RS = C::RS, PS = C::PS, RSTR = C::RSTR;
+   constexpr bool GRAD = DIFF || CONV;
+   extern __shared__ __align__(128) unsigned char smraw[];
+   const int group_doubles = (Q * slab + 3 * RS + 2 * PS + 1) & ~1;
+   // ---- which group am I, which thread of the group
+   int gib, t;                                               // group in block, thread in group
+   if (C::WPG == 1)
+   {
+      const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+      const int sub = lane / T;
+      gib = (sub < C::EPW) ? wib * C::EPW + sub : -1;
+      t = lane - sub * T;
+   }
+   else { gib = threadIdx.x >> 6; t = threadIdx.x & 63; }
+   const bool member = gib >= 0 && t < T;
+   const int gsafe = gib >= 0 ? gib : 0;
+   double *gbase = reinterpret_cast<double *>(smraw) + gsafe * group_doubles;
+   uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smraw) + C::GPB * group_doubles) + gsafe * Q;
+   double *ring = gbase, *sR0 = ring + Q * slab, *sR1 = sR0 + RS, *sR2 = sR1 + RS, *sP0 = sR2 + RS, *sP1 = sP0 + PS;
+   const bool l1 = member && t < D * D, l2 = member && t < Q * D;
+   const int t3 = member ? t : 0;                                      // L3 role: (qx,qy) = t
+   const int qx2 = l2 ? t / D : 0, dz2 = l2 ? t % D : 0;               // L2 role
+   const int t1 = l1 ? t : 0;                                          // L1 role: x-line index dy + D*dz
+   auto gsync = [&]()
+   {
+      if (C::WPG == 1) { __syncwarp(); }
+      else { asm volatile("bar.sync %0, 64;" ::"r"(gsafe + 1) : "memory"); }
+   };
+
+   if (member && t == 0)
+   {
+      for (int q = 0; q < Q; q++) { g_mbar_init(&bars[q], 1); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+   }
+   gsync();
+   const int64_t ngroups = (int64_t)gridDim.x * C::GPB;
+   const int64_t gg = (int64_t)blockIdx.x * C::GPB + gsafe;
+   // every group of a warp runs the same number of rounds (the lowest group of the block needs the most)
+   const int64_t g0 = (int64_t)blockIdx.x * C::GPB;
+   const int64_t rounds = (g0 < ne) ? (ne - g0 + ngroups - 1) / ngroups : 0;
+   const uint32_t slab_bytes = (uint32_t)slab * 8u;
+
+   // gather pipeline: indices two elements ahead, values one element ahead
+   int32_t pg[D], pgn[D];
+   double px[D];
+   #pragma unroll
+   for (int i = 0; i < D; i++) { pg[i] = -1; pgn[i] = -1; px[i] = 0.0; }
+   if (gib >= 0 && gg < ne)
+   {
+      if (member && t == 0)
+      {
+         for (int q = 0; q < Q; q++)
+         {
+            g_mbar_expect_tx(&bars[q], slab_bytes);
+            g_bulk_g2s(ring + q * slab, Dg + (gg * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+         }
+      }
+      if (l1)
+      {
+         #pragma unroll
+         for (int i = 0; i < D; i++) { pg[i] = __ldg(gmap + gg * ND + D * t1 + i); }
+         if (gg + ngroups < ne)
+         {
+            #pragma unroll
+            for (int i = 0; i < D; i++) { pgn[i] = __ldg(gmap + (gg + ngroups) * ND + D * t1 + i); }
+         }
+         #pragma unroll
+         for (int i = 0; i < D; i++) { px[i] = (pg[i] >= 0) ? __ldg(x + pg[i]) : 0.0; }
+      }
+   }
+
+   uint32_t parity = 0;
+   for (int64_t r = 0; r < rounds; r++, parity ^= 1u)
+   {
+      const int64_t e = gg + r * ngroups;
+      const bool valid = gib >= 0 && e < ne;
+      const int64_t en = e + ngroups;
+      const bool more = gib >= 0 && en < ne;
+      int32_t g[D];
+      #pragma unroll
+      for (int i = 0; i < D; i++) { g[i] = pg[i]; }
+      // ---- F1 (L1 threads): x contraction of the own x-line with B and G
+      if (l1 && valid)
+      {
+         #pragma unroll
+         for (int q = 0; q < Q; q++)
+         {
+            double tB = 0.0, tG = 0.0;
+            #pragma unroll
+            for (int d = 0; d < D; d++) { tB += tb.B[q * D + d] * px[d]; if (GRAD) { tG += tb.G[q * D + d] * px[d]; } }
+            sP0[q + Q * t1] = tB;
+            if (GRAD) { sP1[q + Q * t1] = tG; }
+         }
+      }
+      if (l1 && more)
+      {
+         #pragma unroll
+         for (int i = 0; i < D; i++) { pg[i] = pgn[i]; }
+         if (en + ngroups < ne)
+         {
+            #pragma unroll
+            for (int i = 0; i < D; i++) { pgn[i] = __ldg(gmap + (en + ngroups) * ND + D * t1 + i); }
+         }
+         #pragma unroll
+         for (int i = 0; i < D; i++) { px[i] = (pg[i] >= 0) ? __ldg(x + pg[i]) : 0.0; }
+      }
+      gsync();
+      // ---- F2 (L2 threads): y contraction -> (B B), (G B), (B G)
+      if (l2 && valid)
+      {
+         double tB[D], tG[D];
+         #pragma unroll
+         for (int dy = 0; dy < D; dy++)
+         {
+            tB[dy] = sP0[qx2 + Q * (dy + D * dz2)];
+            if (GRAD) { tG[dy] = sP1[qx2 + Q * (dy + D * dz2)]; }
+         }
+         #pragma unroll
+         for (int q = 0; q < Q; q++)
+         {
+            double vbb = 0.0, vgb = 0.0, vbg = 0.0;
+            #pragma unroll
+            for (int dy = 0; dy < D; dy++)
+            {
+               vbb += tb.B[q * D + dy] * tB[dy];
+               if (GRAD) { vgb += tb.B[q * D + dy] * tG[dy]; vbg += tb.G[q * D + dy] * tB[dy]; }
+            }
+            sR0[qx2 + Q * q + RSTR * dz2] = vbb;
+            if (GRAD) { sR1[qx2 + Q * q + RSTR * dz2] = vgb; sR2[qx2 + Q * q + RSTR * dz2] = vbg; }
+         }
+      }
+      gsync();
+      // ---- F3 (L3 threads): z contraction in registers
+      double u[Q], ux[Q], uy[Q], uz[Q];
+      {
+         double vbb[D], vgb[D], vbg[D];
+         #pragma unroll
+         for (int dz = 0; dz < D; dz++)
+         {
+            vbb[dz] = sR0[t3 + RSTR * dz];
+            if (GRAD) { vgb[dz] = sR1[t3 + RSTR * dz]; vbg[dz] = sR2[t3 + RSTR * dz]; }
+         }
+         #pragma unroll
+         for (int qz = 0; qz < Q; qz++)
+         {
+            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+            #pragma unroll
+            for (int dz = 0; dz < D; dz++)
+            {
+               a += tb.B[qz * D + dz] * vbb[dz];
+               if (GRAD) { b += tb.B[qz * D + dz] * vgb[dz]; c += tb.B[qz * D + dz] * vbg[dz]; d += tb.G[qz * D + dz] * vbb[dz]; }
+            }
+            u[qz] = a; ux[qz] = b; uy[qz] = c; uz[qz] = d;
+         }
+      }
+      // ---- point-wise D at the thread's Q quadrature points (registers only)
+      if (valid)
+      {
+         #pragma unroll
+         for (int qz = 0; qz < Q; qz++)
+         {
+            g_mbar_wait(&bars[qz], parity);
+            const double *dp = ring + qz * slab + t3;
+            double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;
+            int c = 0;
+            if (DIFF)
+            {
+               const double d0 = dp[0], d1 = dp[Q2], d2 = dp[2 * Q2], d3 = dp[3 * Q2], d4 = dp[4 * Q2], d5 = dp[5 * Q2];
+               fx = d0 * ux[qz] + d1 * uy[qz] + d2 * uz[qz];
+               fy = d1 * ux[qz] + d3 * uy[qz] + d4 * uz[qz];
+               fz = d2 * ux[qz] + d4 * uy[qz] + d5 * uz[qz];
+               c = 6;
+            }
+            if (CONV) { s = dp[c * Q2] * ux[qz] + dp[(c + 1) * Q2] * uy[qz] + dp[(c + 2) * Q2] * uz[qz]; c += 3; }
+            if (MASS) { s += dp[c * Q2] * u[qz]; }
+            ux[qz] = fx; uy[qz] = fy; uz[qz] = fz; u[qz] = s;
+         }
+      }
+      gsync();                                               // D tile and the R buffers are consumed
+      if (member && t == 0 && more)
+      {
+         for (int q = 0; q < Q; q++)
+         {
+            g_mbar_expect_tx(&bars[q], slab_bytes);
+            g_bulk_g2s(ring + q * slab, Dg + (en * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+         }
+      }
+      // ---- B1 (L3 threads): transposed z contraction in registers
+      if (member && valid)
+      {
+         #pragma unroll
+         for (int dz = 0; dz < D; dz++)
+         {
+            double wx = 0.0, wy = 0.0, wb = 0.0;
+            #pragma unroll
+            for (int qz = 0; qz < Q; qz++)
+            {
+               wb += tb.B[qz * D + dz] * u[qz];
+               if (DIFF) { wx += tb.B[qz * D + dz] * ux[qz]; wy += tb.B[qz * D + dz] * uy[qz]; wb += tb.G[qz * D + dz] * uz[qz]; }
+            }
+            sR2[t3 + RSTR * dz] = wb;
+            if (DIFF) { sR0[t3 + RSTR * dz] = wx; sR1[t3 + RSTR * dz] = wy; }
+         }
+      }
+      gsync();
+      // ---- B2 (L2 threads): transposed y contraction
+      if (l2 && valid)
+      {
+         double wx[Q], wy[Q], wb[Q];
+         #pragma unroll
+         for (int q = 0; q < Q; q++)
+         {
+            wb[q] = sR2[qx2 + Q * q + RSTR * dz2];
+            if (DIFF) { wx[q] = sR0[qx2 + Q * q + RSTR * dz2]; wy[q] = sR1[qx2 + Q * q + RSTR * dz2]; }
+         }
+         #pragma unroll
+         for (int dy = 0; dy < D; dy++)
+         {
+            double a1 = 0.0, a2 = 0.0;
+            #pragma unroll
+            for (int q = 0; q < Q; q++)
+            {
+               a2 += tb.B[q * D + dy] * wb[q];
+               if (DIFF) { a1 += tb.B[q * D + dy] * wx[q]; a2 += tb.G[q * D + dy] * wy[q]; }
+            }
+            sP1[qx2 + Q * (dy + D * dz2)] = a2;
+            if (DIFF) { sP0[qx2 + Q * (dy + D * dz2)] = a1; }
+         }
+      }
+      gsync();
+      // ---- B3 (L1 threads): transposed x contraction of the own x-line, scatter
+      if (l1 && valid)
+      {
+         double a1[Q], a2[Q];
+         #pragma unroll
+         for (int q = 0; q < Q; q++) { a2[q] = sP1[q + Q * t1]; if (DIFF) { a1[q] = sP0[q + Q * t1]; } }
+         #pragma unroll
+         for (int dx = 0; dx < D; dx++)
+         {
+            double a = 0.0;
+            #pragma unroll
+            for (int q = 0; q < Q; q++) { a += tb.B[q * D + dx] * a2[q]; if (DIFF) { a += tb.G[q * D + dx] * a1[q]; } }
+            if (ATOMIC) { if (g[dx] >= 0) { g_red_add(y + g[dx], a); } }
+            else { y[e * ND + D * t1 + dx] = a; }
+         }
+      }
+      gsync();                                               // P buffers are rewritten by the next round's F1
+   }
+}
+
+template <int P, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
+int launch_group(cdm_op *op, const GroupTables &tb, const int32_t *gmap, const double *xL, double *out)
+{
+   using C = GroupCfg<P>;
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   auto kern = k_apply3d_group<P, DIFF, CONV, MASS, ATOMIC>;
+   const int group_doubles = (C::Q * op->slab + 3 * C::RS + 2 * C::PS + 1) & ~1;
+   const size_t smem = (size_t)C::GPB * group_doubles * sizeof(double) + (size_t)C::GPB * C::Q * sizeof(uint64_t);
+   static size_t configured = 0;
+   static int blocks_per_sm = 0;
+   if (configured != smem)
+   {
+      CDM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CDM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, C::THREADS, smem));
+      if (blocks_per_sm < 1) { return cdm_fail(ctx, CDM_ECUDA, "k_apply3d_group does not fit on an SM"); }
+      configured = smem;
+   }
+   int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
+   const int64_t need = (sp->ne + C::GPB - 1) / C::GPB;
+   if (grid > need) { grid = need; }
+   if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }
+   kern<<<(unsigned)grid, C::THREADS, smem, ctx->stream>>>(tb, sp->ne, gmap, xL, op->D_dev, op->slab, out);
+   if (ctx->time_main) { cudaEventRecord(ctx->evk1, ctx->stream); }
+   ctx->launches++;
+   CDM_CUDA(ctx, cudaGetLastError());
+   return CDM_OK;
+}
+
+template <int P>
+int dispatch_order(cdm_op *op, const GroupTables &tb, const int32_t *gmap, const double *xL, double *out, bool atomic)
+{
+#define GRP_ONE(DF, CV, MS) (atomic ? launch_group<P, DF, CV, MS, true>(op, tb, gmap, xL, out) \
+                                    : launch_group<P, DF, CV, MS, false>(op, tb, gmap, xL, out))
+   if (op->has_diff && op->has_conv && op->has_mass) { return GRP_ONE(true, true, true); }
+   if (op->has_diff && !op->has_conv && op->has_mass) { return GRP_ONE(true, false, true); }
+   if (!op->has_diff && !op->has_conv && op->has_mass) { return GRP_ONE(false, false, true); }
+   if (op->has_diff && !op->has_conv && !op->has_mass) { return GRP_ONE(true, false, false); }
+#undef GRP_ONE
+   return 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_restrict_transpose_g(int64_t ndof, const int32_t *__restrict__ offsets, const int32_t *__restrict__ indices,
+                       const double *__restrict__ yE, double *__restrict__ yL)
+{
+   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (g >= ndof) { return; }
+   double s = 0.0;
+   for (int32_t j = offsets[g]; j < offsets[g + 1]; j++) { s += yE[indices[j]]; }
+   yL[g] = s;
+}
+}  // namespace
+
+// returns 1 when this operator is not covered (caller falls back to the generic kernel)
+int cdm_k_apply_group(cdm_op *op, const int32_t *gmap, const double *xL, double *yL)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   if (sp->dim != 3 || sp->p < 1 || sp->p > 6) { return 1; }
+   if (op->has_conv && !(op->has_diff && op->has_mass)) { return 1; }
+   if (!op->has_diff && !op->has_mass) { return 1; }
+   GroupTables tb;
+   memset(&tb, 0, sizeof(tb));
+   for (int i = 0; i < sp->q1d * sp->d1d; i++) { tb.B[i] = sp->B[i]; tb.G[i] = sp->G[i]; }
+   const bool atomic = op->scatter_mode == 1;
+   double *out = yL;
+   if (atomic) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); }
+   else
+   {
+      if (!op->yE_dev) { CDM_CUDA(ctx, cudaMalloc(&op->yE_dev, sizeof(double) * (size_t)sp->ne * sp->nd)); }
+      out = op->yE_dev;
+   }
+   int rc = 1;
+   switch (sp->p)
+   {
+      case 1: rc = dispatch_order<1>(op, tb, gmap, xL, out, atomic); break;
+      case 2: rc = dispatch_order<2>(op, tb, gmap, xL, out, atomic); break;
+      case 3: rc = dispatch_order<3>(op, tb, gmap, xL, out, atomic); break;
+      case 4: rc = dispatch_order<4>(op, tb, gmap, xL, out, atomic); break;
+      case 5: rc = dispatch_order<5>(op, tb, gmap, xL, out, atomic); break;
+      case 6: rc = dispatch_order<6>(op, tb, gmap, xL, out, atomic); break;
+   }
+   if (rc) { return rc; }
+   if (!atomic)
+   {
+      const unsigned nb = (unsigned)((sp->ndof + 255) / 256);
+      k_restrict_transpose_g<<<nb, 256, 0, ctx->stream>>>(sp->ndof, sp->offsets_dev, sp->indices_dev, op->yE_dev, yL);
+      ctx->launches++;
+      CDM_CUDA(ctx, cudaGetLastError());
+   }
+   return CDM_OK;
+}

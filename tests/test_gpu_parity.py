@@ -125,6 +125,27 @@ def test_p3_kernel_variants(torch, ctx, orc, variant):
         assert rel(D.down(yd), P.pa_op(True).mult(x)) < APPLY_TOL
 
 
+@pytest.mark.parametrize("p,n", [(1, 5), (2, 4), (3, 4), (4, 3), (5, 3), (6, 2)])
+@pytest.mark.parametrize("which", ["full", "mass", "diff+mass", "diff"])
+def test_group_kernel_all_orders(torch, ctx, orc, p, n, which):
+    """kernel option 4: the register-z / bulk-async group kernel for every order, uneven element counts
+    (exercises groups that run out of elements before their warp-mates)"""
+    kw = dict(full=dict(), mass=dict(kappa=None, vel=None, mass=1.3), diff=dict(kappa=0.3, vel=None, mass=None))
+    kw["diff+mass"] = dict(kappa=0.3, vel=None, mass=2.0)
+    P, mesh, sp = make(ctx, orc, 3, p, [n, n + 1, n], perturb=0.12, shuffle_seed=p, **kw[which])
+    D = Dev(torch, ctx)
+    x = np.random.default_rng(11).uniform(-1, 1, P.ndof)
+    for scatter in (0, 1):
+        op = make_op(P, sp)
+        op.set_option("kernel", 4)
+        op.set_option("scatter", scatter)
+        xd, yd = D.up(x), D.zeros(P.ndof)
+        op.MultUnconstrained(xd, yd)
+        assert rel(D.down(yd), P.pa_apply(x)) < APPLY_TOL
+        op.Mult(xd, yd)
+        assert rel(D.down(yd), P.pa_op(True).mult(x)) < APPLY_TOL
+
+
 @pytest.mark.parametrize("dim,p,n", [(2, 2, 4), (3, 2, 3), (3, 3, 3)])
 @pytest.mark.parametrize("which", ["mass", "diff", "diff+mass", "conv", "heat"])
 def test_integrator_subsets(torch, ctx, orc, dim, p, n, which):
