@@ -67,6 +67,12 @@ void orc_pa_apply(int dim, int p, int64_t ne, int64_t ndof,
                   const int32_t *gather, const int32_t *offsets, const int32_t *indices,
                   const double *Ddiff, const double *Dconv, const double *Dmass,
                   const double *x, double *y);
+/* fused, order-specialised CPU apply (3D) used for the CPU baseline timing; same result as
+   orc_pa_apply up to summation order; yE_work: optional ne*nd scratch */
+void orc_pa_apply_fast(int dim, int p, int64_t ne, int64_t ndof,
+                       const int32_t *gather, const int32_t *offsets, const int32_t *indices,
+                       const double *Ddiff, const double *Dconv, const double *Dmass,
+                       const double *x, double *y, double *yE_work);
 void orc_pa_diag(int dim, int p, int64_t ne, int64_t ndof,
                  const int32_t *gather, const int32_t *offsets, const int32_t *indices,
                  const double *Ddiff, const double *Dconv, const double *Dmass,

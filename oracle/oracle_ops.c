@@ -547,3 +547,126 @@ void orc_csr_eliminate(int64_t n, const int64_t *rowptr, const int32_t *colind,
       b[i] = d * x[i];
    }
 }
+
+/* ------------------------------------------------------------------------------
+ * Fast CPU partial-assembly apply (3D): one fused pass per element with compile-time
+ * loop bounds (macro-instantiated per order), the shape an optimised CPU PA code has
+ * (MFEM's SmemPA*Apply3D kernels fused over the three integrators).  Used for the
+ * cpu_baseline timing of bench.py; checked against orc_pa_apply in tests/test_oracle.py.
+ * ------------------------------------------------------------------------------ */
+#define DEFINE_FAST_APPLY3D(D, Q)                                                                   \
+static void fast_elem_apply3d_##D##_##Q(const double *restrict B, const double *restrict G,        \
+                                        const double *restrict Dd, const double *restrict Dc,      \
+                                        const double *restrict Dm, const double *restrict xE,      \
+                                        double *restrict yE)                                       \
+{                                                                                                   \
+   enum { NQ = Q * Q * Q };                                                                         \
+   double tB[D][D][Q], tG[D][D][Q];               /* [dz][dy][qx] */                                \
+   double vBB[D][Q][Q], vGB[D][Q][Q], vBG[D][Q][Q];   /* [dz][qy][qx] */                            \
+   double u[Q][Q][Q], ux[Q][Q][Q], uy[Q][Q][Q], uz[Q][Q][Q];                                        \
+   for (int dz = 0; dz < D; dz++) for (int dy = 0; dy < D; dy++) for (int qx = 0; qx < Q; qx++)    \
+   {                                                                                                \
+      double a = 0.0, b = 0.0;                                                                      \
+      for (int dx = 0; dx < D; dx++) { const double v = xE[dx + D * (dy + D * dz)]; a += B[qx * D + dx] * v; b += G[qx * D + dx] * v; } \
+      tB[dz][dy][qx] = a; tG[dz][dy][qx] = b;                                                       \
+   }                                                                                                \
+   for (int dz = 0; dz < D; dz++) for (int qy = 0; qy < Q; qy++) for (int qx = 0; qx < Q; qx++)    \
+   {                                                                                                \
+      double a = 0.0, b = 0.0, c = 0.0;                                                             \
+      for (int dy = 0; dy < D; dy++)                                                                \
+      { a += B[qy * D + dy] * tB[dz][dy][qx]; b += B[qy * D + dy] * tG[dz][dy][qx]; c += G[qy * D + dy] * tB[dz][dy][qx]; } \
+      vBB[dz][qy][qx] = a; vGB[dz][qy][qx] = b; vBG[dz][qy][qx] = c;                                \
+   }                                                                                                \
+   for (int qz = 0; qz < Q; qz++) for (int qy = 0; qy < Q; qy++) for (int qx = 0; qx < Q; qx++)    \
+   {                                                                                                \
+      double a = 0.0, b = 0.0, c = 0.0, d = 0.0;                                                    \
+      for (int dz = 0; dz < D; dz++)                                                                \
+      {                                                                                             \
+         a += B[qz * D + dz] * vBB[dz][qy][qx]; b += B[qz * D + dz] * vGB[dz][qy][qx];              \
+         c += B[qz * D + dz] * vBG[dz][qy][qx]; d += G[qz * D + dz] * vBB[dz][qy][qx];              \
+      }                                                                                             \
+      const int q = qx + Q * (qy + Q * qz);                                                         \
+      double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;                                                 \
+      if (Dd)                                                                                       \
+      {                                                                                             \
+         fx = Dd[q] * b + Dd[NQ + q] * c + Dd[2 * NQ + q] * d;                                      \
+         fy = Dd[NQ + q] * b + Dd[3 * NQ + q] * c + Dd[4 * NQ + q] * d;                             \
+         fz = Dd[2 * NQ + q] * b + Dd[4 * NQ + q] * c + Dd[5 * NQ + q] * d;                         \
+      }                                                                                             \
+      if (Dc) { s = Dc[q] * b + Dc[NQ + q] * c + Dc[2 * NQ + q] * d; }                              \
+      if (Dm) { s += Dm[q] * a; }                                                                   \
+      u[qz][qy][qx] = s; ux[qz][qy][qx] = fx; uy[qz][qy][qx] = fy; uz[qz][qy][qx] = fz;             \
+   }                                                                                                \
+   /* transposed: z, y, x */                                                                        \
+   for (int dz = 0; dz < D; dz++) for (int qy = 0; qy < Q; qy++) for (int qx = 0; qx < Q; qx++)    \
+   {                                                                                                \
+      double a = 0.0, b = 0.0, c = 0.0;                                                             \
+      for (int qz = 0; qz < Q; qz++)                                                                \
+      {                                                                                             \
+         a += B[qz * D + dz] * ux[qz][qy][qx]; b += B[qz * D + dz] * uy[qz][qy][qx];                \
+         c += G[qz * D + dz] * uz[qz][qy][qx] + B[qz * D + dz] * u[qz][qy][qx];                     \
+      }                                                                                             \
+      vBB[dz][qy][qx] = a; vGB[dz][qy][qx] = b; vBG[dz][qy][qx] = c;                                \
+   }                                                                                                \
+   for (int dz = 0; dz < D; dz++) for (int dy = 0; dy < D; dy++) for (int qx = 0; qx < Q; qx++)    \
+   {                                                                                                \
+      double a = 0.0, b = 0.0;                                                                      \
+      for (int qy = 0; qy < Q; qy++)                                                                \
+      { a += B[qy * D + dy] * vBB[dz][qy][qx]; b += G[qy * D + dy] * vGB[dz][qy][qx] + B[qy * D + dy] * vBG[dz][qy][qx]; } \
+      tB[dz][dy][qx] = a; tG[dz][dy][qx] = b;                                                       \
+   }                                                                                                \
+   for (int dz = 0; dz < D; dz++) for (int dy = 0; dy < D; dy++) for (int dx = 0; dx < D; dx++)    \
+   {                                                                                                \
+      double a = 0.0;                                                                               \
+      for (int qx = 0; qx < Q; qx++) { a += G[qx * D + dx] * tB[dz][dy][qx] + B[qx * D + dx] * tG[dz][dy][qx]; } \
+      yE[dx + D * (dy + D * dz)] = a;                                                               \
+   }                                                                                                \
+}
+DEFINE_FAST_APPLY3D(2, 3)
+DEFINE_FAST_APPLY3D(3, 4)
+DEFINE_FAST_APPLY3D(4, 5)
+DEFINE_FAST_APPLY3D(5, 6)
+DEFINE_FAST_APPLY3D(6, 7)
+DEFINE_FAST_APPLY3D(7, 8)
+
+void orc_pa_apply_fast(int dim, int p, int64_t ne, int64_t ndof,
+                       const int32_t *gather, const int32_t *offsets, const int32_t *indices,
+                       const double *Ddiff, const double *Dconv, const double *Dmass,
+                       const double *x, double *y, double *yE_work)
+{
+   if (dim != 3 || p < 1 || p > 6)
+   {
+      orc_pa_apply(dim, p, ne, ndof, gather, offsets, indices, Ddiff, Dconv, Dmass, x, y);
+      return;
+   }
+   const int d1d = p + 1, q1d = p + 2, nd = d1d * d1d * d1d, nq = q1d * q1d * q1d;
+   double B[MAXQ * MAXD], G[MAXQ * MAXD], qw[MAXQ];
+   orc_basis(p, q1d, B, G, qw);
+   double *yE = yE_work ? yE_work : malloc(sizeof(double) * (size_t)ne * nd);
+   #pragma omp parallel for schedule(static)
+   for (int64_t e = 0; e < ne; e++)
+   {
+      double xE[MAXD * MAXD * MAXD];
+      for (int i = 0; i < nd; i++) { xE[i] = x[gather[e * nd + i]]; }
+      const double *dd = Ddiff ? Ddiff + e * 6 * nq : NULL, *dc = Dconv ? Dconv + e * 3 * nq : NULL;
+      const double *dm = Dmass ? Dmass + e * nq : NULL;
+      double *ye = yE + e * nd;
+      switch (p)
+      {
+         case 1: fast_elem_apply3d_2_3(B, G, dd, dc, dm, xE, ye); break;
+         case 2: fast_elem_apply3d_3_4(B, G, dd, dc, dm, xE, ye); break;
+         case 3: fast_elem_apply3d_4_5(B, G, dd, dc, dm, xE, ye); break;
+         case 4: fast_elem_apply3d_5_6(B, G, dd, dc, dm, xE, ye); break;
+         case 5: fast_elem_apply3d_6_7(B, G, dd, dc, dm, xE, ye); break;
+         default: fast_elem_apply3d_7_8(B, G, dd, dc, dm, xE, ye); break;
+      }
+   }
+   #pragma omp parallel for schedule(static)
+   for (int64_t g = 0; g < ndof; g++)
+   {
+      double s = 0.0;
+      for (int32_t j = offsets[g]; j < offsets[g + 1]; j++) { s += yE[indices[j]]; }
+      y[g] = s;
+   }
+   if (!yE_work) { free(yE); }
+}

@@ -65,6 +65,7 @@ def lib():
     L.orc_node_coords.argtypes = [ci, ci, i64, i32p, f64p, f64p]
     L.orc_qdata.argtypes = [ci, ci, i64, i32p, f64p, ci, ci, vp, ci, vp, cd, ci, vp, vp, vp, vp]
     L.orc_pa_apply.argtypes = [ci, ci, i64, i64, i32p, i32p, i32p, vp, vp, vp, f64p, f64p]
+    L.orc_pa_apply_fast.argtypes = [ci, ci, i64, i64, i32p, i32p, i32p, vp, vp, vp, f64p, f64p, vp]
     L.orc_pa_diag.argtypes = [ci, ci, i64, i64, i32p, i32p, i32p, vp, vp, vp, f64p]
     L.orc_csr_pattern.argtypes = [i64, ci, i64, i32p, i64p, vp]
     L.orc_csr_pattern.restype = i64
@@ -230,6 +231,17 @@ class Problem:
         lib().orc_pa_apply(self.dim, self.p, self.ne, self.ndof, self.elem_dof, self.offsets,
                            self.indices, _opt(self.Dd), _opt(self.Dc), _opt(self.Dm),
                            np.ascontiguousarray(x, np.float64), y)
+        return y
+
+    def pa_apply_fast(self, x, y=None):
+        """fused order-specialised CPU apply (cpu_baseline timing path)"""
+        if y is None:
+            y = np.zeros(self.ndof)
+        if getattr(self, "_yE", None) is None:
+            self._yE = np.zeros(self.ne * self.nd)
+        lib().orc_pa_apply_fast(self.dim, self.p, self.ne, self.ndof, self.elem_dof, self.offsets,
+                                self.indices, _opt(self.Dd), _opt(self.Dc), _opt(self.Dm),
+                                np.ascontiguousarray(x, np.float64), y, _opt(self._yE))
         return y
 
     def pa_diag(self):

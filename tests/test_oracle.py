@@ -106,6 +106,19 @@ def test_csr_and_pa_formulations_agree(orc, dim, p):
     assert np.linalg.norm(d1 - d2) <= 1e-13 * np.linalg.norm(d1)
 
 
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
+def test_fast_cpu_apply_matches_three_pass_apply(orc, p):
+    """the fused order-specialised CPU apply timed as cpu_baseline is the same operator"""
+    P = orc.Problem(3, p, 3 if p < 5 else 2, perturb=0.12, shuffle_seed=p)
+    x = np.random.default_rng(p).uniform(-1, 1, P.ndof)
+    a, b = P.pa_apply(x), P.pa_apply_fast(x)
+    assert np.linalg.norm(a - b) <= 1e-14 * np.linalg.norm(a)
+    for kw in (dict(kappa=None, vel=None, mass=1.0), dict(kappa=0.3, vel=None, mass=None)):
+        Q = orc.Problem(3, p, 2, perturb=0.1, **kw)
+        x = np.random.default_rng(1).uniform(-1, 1, Q.ndof)
+        assert np.linalg.norm(Q.pa_apply(x) - Q.pa_apply_fast(x)) <= 1e-14 * np.linalg.norm(Q.pa_apply(x))
+
+
 def test_variable_and_matrix_coefficients_agree(orc):
     rng = np.random.default_rng(3)
     for dim in (2, 3):
