@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--kernel", type=int, default=-1)
     ap.add_argument("--scatter", type=int, default=-1)
+    ap.add_argument("--overlap", type=int, default=1, help="multi-GPU: overlap the halo exchange with interior elements")
     ap.add_argument("--krylov-iters", type=int, default=60)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -176,6 +177,7 @@ def main():
         op.set_option("kernel", args.kernel)
     if args.scatter >= 0:
         op.set_option("scatter", args.scatter)
+    op.set_option("overlap", args.overlap)
     op.set_option("tail", 1)        # x, y are allocated with the local (L-vector) size: no T<->L copies
     n_true = sp.ntrue
     tot = torch.tensor([n_true, sp.ne], dtype=torch.int64, device="cuda")

@@ -89,6 +89,7 @@ SIGNATURES = {
     "cdm_space_halo_peers": (_ci, [_vp, C.POINTER(_ci)]),
     "cdm_space_halo_peer": (_ci, [_vp, _ci, C.POINTER(_ci), C.POINTER(_i64), C.POINTER(_i64), _vp, _vp]),
     "cdm_space_dof_global": (_ci, [_vp, _vp]),
+    "cdm_space_elem_perm": (_ci, [_vp, _vp, C.POINTER(_i64)]),
     "cdm_space_destroy": (_ci, [_vp]),
     "cdm_operator_create": (_ci, [_vp, C.POINTER(Coeff), C.POINTER(Coeff), _cd, C.POINTER(Coeff), _vp, _i64, _pp]),
     "cdm_operator_update": (_ci, [_vp, C.POINTER(Coeff), C.POINTER(Coeff), _cd, C.POINTER(Coeff)]),
@@ -327,6 +328,13 @@ class H1Space:
             lib().cdm_space_halo_peer(self.h, i, C.byref(r), C.byref(no), C.byref(ng), _ptr(own), _ptr(ghost))
             out.append((r.value, own, ghost))
         return out
+
+    def elem_perm(self):
+        """(perm, n_boundary): perm[e] = mesh index of the space's e-th element"""
+        perm = np.zeros(self.ne, np.int64)
+        nb = C.c_int64()
+        lib().cdm_space_elem_perm(self.h, _ptr(perm), C.byref(nb))
+        return perm, nb.value
 
     def dof_global(self):
         k = np.zeros(self.ndof, np.int64)

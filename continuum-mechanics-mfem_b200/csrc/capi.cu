@@ -109,9 +109,12 @@ static int space_finish(cdm_ctx *ctx, const cdm_mesh *mesh, cdm_space *sp)
    const int nvpe = (sp->dim == 2) ? 4 : 8;
    sp->elem_x.resize((size_t)sp->ne * nvpe * sp->dim);
    for (int64_t e = 0; e < sp->ne; e++)
+   {
+      const int64_t em = sp->elem_perm.empty() ? e : sp->elem_perm[e];      // element index in the mesh
       for (int k = 0; k < nvpe; k++)
          for (int c = 0; c < sp->dim; c++)
-            sp->elem_x[((size_t)e * nvpe + k) * sp->dim + c] = mesh->vx[(size_t)mesh->ev[(size_t)e * nvpe + k] * sp->dim + c];
+            sp->elem_x[((size_t)e * nvpe + k) * sp->dim + c] = mesh->vx[(size_t)mesh->ev[(size_t)em * nvpe + k] * sp->dim + c];
+   }
    cdm_host_restriction(sp->ne, sp->nd, sp->ndof, sp->gather, sp->offsets, sp->indices);
    if (ctx->device >= 0)
    {
@@ -243,6 +246,24 @@ static void build_partition(const cdm_mesh *m, cdm_space *sp)
    sp->ntrue = nown;
    for (auto &g : sp->gather) { g = newid[g]; }
    for (auto &g : sp->bdr_dofs_flat) { g = newid[g]; }
+   // boundary-first element order: elements touching a shared dof come first so that the halo
+   // exchange can overlap the interior elements
+   {
+      std::vector<uint8_t> shared(sp->ndof, 0);
+      for (const Share &s : shares) { shared[newid[s.dof]] = 1; }
+      std::vector<uint8_t> isb(sp->ne, 0);
+      for (int64_t e = 0; e < sp->ne; e++)
+         for (int l = 0; l < sp->nd; l++)
+            if (shared[sp->gather[(size_t)e * sp->nd + l]]) { isb[e] = 1; break; }
+      sp->elem_perm.clear();
+      for (int64_t e = 0; e < sp->ne; e++) if (isb[e]) { sp->elem_perm.push_back(e); }
+      sp->n_bdr_elems = (int64_t)sp->elem_perm.size();
+      for (int64_t e = 0; e < sp->ne; e++) if (!isb[e]) { sp->elem_perm.push_back(e); }
+      std::vector<int32_t> g2(sp->gather.size());
+      for (int64_t e = 0; e < sp->ne; e++)
+         std::memcpy(&g2[(size_t)e * sp->nd], &sp->gather[(size_t)sp->elem_perm[e] * sp->nd], sizeof(int32_t) * sp->nd);
+      sp->gather.swap(g2);
+   }
    sp->dof_global.assign(sp->ndof, 0);
    for (int64_t g = 0; g < sp->ndof; g++) { sp->dof_global[newid[g]] = key[g]; }
    std::sort(shares.begin(), shares.end(), [](const Share &a, const Share &b)
@@ -414,6 +435,14 @@ int cdm_space_halo_peer(const cdm_space *sp, int i, int *rank, int64_t *n_own, i
    return CDM_OK;
 }
 
+int cdm_space_elem_perm(const cdm_space *sp, int64_t *perm, int64_t *n_boundary)
+{
+   if (!sp) { return CDM_EINVAL; }
+   if (perm) { for (int64_t e = 0; e < sp->ne; e++) { perm[e] = sp->elem_perm.empty() ? e : sp->elem_perm[e]; } }
+   if (n_boundary) { *n_boundary = sp->n_bdr_elems; }
+   return CDM_OK;
+}
+
 int cdm_space_dof_global(const cdm_space *sp, int64_t *keys)
 {
    if (!sp || !keys) { return CDM_EINVAL; }
@@ -530,6 +559,7 @@ int cdm_operator_set_option(cdm_op *op, const char *name, int value)
    if (!std::strcmp(name, "scatter")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->scatter_mode = value; return CDM_OK; }
    if (!std::strcmp(name, "kernel")) { op->kernel_variant = value; return CDM_OK; }
    if (!std::strcmp(name, "tail")) { op->tail = value != 0; return CDM_OK; }
+   if (!std::strcmp(name, "overlap")) { op->overlap = value != 0; return CDM_OK; }
    return cdm_fail(op->sp->ctx, CDM_EINVAL, std::string("unknown option ") + name);
 }
 
@@ -549,6 +579,53 @@ int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained)
    cdm_ctx *ctx = sp->ctx;
    int rc;
    const bool par = ctx->nranks > 1 && !sp->peers.empty();
+   // Overlapped schedule (atomic scatter, range-capable kernels): the halo exchange runs on a
+   // high-priority stream with its own communicator while the compute stream works on interior
+   // elements:   H: pack, P exchange, unpack      | C: memset y, interior A
+   //             C: boundary elements             |
+   //             H: pack, P^T exchange, unpack-add | C: interior B
+   // Each interior launch waits for the pack kernel of its phase, so the NCCL kernel (ready at the
+   // same moment, higher priority) is placed before the persistent element kernel fills the SMs.
+   if (par && op->overlap && ctx->stream_halo && op->scatter_mode == 1 && sp->dim == 3 &&
+       (op->kernel_variant == 3 || op->kernel_variant == 4) && sp->n_bdr_elems > 0 && sp->n_bdr_elems < sp->ne)
+   {
+      cudaStream_t C = ctx->stream, H = ctx->stream_halo;
+      cudaEvent_t *ev = ctx->ev_h;
+      const int64_t nb = sp->n_bdr_elems, mid = nb + (sp->ne - nb) / 2;
+      CDM_CUDA(ctx, cudaEventRecord(ev[0], C));                       // x is ready
+      CDM_CUDA(ctx, cudaStreamWaitEvent(H, ev[0], 0));
+      if ((rc = cdm_halo_P_async(op, x_buf, ev[1]))) { return rc; }   // H: pack (ev[1]), exchange, unpack
+      CDM_CUDA(ctx, cudaEventRecord(ev[2], H));
+      CDM_CUDA(ctx, cudaMemsetAsync(y_buf, 0, sizeof(double) * (size_t)sp->ndof, C));
+      CDM_CUDA(ctx, cudaStreamWaitEvent(C, ev[1], 0));
+      op->range_on = true;
+      op->e_begin = nb; op->e_end = mid;
+      rc = cdm_k_apply(op, x_buf, y_buf, constrained);                // C: interior A
+      if (!rc)
+      {
+         cudaStreamWaitEvent(C, ev[2], 0);                            // ghosts of x have arrived
+         op->e_begin = 0; op->e_end = nb;
+         rc = cdm_k_apply(op, x_buf, y_buf, constrained);             // C: boundary elements
+      }
+      if (!rc)
+      {
+         cudaEventRecord(ev[3], C);
+         cudaStreamWaitEvent(H, ev[3], 0);
+         rc = cdm_halo_PT_async(op, y_buf, ev[4]);                    // H: pack (ev[4]), exchange, unpack-add
+         cudaEventRecord(ev[5], H);
+      }
+      if (!rc)
+      {
+         cudaStreamWaitEvent(C, ev[4], 0);
+         op->e_begin = mid; op->e_end = sp->ne;
+         rc = cdm_k_apply(op, x_buf, y_buf, constrained);             // C: interior B
+         cudaStreamWaitEvent(C, ev[5], 0);
+      }
+      op->range_on = false;
+      if (rc) { return rc; }
+      if (constrained && op->n_ess > 0) { rc = cdm_k_copy_idx(ctx, op->n_ess, op->ess_dev, x_buf, y_buf); }
+      return rc;
+   }
    if (par && (rc = cdm_halo_P(op, x_buf))) { return rc; }
    if ((rc = cdm_k_apply(op, x_buf, y_buf, constrained))) { return rc; }
    if (par && (rc = cdm_halo_PT(op, y_buf))) { return rc; }

@@ -26,6 +26,10 @@ struct cdm_ctx
    double *red_host = nullptr;      // pinned, RED_MAXK
    int sm_count = 148;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   // halo / compute overlap: a high-priority stream with its own communicator (ncclCommSplit)
+   cudaStream_t stream_halo = nullptr;
+   ncclComm *comm_halo = nullptr;
+   cudaEvent_t ev_h[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    // kernel-only timing (cdm_operator_time_kernel)
    bool time_main = false;
    cudaEvent_t evk0 = nullptr, evk1 = nullptr;
@@ -91,6 +95,10 @@ struct cdm_space
    // multi-GPU
    std::vector<cdm_halo_peer> peers;
    cdm_halo_plan halo;
+   // partitioned spaces order their elements "boundary first": elements [0, n_bdr_elems) touch a
+   // shared dof, the rest are interior; elem_perm[new] = element index in the mesh
+   int64_t n_bdr_elems = 0;
+   std::vector<int64_t> elem_perm;
    std::vector<int64_t> dof_global;                    // local dof -> global dof id (partitioned spaces)
 };
 
@@ -109,7 +117,10 @@ struct cdm_op
    double *yE_dev = nullptr;       // E-vector scratch (scatter mode 0)
    double *xL_dev = nullptr, *yL_dev = nullptr;   // L-vector scratch (multi-GPU / host mult)
    double *dinv_dev = nullptr;     // cached Jacobi inverse diagonal
-   bool tail = false;              // caller vectors have room for the ghost tail (length >= ndof)
+   bool range_on = false;          // launch only elements [e_begin, e_end) (overlapped multi-GPU apply)
+   int64_t e_begin = 0, e_end = 0;
+   int overlap = 1;                // 1: overlap the halo exchange with interior elements when possible
+   bool tail = false;             // caller vectors have room for the ghost tail (length >= ndof)
    int scatter_mode = 1;           // 0: E-vector + gather transpose, 1: FP64 red.add
    int kernel_variant = 0;
    // krylov workspace (lazy)
@@ -180,3 +191,6 @@ int cdm_k_cg_update(cdm_ctx *c, int64_t n, double a, const double *d, const doub
 int cdm_halo_P(cdm_op *op, double *xL);            // owner -> ghost values
 int cdm_halo_PT(cdm_op *op, double *yL);           // ghost partial sums -> owner (add)
 int cdm_allreduce_sum(cdm_ctx *c, double *buf_dev, int k);
+// same exchanges on the halo stream / communicator; ev_packed is recorded right after the pack kernel
+int cdm_halo_P_async(cdm_op *op, double *xL, cudaEvent_t ev_packed);
+int cdm_halo_PT_async(cdm_op *op, double *yL, cudaEvent_t ev_packed);

@@ -26,6 +26,7 @@ struct NcclApi
    nccl_result (*GroupStart)() = nullptr;
    nccl_result (*GroupEnd)() = nullptr;
    const char *(*GetErrorString)(nccl_result) = nullptr;
+   nccl_result (*CommSplit)(ncclComm *, int, int, ncclComm **, void *) = nullptr;   // optional (NCCL >= 2.18)
 };
 const int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
 
@@ -43,6 +44,7 @@ NcclApi *api()
    SYM(AllReduce, "ncclAllReduce") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
+   *(void **)(&a.CommSplit) = dlsym(a.h, "ncclCommSplit");
    return &a;
 }
 }  // namespace
@@ -76,6 +78,17 @@ extern "C" int cdm_comm_init(cdm_ctx *ctx, int rank, int nranks, const void *uid
    std::memcpy(&id, uid128, sizeof(id));
    CDM_CUDA(ctx, cudaSetDevice(ctx->device));
    NCCL_CALL(ctx, a->CommInitRank(&ctx->comm, nranks, id, rank));
+   // second communicator + high-priority stream for the halo exchange, so that it can run beside the
+   // element kernels of the compute stream (and beside the Krylov all-reduces of the main communicator)
+   if (a->CommSplit && a->CommSplit(ctx->comm, 0, rank, &ctx->comm_halo, nullptr) == 0 && ctx->comm_halo)
+   {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&ctx->stream_halo, cudaStreamNonBlocking, hi) != cudaSuccess)
+      { cudaGetLastError(); ctx->stream_halo = nullptr; }
+      for (int i = 0; i < 6 && ctx->stream_halo; i++)
+         if (cudaEventCreateWithFlags(&ctx->ev_h[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ctx->stream_halo = nullptr; }
+   }
    return CDM_OK;
 }
 
@@ -94,42 +107,63 @@ int cdm_allreduce_sum(cdm_ctx *c, double *buf_dev, int k)
    return CDM_OK;
 }
 
-// x_L ghost entries <- owner values
-int cdm_halo_P(cdm_op *op, double *xL)
+// Run `body` with the context's stream temporarily replaced (the kernel launchers read c->stream).
+struct StreamSwap
+{
+   cdm_ctx *c; cudaStream_t saved;
+   StreamSwap(cdm_ctx *ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { c->stream = s; }
+   ~StreamSwap() { c->stream = saved; }
+};
+
+// x_L ghost entries <- owner values.  halo_stream: run on the halo stream / communicator and record
+// ev_packed right after the pack kernel (the compute stream waits on it before filling the GPU).
+static int halo_P_impl(cdm_op *op, double *xL, bool halo_stream, cudaEvent_t ev_packed)
 {
    cdm_space *sp = op->sp;
    cdm_ctx *c = sp->ctx;
    if (!c->comm) { return cdm_fail(c, CDM_ENCCL, "partitioned space used without cdm_comm_init"); }
    NcclApi *a = api();
    cdm_halo_plan &hp = sp->halo;
+   StreamSwap sw(c, halo_stream ? c->stream_halo : c->stream);
+   ncclComm *comm = halo_stream ? c->comm_halo : c->comm;
    int rc = cdm_k_pack(c, (int64_t)hp.own_all.size(), hp.own_all_dev, xL, hp.send_dev);
    if (rc) { return rc; }
+   if (ev_packed) { CDM_CUDA(c, cudaEventRecord(ev_packed, c->stream)); }
    NCCL_CALL(c, a->GroupStart());
    for (auto &pr : sp->peers)
    {
-      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Send(hp.send_dev + pr.own_off, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
-      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Recv(hp.recv_dev + pr.ghost_off, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
+      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Send(hp.send_dev + pr.own_off, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
+      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Recv(hp.recv_dev + pr.ghost_off, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
    }
    NCCL_CALL(c, a->GroupEnd());
    return cdm_k_unpack(c, (int64_t)hp.ghost_all.size(), hp.ghost_all_dev, hp.recv_dev, xL, 0);
 }
 
+int cdm_halo_P(cdm_op *op, double *xL) { return halo_P_impl(op, xL, false, nullptr); }
+int cdm_halo_P_async(cdm_op *op, double *xL, cudaEvent_t ev_packed) { return halo_P_impl(op, xL, true, ev_packed); }
+
 // owner entries of y_L += partial sums held in the sharers' ghost entries (fixed peer order)
-int cdm_halo_PT(cdm_op *op, double *yL)
+static int halo_PT_impl(cdm_op *op, double *yL, bool halo_stream, cudaEvent_t ev_packed)
 {
    cdm_space *sp = op->sp;
    cdm_ctx *c = sp->ctx;
    if (!c->comm) { return cdm_fail(c, CDM_ENCCL, "partitioned space used without cdm_comm_init"); }
    NcclApi *a = api();
    cdm_halo_plan &hp = sp->halo;
+   StreamSwap sw(c, halo_stream ? c->stream_halo : c->stream);
+   ncclComm *comm = halo_stream ? c->comm_halo : c->comm;
    int rc = cdm_k_pack(c, (int64_t)hp.ghost_all.size(), hp.ghost_all_dev, yL, hp.send_dev);
    if (rc) { return rc; }
+   if (ev_packed) { CDM_CUDA(c, cudaEventRecord(ev_packed, c->stream)); }
    NCCL_CALL(c, a->GroupStart());
    for (auto &pr : sp->peers)
    {
-      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Send(hp.send_dev + pr.ghost_off, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
-      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Recv(hp.recv_dev + pr.own_off, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, c->comm, c->stream)); }
+      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Send(hp.send_dev + pr.ghost_off, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
+      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Recv(hp.recv_dev + pr.own_off, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
    }
    NCCL_CALL(c, a->GroupEnd());
    return cdm_k_unpack_add_csr(c, (int64_t)hp.pt_dof.size(), hp.pt_dof_dev, hp.pt_off_dev, hp.pt_src_dev, hp.recv_dev, yL);
 }
+
+int cdm_halo_PT(cdm_op *op, double *yL) { return halo_PT_impl(op, yL, false, nullptr); }
+int cdm_halo_PT_async(cdm_op *op, double *yL, cudaEvent_t ev_packed) { return halo_PT_impl(op, yL, true, ev_packed); }

@@ -636,11 +636,16 @@ int launch_bg(cdm_op *op, const WarpTablesBG &tb, const int32_t *gmap, const dou
       if (blocks_per_sm < 1) { return cdm_fail(ctx, CDM_ECUDA, "k_apply3d_warp_bg does not fit on an SM"); }
       configured = smem;
    }
+   // element range [e0, e1): the kernel sees a shifted view of the per-element arrays
+   const int64_t e0 = op->range_on ? op->e_begin : 0, e1 = op->range_on ? op->e_end : sp->ne;
+   const int64_t n = e1 - e0;
+   if (n <= 0) { return CDM_OK; }
    int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
-   const int64_t need = (sp->ne + NW - 1) / NW;
+   const int64_t need = (n + NW - 1) / NW;
    if (grid > need) { grid = need; }
    if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }
-   kern<<<(unsigned)grid, NW * 32, smem, ctx->stream>>>(tb, sp->ne, gmap, xL, op->D_dev, op->slab, out);
+   kern<<<(unsigned)grid, NW * 32, smem, ctx->stream>>>(tb, n, gmap + e0 * 64, xL, op->D_dev + e0 * 5 * (int64_t)op->slab,
+                                                        op->slab, ATOMIC ? out : out + e0 * 64);
    if (ctx->time_main) { cudaEventRecord(ctx->evk1, ctx->stream); }
    ctx->launches++;
    CDM_CUDA(ctx, cudaGetLastError());
@@ -739,7 +744,7 @@ int cdm_k_apply_p3(cdm_op *op, const int32_t *gmap, const double *xL, double *yL
    const bool atomic = op->scatter_mode == 1;
    const bool ph = op->kernel_variant >= 2;
    double *out = yL;
-   if (atomic) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); }
+   if (atomic) { if (!op->range_on) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); } }
    else
    {
       if (!op->yE_dev) { CDM_CUDA(ctx, cudaMalloc(&op->yE_dev, sizeof(double) * (size_t)sp->ne * sp->nd)); }

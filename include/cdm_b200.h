@@ -118,6 +118,11 @@ int  cdm_space_halo_peers(const cdm_space *space, int *npeers);
 int  cdm_space_halo_peer(const cdm_space *space, int i, int *rank, int64_t *n_own, int64_t *n_ghost,
                          int32_t *own_idx, int32_t *ghost_idx);
 int  cdm_space_dof_global(const cdm_space *space, int64_t *keys);
+/* element order of the space: perm[e] = index in the mesh of the space's e-th element (identity
+   unless the space is partitioned: then the n_boundary elements touching a shared dof come first,
+   so that the halo exchange overlaps the interior elements).  Per-element inputs (gather map,
+   CDM_COEFF_QPT arrays, cdm_space_qpt_coords) are in the space's element order. */
+int  cdm_space_elem_perm(const cdm_space *space, int64_t *perm, int64_t *n_boundary);
 int  cdm_space_destroy(cdm_space *space);
 
 /* --------------------------------------------------------------- operator */
