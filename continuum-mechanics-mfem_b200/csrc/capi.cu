@@ -559,7 +559,7 @@ int cdm_operator_set_option(cdm_op *op, const char *name, int value)
    if (!std::strcmp(name, "scatter")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->scatter_mode = value; return CDM_OK; }
    if (!std::strcmp(name, "kernel")) { op->kernel_variant = value; return CDM_OK; }
    if (!std::strcmp(name, "tail")) { op->tail = value != 0; return CDM_OK; }
-   if (!std::strcmp(name, "overlap")) { op->overlap = value != 0; return CDM_OK; }
+   if (!std::strcmp(name, "overlap")) { if (value < 0 || value > 2) { return CDM_EINVAL; } op->overlap = value; return CDM_OK; }
    return cdm_fail(op->sp->ctx, CDM_EINVAL, std::string("unknown option ") + name);
 }
 
@@ -586,7 +586,11 @@ int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained)
    //             H: pack, P^T exchange, unpack-add | C: interior B
    // Each interior launch waits for the pack kernel of its phase, so the NCCL kernel (ready at the
    // same moment, higher priority) is placed before the persistent element kernel fills the SMs.
-   if (par && op->overlap && ctx->stream_halo && op->scatter_mode == 1 && sp->dim == 3 &&
+   // Measured (profiles/r01_scaling.md): faster with 1 neighbour, slower with 7 (the NCCL kernel then competes
+   // with the persistent element kernel for SM slots), so by default only used up to 3 neighbours;
+   // option "overlap" = 2 forces it.
+   if (par && (op->overlap == 2 || (op->overlap == 1 && sp->peers.size() <= 3)) && ctx->stream_halo &&
+       op->scatter_mode == 1 && sp->dim == 3 &&
        (op->kernel_variant == 3 || op->kernel_variant == 4) && sp->n_bdr_elems > 0 && sp->n_bdr_elems < sp->ne)
    {
       cudaStream_t C = ctx->stream, H = ctx->stream_halo;
