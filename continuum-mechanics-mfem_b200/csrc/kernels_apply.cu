@@ -225,6 +225,21 @@ k_apply3d_generic(BasisTables bs, int64_t ne, const int32_t *__restrict__ gather
    double (*s0) = sm[tz][0], (*s1) = sm[tz][1], (*s2) = sm[tz][2], (*s3) = sm[tz][3], (*s4) = sm[tz][4];
    int32_t gi[D];
    // gather: thread (dx,dy) holds the z-column
+   // low orders (Q1D <= 4): prefetch this thread's whole D column (Q1D slabs x ncomp values) into
+   // registers, so that the HBM latency overlaps the gather and the x / y contractions
+   constexpr bool PRE = (Q <= 4);
+   double dr[PRE ? Q : 1][10];
+   if (PRE && live)
+   {
+      const int ncomp = (has_diff ? 6 : 0) + (has_conv ? 3 : 0) + (has_mass ? 1 : 0);
+      #pragma unroll
+      for (int qz = 0; qz < (PRE ? Q : 1); qz++)
+      {
+         const double *dp = Dq + ((e * Q + qz) * (int64_t)slab + tx + Q * ty);
+         #pragma unroll
+         for (int c = 0; c < 10; c++) { dr[qz][c] = (c < ncomp) ? __ldg(dp + c * Q2) : 0.0; }
+      }
+   }
    if (live && tx < D && ty < D)
    {
       #pragma unroll
@@ -286,17 +301,36 @@ k_apply3d_generic(BasisTables bs, int64_t ne, const int32_t *__restrict__ gather
       double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;
       if (live)
       {
-         const double *dp = Dq + ((e * Q + qz) * (int64_t)slab + qxy);
-         if (has_diff)
+         if (PRE)
          {
-            const double d0 = dp[0], d1 = dp[Q2], d2 = dp[2 * Q2], d3 = dp[3 * Q2], d4 = dp[4 * Q2], d5 = dp[5 * Q2];
-            fx = d0 * ux + d1 * uy + d2 * uz;
-            fy = d1 * ux + d3 * uy + d4 * uz;
-            fz = d2 * ux + d4 * uy + d5 * uz;
-            dp += 6 * Q2;
+            const double *dv = dr[PRE ? qz : 0];
+            if (has_diff)
+            {
+               fx = dv[0] * ux + dv[1] * uy + dv[2] * uz;
+               fy = dv[1] * ux + dv[3] * uy + dv[4] * uz;
+               fz = dv[2] * ux + dv[4] * uy + dv[5] * uz;
+            }
+            if (has_conv)
+            {
+               const double c0 = has_diff ? dv[6] : dv[0], c1 = has_diff ? dv[7] : dv[1], c2 = has_diff ? dv[8] : dv[2];
+               s = c0 * ux + c1 * uy + c2 * uz;
+            }
+            if (has_mass) { s += (has_diff ? (has_conv ? dv[9] : dv[6]) : (has_conv ? dv[3] : dv[0])) * u; }
          }
-         if (has_conv) { s = dp[0] * ux + dp[Q2] * uy + dp[2 * Q2] * uz; dp += 3 * Q2; }
-         if (has_mass) { s += dp[0] * u; }
+         else
+         {
+            const double *dp = Dq + ((e * Q + qz) * (int64_t)slab + qxy);
+            if (has_diff)
+            {
+               const double d0 = dp[0], d1 = dp[Q2], d2 = dp[2 * Q2], d3 = dp[3 * Q2], d4 = dp[4 * Q2], d5 = dp[5 * Q2];
+               fx = d0 * ux + d1 * uy + d2 * uz;
+               fy = d1 * ux + d3 * uy + d4 * uz;
+               fz = d2 * ux + d4 * uy + d5 * uz;
+               dp += 6 * Q2;
+            }
+            if (has_conv) { s = dp[0] * ux + dp[Q2] * uy + dp[2 * Q2] * uz; dp += 3 * Q2; }
+            if (has_mass) { s += dp[0] * u; }
+         }
       }
       #pragma unroll
       for (int dz = 0; dz < D; dz++)

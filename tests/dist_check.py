@@ -99,7 +99,8 @@ def main():
         xd = torch.from_numpy(xg[mine[:nt]]).cuda()
         yd = torch.zeros(nt, dtype=torch.float64, device="cuda")
         torch.cuda.synchronize()
-        for kernel, scatter, overlap in ((0, 0, 0), (0, 1, 0), (1, 1, 0), (3, 0, 0), (3, 1, 0), (3, 1, 1), (4, 1, 1)):
+        # overlap: 0 serial halo exchange, 1 automatic (by neighbour count), 2 forced overlapped schedule
+        for kernel, scatter, overlap in ((0, 0, 0), (0, 1, 0), (1, 1, 0), (3, 0, 0), (3, 1, 0), (3, 1, 1), (3, 1, 2), (4, 1, 2)):
             op.set_option("kernel", kernel)
             op.set_option("scatter", scatter)
             op.set_option("overlap", overlap)
