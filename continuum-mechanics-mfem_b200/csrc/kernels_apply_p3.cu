@@ -54,8 +54,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier (TMA engine)
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
-   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+   // D is read exactly once per apply: mark its lines evict-first in L2 so that the stream does not push
+   // out the x / y vectors, which are re-read (gather) and re-written (red.add) by neighbouring elements
+   uint64_t pol;
+   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void red_add_f64(double *addr, double v)
 {

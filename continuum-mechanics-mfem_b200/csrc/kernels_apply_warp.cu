@@ -41,8 +41,11 @@ __device__ __forceinline__ void g_mbar_wait(uint64_t *bar, uint32_t parity)
 }
 __device__ __forceinline__ void g_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
-   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+   // evict-first: the D stream must not push the x / y vectors out of L2 (see kernels_apply_p3.cu)
+   uint64_t pol;
+   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void g_red_add(double *addr, double v)
 { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory"); }
