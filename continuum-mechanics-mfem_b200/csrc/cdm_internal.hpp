@@ -99,6 +99,7 @@ struct cdm_space
    // shared dof, the rest are interior; elem_perm[new] = element index in the mesh
    int64_t n_bdr_elems = 0;
    std::vector<int64_t> elem_perm;
+   std::vector<int64_t> class_off;                     // entity-class dof ranges (spaces numbered by this library)
    std::vector<int64_t> dof_global;                    // local dof -> global dof id (partitioned spaces)
 };
 
@@ -123,6 +124,17 @@ struct cdm_op
    bool tail = false;             // caller vectors have room for the ghost tail (length >= ndof)
    int scatter_mode = 1;           // 0: E-vector + gather transpose, 1: FP64 red.add
    int kernel_variant = 0;
+   // pipelined host-vector apply (cdm_operator_mult_host): element chunks, per-class upload / download bounds
+   struct host_pipe
+   {
+      int K = 0;
+      std::vector<int64_t> eb, ub, db;      // eb[K+1]; ub, db[(K+1)*4]
+      cudaStream_t su = nullptr, sd = nullptr;
+      std::vector<cudaEvent_t> ev_up, ev_k;
+      std::vector<int64_t> ess_off;         // essential dofs grouped by download chunk
+      int32_t *ess_by_chunk_dev = nullptr;
+   } pipe;
+   int host_pipeline = 1;
    // krylov workspace (lazy)
    double *kry_dev = nullptr; int64_t kry_len = 0;
    std::vector<double> coef_scratch;
@@ -146,7 +158,8 @@ void cdm_host_gauss_lobatto(int n, double *x);
 void cdm_host_basis(int p, int q1d, double *B, double *G, double *qw, double *nodes, double *qx);
 int  cdm_host_q1d(int dim, int p);
 int64_t cdm_host_h1_numbering(const cdm_mesh &m, int p, std::vector<int32_t> &elem_dof,
-                              std::vector<int32_t> &bdr_off, std::vector<int32_t> &bdr_flat);
+                              std::vector<int32_t> &bdr_off, std::vector<int32_t> &bdr_flat,
+                              int64_t *class_off = nullptr);   // [vertices | edges | faces | interiors] dof ranges
 void cdm_host_restriction(int64_t ne, int nd, int64_t ndof, const std::vector<int32_t> &gather,
                           std::vector<int32_t> &offsets, std::vector<int32_t> &indices);
 

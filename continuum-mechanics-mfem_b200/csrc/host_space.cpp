@@ -281,7 +281,8 @@ void lex_to_native(int dim, int p, std::vector<int> &map)
 // Returns ndof, fills elem_dof (lexicographic within each element) and, per
 // boundary element, the list of dofs lying on it.
 int64_t cdm_host_h1_numbering(const cdm_mesh &m, int p, std::vector<int32_t> &elem_dof,
-                              std::vector<int32_t> &bdr_off, std::vector<int32_t> &bdr_flat)
+                              std::vector<int32_t> &bdr_off, std::vector<int32_t> &bdr_flat,
+                              int64_t *class_off)
 {
    const int dim = m.dim, p1 = p + 1, pm1 = p - 1;
    const int nd = (dim == 2) ? p1 * p1 : p1 * p1 * p1;
@@ -316,6 +317,7 @@ int64_t cdm_host_h1_numbering(const cdm_mesh &m, int p, std::vector<int32_t> &el
    int nint = 1; for (int d = 0; d < dim; d++) { nint *= pm1; }
    if (pm1 <= 0) { nint = 0; }
    const int64_t ndof = int0 + m.ne * nint;
+   if (class_off) { class_off[0] = 0; class_off[1] = edge0; class_off[2] = face0; class_off[3] = int0; class_off[4] = ndof; }
 
    std::vector<int> l2n;
    lex_to_native(dim, p, l2n);

@@ -125,6 +125,33 @@ def test_p3_kernel_variants(torch, ctx, orc, variant):
         assert rel(D.down(yd), P.pa_op(True).mult(x)) < APPLY_TOL
 
 
+@pytest.mark.parametrize("p,n", [(3, 24), (4, 21)])
+def test_pipelined_host_apply(torch, ctx, p, n):
+    """cdm_operator_mult_host on >= 8192 elements runs the chunked upload / compute / download pipeline:
+    same result as the device-vector apply, with and without constraints, pinned or pageable host memory"""
+    D = Dev(torch, ctx)
+    mesh = cdm.Mesh.cartesian(ctx, 3, n, perturb=0.1)
+    sp = cdm.H1Space(mesh, p)
+    ess = sp.essential_dofs(np.ones(6, np.int32))
+    op = cdm.ConvectionDiffusionOperator(sp, kappa=0.1, vel=(1.0, -2.0, 0.5), mass=1.0, ess_dofs=ess)
+    x = np.random.default_rng(4).uniform(-1, 1, sp.ndof)
+    xp = torch.from_numpy(x).pin_memory()
+    yp = torch.zeros(sp.ndof, dtype=torch.float64).pin_memory()
+    xd, yd = D.up(x), D.zeros(sp.ndof)
+    for constrained in (True, False):
+        (op.Mult if constrained else op.MultUnconstrained)(xd, yd)
+        y_dev = D.down(yd)
+        for rep in range(2):
+            y_pipe = op.mult_host(x, constrained=constrained)
+        op.mult_host(xp.numpy(), yp.numpy(), constrained=constrained)
+        op.set_option("host_pipeline", 0)
+        y_plain = op.mult_host(x, constrained=constrained)
+        op.set_option("host_pipeline", 1)
+        assert rel(y_pipe, y_dev) < 1e-13 and rel(y_plain, y_dev) < 1e-13 and rel(yp.numpy(), y_dev) < 1e-13
+        if constrained:
+            assert np.array_equal(y_pipe[ess], x[ess]) and np.array_equal(yp.numpy()[ess], x[ess])
+
+
 @pytest.mark.parametrize("p,n", [(1, 5), (2, 4), (3, 4), (4, 3), (5, 3), (6, 2)])
 @pytest.mark.parametrize("which", ["full", "mass", "diff+mass", "diff"])
 def test_group_kernel_all_orders(torch, ctx, orc, p, n, which):
