@@ -152,6 +152,10 @@ def main():
         print(json.dumps(line))
         return 0
 
+    if world > 1:
+        # the halo messages (<= 0.7 MB) and the Krylov all-reduces (<= 31 doubles) are latency-bound:
+        # NCCL's LL protocol is 5.6 % faster per Krylov iteration at 8 GPUs (profiles/r01_scaling.md)
+        os.environ.setdefault("NCCL_PROTO", "LL")
     import torch
     import torch.distributed as dist
     cdm = importlib.import_module("continuum-mechanics-mfem_b200")
@@ -241,6 +245,21 @@ def main():
                 "traffic": traffic, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": bytes_launch,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
 
+    # ---- setup kernels (a.Assemble(): quadrature data; Jacobi diagonal), device time of one call each
+    dvec = torch.zeros(ld, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    op.update(kappa=KAPPA, vel=VEL, mass=MASS)
+    op.AssembleDiagonal(dvec)
+    ctx.sync()
+    s0, s1, s2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    s0.record(stream)
+    op.update(kappa=KAPPA, vel=VEL, mass=MASS)
+    s1.record(stream)
+    op.AssembleDiagonal(dvec)
+    s2.record(stream)
+    ctx.sync()
+    setup = {"qdata_ms": s0.elapsed_time(s1), "diag_ms": s1.elapsed_time(s2)}
+
     # ---- end to end through the host-buffer entry point (mfem::Vector under Device("cpu"))
     xh = torch.empty(n_true, dtype=torch.float64).pin_memory()
     yh = torch.empty(n_true, dtype=torch.float64).pin_memory()
@@ -288,11 +307,12 @@ def main():
                 "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "global_dofs": n_global, "global_elements": ne_global,
-                           "partition": "x".join(map(str, parts)), "l2_policy": "inputs larger than L2 "
+                           "partition": "x".join(map(str, parts)),
+                           "nccl_proto": os.environ.get("NCCL_PROTO") if world > 1 else None, "l2_policy": "inputs larger than L2 "
                            f"({bytes_launch / 1e9:.2f} GB streamed per apply per GPU vs 126 MB L2)",
                            "scatter": "fp64 red.add" if op_scatter(op, args) == 1 else "E-vector + gather transpose"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-                "krylov": krylov, "clocks": clocks}
+                "krylov": krylov, "setup": setup, "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

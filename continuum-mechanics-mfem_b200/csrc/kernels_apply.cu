@@ -530,6 +530,70 @@ k_diag_elem(BasisTables bs, int d1d, int q1d, int64_t ne, const double *__restri
    dE[gid] = acc;
 }
 
+// Sum-factorised 3D diagonal: because phi_l is a tensor product, every term of the diagonal factors into
+// 1-D tables BB = B^2, BG = B G, GG = G^2.  One thread per (element, dx, dy) contracts x and y for each z-slab
+// into three partial sums (one per z-factor type), then finishes the D1D values of its z-column.
+template <int D, int Q>
+__global__ void __launch_bounds__(128)
+k_diag3d_sumfact(BasisTables bs, int64_t ne, const double *__restrict__ Dq, int slab,
+                 int has_diff, int has_conv, int has_mass, double *__restrict__ dE)
+{
+   constexpr int Q2 = Q * Q;
+   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (gid >= ne * D * D) { return; }
+   const int64_t e = gid / (D * D);
+   const int l = (int)(gid - e * (D * D));
+   const int dx = l % D, dy = l / D;
+   double bbx[Q], bgx[Q], ggx[Q], bby[Q], bgy[Q], ggy[Q];
+   #pragma unroll
+   for (int q = 0; q < Q; q++)
+   {
+      const double b = bs.B[q * D + dx], g = bs.G[q * D + dx];
+      bbx[q] = b * b; bgx[q] = b * g; ggx[q] = g * g;
+      const double b2 = bs.B[q * D + dy], g2 = bs.G[q * D + dy];
+      bby[q] = b2 * b2; bgy[q] = b2 * g2; ggy[q] = g2 * g2;
+   }
+   double out[D];
+   #pragma unroll
+   for (int dz = 0; dz < D; dz++) { out[dz] = 0.0; }
+   // component offsets inside a slab
+   const int oc = has_diff ? 6 : 0, om = oc + (has_conv ? 3 : 0);
+   for (int qz = 0; qz < Q; qz++)
+   {
+      const double *base = Dq + (e * Q + qz) * (int64_t)slab;
+      double sbb = 0.0, sbg = 0.0, sgg = 0.0;          // partial sums that meet B^2, B G, G^2 in z
+      for (int qy = 0; qy < Q; qy++)
+      {
+         #pragma unroll
+         for (int qx = 0; qx < Q; qx++)
+         {
+            const double *dp = base + qx + Q * qy;
+            const double xx = bbx[qx] * bby[qy];
+            if (has_diff)
+            {
+               sbb += dp[0] * ggx[qx] * bby[qy] + 2.0 * dp[Q2] * bgx[qx] * bgy[qy] + dp[3 * Q2] * bbx[qx] * ggy[qy];
+               sbg += 2.0 * (dp[2 * Q2] * bgx[qx] * bby[qy] + dp[4 * Q2] * bbx[qx] * bgy[qy]);
+               sgg += dp[5 * Q2] * xx;
+            }
+            if (has_conv)
+            {
+               sbb += dp[oc * Q2] * bgx[qx] * bby[qy] + dp[(oc + 1) * Q2] * bbx[qx] * bgy[qy];
+               sbg += dp[(oc + 2) * Q2] * xx;
+            }
+            if (has_mass) { sbb += dp[om * Q2] * xx; }
+         }
+      }
+      #pragma unroll
+      for (int dz = 0; dz < D; dz++)
+      {
+         const double b = bs.B[qz * D + dz], g = bs.G[qz * D + dz];
+         out[dz] += b * b * sbb + b * g * sbg + g * g * sgg;
+      }
+   }
+   #pragma unroll
+   for (int dz = 0; dz < D; dz++) { dE[e * (D * D * D) + dx + D * (dy + D * dz)] = out[dz]; }
+}
+
 // ------------------------------------------------------------- launchers
 
 static BasisTables make_tables(const cdm_space *sp)
@@ -625,8 +689,19 @@ int cdm_k_diag(cdm_op *op, double *dL)
    const int64_t n = sp->ne * sp->nd;
    const unsigned nb = (unsigned)((n + 127) / 128);
    if (sp->dim == 3)
-      k_diag_elem<3><<<nb, 128, 0, ctx->stream>>>(bt, sp->d1d, sp->q1d, sp->ne, op->D_dev, op->slab,
-                                                  op->has_diff, op->has_conv, op->has_mass, op->yE_dev);
+   {
+      const unsigned nb3 = (unsigned)((sp->ne * sp->d1d * sp->d1d + 127) / 128);
+#define DIAG3(P) case P: k_diag3d_sumfact<P + 1, P + 2><<<nb3, 128, 0, ctx->stream>>>(                    \
+         bt, sp->ne, op->D_dev, op->slab, op->has_diff, op->has_conv, op->has_mass, op->yE_dev); break
+      switch (sp->p)
+      {
+         DIAG3(1); DIAG3(2); DIAG3(3); DIAG3(4); DIAG3(5); DIAG3(6);
+         default:
+            k_diag_elem<3><<<nb, 128, 0, ctx->stream>>>(bt, sp->d1d, sp->q1d, sp->ne, op->D_dev, op->slab,
+                                                        op->has_diff, op->has_conv, op->has_mass, op->yE_dev);
+      }
+#undef DIAG3
+   }
    else
       k_diag_elem<2><<<nb, 128, 0, ctx->stream>>>(bt, sp->d1d, sp->q1d, sp->ne, op->D_dev, op->slab,
                                                   op->has_diff, op->has_conv, op->has_mass, op->yE_dev);
