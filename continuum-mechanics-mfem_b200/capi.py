@@ -104,6 +104,11 @@ SIGNATURES = {
     "cdm_operator_get_qdata": (_ci, [_vp, _vp, _vp, _vp]),
     "cdm_operator_set_option": (_ci, [_vp, C.c_char_p, _ci]),
     "cdm_operator_time_kernel": (_ci, [_vp, _vp, _vp, _ci, _ci, C.POINTER(_cd)]),
+    "cdm_rule_points": (_ci, [_ci]),
+    "cdm_space_rule_coords": (_ci, [_vp, _ci, _vp]),
+    "cdm_domain_lf": (_ci, [_vp, _ci, _vp, _cd, _ci, _vp]),
+    "cdm_l2_error": (_ci, [_vp, _ci, _vp, _vp, C.POINTER(_cd)]),
+    "cdm_vec_set_indexed": (_ci, [_vp, _i64, _vp, _vp, _vp]),
     "cdm_launch_count": (_i64, [_vp]),
     "cdm_vec_alloc": (_ci, [_vp, _i64, _pp]),
     "cdm_vec_free": (_ci, [_vp, _vp]),
@@ -346,6 +351,41 @@ class H1Space:
         lib().cdm_space_qpt_coords(self.h, _ptr(out))
         return out
 
+    # --- linear forms, projection, error norms (the steps either side of the solve)
+    def rule_coords(self, q1d=0, out=None):
+        """physical points of the q1d^dim Gauss-Legendre rule, (ne, q1d^dim, dim); `out` may be a
+        CUDA tensor (the coordinates then stay on the device)"""
+        q = self.q1d if q1d == 0 else q1d
+        if out is None:
+            out = np.zeros((self.ne, q ** self.dim, self.dim))
+        self.ctx.check(lib().cdm_space_rule_coords(self.h, q1d, _ptr(out)))
+        return out
+
+    def domain_lf(self, f_q, b, q1d=0, scale=1.0, accumulate=False):
+        """b = [b +] scale * DomainLFIntegrator(f) assembled on the true dofs (b: device tensor)"""
+        if isinstance(f_q, np.ndarray):
+            f_q = np.ascontiguousarray(f_q, np.float64)
+        self.ctx.check(lib().cdm_domain_lf(self.h, q1d, _ptr(f_q), float(scale), 1 if accumulate else 0, _ptr(b)))
+        return b
+
+    def l2_error(self, u, uex_q, q1d=0):
+        """ComputeL2Error(u_h, u_exact) with the app's rule; u=None -> ||u_exact||, uex_q=None -> ||u_h||"""
+        if isinstance(uex_q, np.ndarray):
+            uex_q = np.ascontiguousarray(uex_q, np.float64)
+        r = C.c_double(0.0)
+        self.ctx.check(lib().cdm_l2_error(self.h, q1d, _ptr(u), _ptr(uex_q), C.byref(r)))
+        return r.value
+
+    def project_dofs(self, idx, vals, u):
+        """u[idx] = vals (ProjectBdrCoefficient with vals = g at the dof coordinates of idx)"""
+        if isinstance(idx, np.ndarray):
+            idx = np.ascontiguousarray(idx, np.int32)
+        if isinstance(vals, np.ndarray):
+            vals = np.ascontiguousarray(vals, np.float64)
+        n = idx.numel() if hasattr(idx, "numel") else len(idx)
+        self.ctx.check(lib().cdm_vec_set_indexed(self.ctx.h, n, _ptr(idx), _ptr(vals), _ptr(u)))
+        return u
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().cdm_space_destroy(self.h)
@@ -356,6 +396,11 @@ def _coeff(c, dim, which, keep):
     """None | scalar | vector | per-qpt array (ne, nq[, ncomp]) -> Coeff"""
     if c is None:
         return Coeff(COEFF_NONE, 0, None)
+    if hasattr(c, "data_ptr"):
+        # device-resident per-point values (torch.float64 CUDA tensor, (ne, nq[, ncomp])): used in place
+        t = c.contiguous()
+        keep.append(t)
+        return Coeff(COEFF_QPT, int(t.shape[2]) if t.dim() == 3 else 1, C.c_void_p(t.data_ptr()))
     a = np.ascontiguousarray(np.asarray(c, dtype=np.float64))
     keep.append(a)
     if a.ndim <= 1:
@@ -381,6 +426,8 @@ class ConvectionDiffusionOperator:
         self.h = C.c_void_p()
         self.ctx.check(lib().cdm_operator_create(space.h, C.byref(ck), C.byref(cv), float(alpha), C.byref(cm),
                                                  _ptr(ess), 0 if ess is None else len(ess), C.byref(self.h)))
+        if any(hasattr(k, "data_ptr") for k in keep):
+            self.ctx.sync()
         self.height = self.width = int(lib().cdm_operator_size(self.h))
         self.local_size = int(lib().cdm_operator_local_size(self.h))
         self.flags = (kappa is not None, vel is not None, mass is not None)
@@ -392,6 +439,8 @@ class ConvectionDiffusionOperator:
         ck, cv, cm = (_coeff(kappa, self.space.dim, 0, keep), _coeff(vel, self.space.dim, 1, keep),
                       _coeff(mass, self.space.dim, 2, keep))
         self.ctx.check(lib().cdm_operator_update(self.h, C.byref(ck), C.byref(cv), float(alpha), C.byref(cm)))
+        if any(hasattr(k, "data_ptr") for k in keep):
+            self.ctx.sync()          # device-resident coefficient tensors are read asynchronously
 
     def set_option(self, name, value):
         self.ctx.check(lib().cdm_operator_set_option(self.h, name.encode(), int(value)))

@@ -461,6 +461,7 @@ int cdm_space_destroy(cdm_space *sp)
    if (sp->ctx && sp->ctx->device >= 0)
    {
       cudaFree(sp->gather_dev); cudaFree(sp->offsets_dev); cudaFree(sp->indices_dev); cudaFree(sp->elem_x_dev);
+      cudaFree(sp->work_dev); cudaFree(sp->elem_part_dev);
       cdm_halo_plan &hp = sp->halo;
       cudaFree(hp.own_all_dev); cudaFree(hp.ghost_all_dev); cudaFree(hp.pt_dof_dev); cudaFree(hp.pt_off_dev);
       cudaFree(hp.pt_src_dev); cudaFree(hp.send_dev); cudaFree(hp.recv_dev);
@@ -550,6 +551,7 @@ int cdm_operator_destroy(cdm_op *op)
    if (op->sp && op->sp->ctx && op->sp->ctx->stream) { cudaStreamSynchronize(op->sp->ctx->stream); }
    cudaFree(op->D_dev); cudaFree(op->gather_c_dev); cudaFree(op->ess_dev); cudaFree(op->yE_dev);
    cudaFree(op->xL_dev); cudaFree(op->yL_dev); cudaFree(op->dinv_dev); cudaFree(op->kry_dev);
+   for (int i = 0; i < 3; i++) { cudaFree(op->coef_dev[i]); }
    delete op;
    return CDM_OK;
 }

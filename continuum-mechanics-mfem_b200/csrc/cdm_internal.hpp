@@ -92,6 +92,8 @@ struct cdm_space
    // device
    int32_t *gather_dev = nullptr, *offsets_dev = nullptr, *indices_dev = nullptr;
    double *elem_x_dev = nullptr;
+   double *work_dev = nullptr;                        // L-vector scratch of the form kernels (lazy, partitioned spaces)
+   double *elem_part_dev = nullptr;                   // per-block partial sums of the error-norm kernel (lazy)
    // multi-GPU
    std::vector<cdm_halo_peer> peers;
    cdm_halo_plan halo;
@@ -138,6 +140,8 @@ struct cdm_op
    // krylov workspace (lazy)
    double *kry_dev = nullptr; int64_t kry_len = 0;
    std::vector<double> coef_scratch;
+   double *coef_dev[3] = {nullptr, nullptr, nullptr};   // staging of host per-point coefficient arrays
+   size_t coef_bytes[3] = {0, 0, 0};
 };
 
 // ---- error helpers
@@ -203,6 +207,8 @@ int cdm_k_cg_update(cdm_ctx *c, int64_t n, double a, const double *d, const doub
 // ---- halo exchange (comm.cpp)
 int cdm_halo_P(cdm_op *op, double *xL);            // owner -> ghost values
 int cdm_halo_PT(cdm_op *op, double *yL);           // ghost partial sums -> owner (add)
+int cdm_halo_P_space(cdm_space *sp, double *xL);   // the same exchanges for callers without an operator
+int cdm_halo_PT_space(cdm_space *sp, double *yL);
 int cdm_allreduce_sum(cdm_ctx *c, double *buf_dev, int k);
 // same exchanges on the halo stream / communicator; ev_packed is recorded right after the pack kernel
 int cdm_halo_P_async(cdm_op *op, double *xL, cudaEvent_t ev_packed);

@@ -117,9 +117,8 @@ struct StreamSwap
 
 // x_L ghost entries <- owner values.  halo_stream: run on the halo stream / communicator and record
 // ev_packed right after the pack kernel (the compute stream waits on it before filling the GPU).
-static int halo_P_impl(cdm_op *op, double *xL, bool halo_stream, cudaEvent_t ev_packed)
+static int halo_P_impl(cdm_space *sp, double *xL, bool halo_stream, cudaEvent_t ev_packed)
 {
-   cdm_space *sp = op->sp;
    cdm_ctx *c = sp->ctx;
    if (!c->comm) { return cdm_fail(c, CDM_ENCCL, "partitioned space used without cdm_comm_init"); }
    NcclApi *a = api();
@@ -139,13 +138,13 @@ static int halo_P_impl(cdm_op *op, double *xL, bool halo_stream, cudaEvent_t ev_
    return cdm_k_unpack(c, (int64_t)hp.ghost_all.size(), hp.ghost_all_dev, hp.recv_dev, xL, 0);
 }
 
-int cdm_halo_P(cdm_op *op, double *xL) { return halo_P_impl(op, xL, false, nullptr); }
-int cdm_halo_P_async(cdm_op *op, double *xL, cudaEvent_t ev_packed) { return halo_P_impl(op, xL, true, ev_packed); }
+int cdm_halo_P(cdm_op *op, double *xL) { return halo_P_impl(op->sp, xL, false, nullptr); }
+int cdm_halo_P_async(cdm_op *op, double *xL, cudaEvent_t ev_packed) { return halo_P_impl(op->sp, xL, true, ev_packed); }
+int cdm_halo_P_space(cdm_space *sp, double *xL) { return halo_P_impl(sp, xL, false, nullptr); }
 
 // owner entries of y_L += partial sums held in the sharers' ghost entries (fixed peer order)
-static int halo_PT_impl(cdm_op *op, double *yL, bool halo_stream, cudaEvent_t ev_packed)
+static int halo_PT_impl(cdm_space *sp, double *yL, bool halo_stream, cudaEvent_t ev_packed)
 {
-   cdm_space *sp = op->sp;
    cdm_ctx *c = sp->ctx;
    if (!c->comm) { return cdm_fail(c, CDM_ENCCL, "partitioned space used without cdm_comm_init"); }
    NcclApi *a = api();
@@ -165,5 +164,6 @@ static int halo_PT_impl(cdm_op *op, double *yL, bool halo_stream, cudaEvent_t ev
    return cdm_k_unpack_add_csr(c, (int64_t)hp.pt_dof.size(), hp.pt_dof_dev, hp.pt_off_dev, hp.pt_src_dev, hp.recv_dev, yL);
 }
 
-int cdm_halo_PT(cdm_op *op, double *yL) { return halo_PT_impl(op, yL, false, nullptr); }
-int cdm_halo_PT_async(cdm_op *op, double *yL, cudaEvent_t ev_packed) { return halo_PT_impl(op, yL, true, ev_packed); }
+int cdm_halo_PT(cdm_op *op, double *yL) { return halo_PT_impl(op->sp, yL, false, nullptr); }
+int cdm_halo_PT_async(cdm_op *op, double *yL, cudaEvent_t ev_packed) { return halo_PT_impl(op->sp, yL, true, ev_packed); }
+int cdm_halo_PT_space(cdm_space *sp, double *yL) { return halo_PT_impl(sp, yL, false, nullptr); }

@@ -165,18 +165,28 @@ int cdm_k_setup_qdata(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel, 
    a.alpha = alpha;
    for (int i = 0; i < sp->q1d; i++) { a.qx[i] = sp->qx[i]; a.qw[i] = sp->qw[i]; }
    const int64_t npts = sp->ne * sp->nq;
-   double *tmp[3] = {nullptr, nullptr, nullptr};
+   // per-point coefficient arrays: device pointers are used in place (no copy); host arrays go through a
+   // staging buffer kept on the operator, so a per-step cdm_operator_update (ALE drivers,
+   // diffusion_mms_ale.cpp:1017-1023) does not allocate
+   bool staged_host = false;
    auto stage = [&](const cdm_coeff *c, int ncomp, double *cst, const double **qptr, int *kind, int slot) -> int
    {
       *kind = c->kind;
-      if (c->kind == CDM_COEFF_CONST) { for (int i = 0; i < ncomp; i++) { cst[i] = c->data[i]; } }
-      else
+      if (c->kind == CDM_COEFF_CONST) { for (int i = 0; i < ncomp; i++) { cst[i] = c->data[i]; } return CDM_OK; }
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, c->data) == cudaSuccess &&
+          (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) { *qptr = c->data; return CDM_OK; }
+      cudaGetLastError();
+      const size_t bytes = (size_t)npts * ncomp * sizeof(double);
+      if (op->coef_bytes[slot] < bytes)
       {
-         const size_t bytes = (size_t)npts * ncomp * sizeof(double);
-         CDM_CUDA(ctx, cudaMalloc(&tmp[slot], bytes));
-         CDM_CUDA(ctx, cudaMemcpyAsync(tmp[slot], c->data, bytes, cudaMemcpyHostToDevice, ctx->stream));
-         *qptr = tmp[slot];
+         if (op->coef_dev[slot]) { cudaFree(op->coef_dev[slot]); op->coef_dev[slot] = nullptr; op->coef_bytes[slot] = 0; }
+         CDM_CUDA(ctx, cudaMalloc(&op->coef_dev[slot], bytes));
+         op->coef_bytes[slot] = bytes;
       }
+      CDM_CUDA(ctx, cudaMemcpyAsync(op->coef_dev[slot], c->data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      *qptr = op->coef_dev[slot];
+      staged_host = true;
       return CDM_OK;
    };
    int rc = CDM_OK;
@@ -193,11 +203,8 @@ int cdm_k_setup_qdata(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel, 
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) { rc = cdm_fail(ctx, CDM_ECUDA, std::string("k_setup_qdata: ") + cudaGetErrorString(e)); }
    }
-   if (tmp[0] || tmp[1] || tmp[2])
-   {
-      cudaStreamSynchronize(ctx->stream);
-      for (int i = 0; i < 3; i++) if (tmp[i]) { cudaFree(tmp[i]); }
-   }
+   // the caller may reuse (pinned) host arrays as soon as this returns
+   if (staged_host) { cudaStreamSynchronize(ctx->stream); }
    return rc;
 }
 

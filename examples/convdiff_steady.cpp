@@ -1,7 +1,8 @@
 // convdiff_steady.cpp -- the reference's steady driver (linear_convection_diffusion_2D.cpp:238-446)
 // re-hosted on the B200 library through the MFEM-shaped shim: same sequence of calls
 // (mesh -> H1 space -> essential dofs -> Diffusion+Convection+Mass form -> linear form ->
-// boundary projection -> FormLinearSystem -> GMRES+Jacobi -> error vs the manufactured solution),
+// boundary projection -> FormLinearSystem -> GMRES+Jacobi -> L2 error vs the manufactured solution),
+// every step on the device,
 // on an inline-hex (or inline-quad) Cartesian mesh instead of the Gmsh triangle mesh.
 //
 //   ./convdiff_steady [dim=3] [n=16] [order=3]
@@ -51,25 +52,13 @@ int main(int argc, char **argv)
       a.SetEssentialTrueDofs(ess_tdof_list);
       a.Assemble();
 
-      // ParLinearForm b: DomainLFIntegrator(f) (:341-343) = (mass form weighted by f) applied to 1
+      // ParLinearForm b: DomainLFIntegrator(f) (:341-343)
       const int64_t N = fespace.GetTrueVSize();
-      cdm::Vector b(device, N), one(device, N), u(device, N), X(device, N);
-      {
-         const std::vector<double> xq = fespace.QuadraturePointCoordinates();
-         std::vector<double> fq(xq.size() / dim);
-         for (size_t i = 0; i < fq.size(); i++) { fq[i] = forcing(&xq[i * dim]); }
-         cdm::ConvectionDiffusionForm lf(fespace);
-         lf.AddMassIntegrator(fq);
-         lf.Assemble();
-         one = 1.0;
-         lf.MultUnconstrained(one, b);
-      }
+      cdm::Vector b(device, N), u(device, N), X(device, N);
+      fespace.AssembleDomainLF(forcing, b);
       // u = 0; u.ProjectBdrCoefficient(exact, ess_bdr) (:345-347)
-      const std::vector<double> xd = fespace.DofCoordinates();
-      std::vector<double> uex(N), ub(N, 0.0);
-      for (int64_t i = 0; i < N; i++) { uex[i] = exact(&xd[i * dim]); }
-      for (int32_t i : ess_tdof_list) { ub[i] = uex[i]; }
-      u.SetFromHost(ub.data());
+      u = 0.0;
+      fespace.ProjectBdrCoefficient(exact, ess_tdof_list, u);
       a.FormLinearSystem(u, b);                                       // (:351)
 
       // PetscLinearSolver with Input/petsc.opts: gmres, rtol 1e-10, atol 1e-12, max_it 500, jacobi (:368-374)
@@ -83,13 +72,13 @@ int main(int argc, char **argv)
          throw std::runtime_error("solver did not converge. Iterations=" + std::to_string(solver.GetNumIterations()) +
                                   ", residual=" + std::to_string(solver.GetFinalNorm()));
       }
-      // nodal error against the manufactured solution
-      const std::vector<double> xs = X.HostCopy();
-      double e2 = 0.0, n2 = 0.0;
-      for (int64_t i = 0; i < N; i++) { e2 += (xs[i] - uex[i]) * (xs[i] - uex[i]); n2 += uex[i] * uex[i]; }
+      // u.ComputeL2Error(exact, irs) / ComputeGlobalLpNorm with rules of order max(2, 2p+3) (:383-392)
+      const double abs_l2 = fespace.ComputeL2Error(X, exact);
+      const double exact_l2 = fespace.ComputeGlobalL2Norm(exact);
+      const double rel_l2 = (exact_l2 > 1.0e-14) ? abs_l2 / exact_l2 : 0.0;
       std::printf("GMRES iterations: %d, final residual %.3e, solve %.3f ms\n", solver.GetNumIterations(),
                   solver.GetFinalNorm(), solver.GetSolveSeconds() * 1e3);
-      std::printf("nodal l2 error (relative): %.6e\n", std::sqrt(e2 / n2));
+      std::printf("L2 error: abs %.6e  rel %.6e\n", abs_l2, rel_l2);
    }
    catch (const std::exception &e)
    {

@@ -183,6 +183,34 @@ int  cdm_operator_set_option(cdm_op *op, const char *name, int value);
    stream directly around each launch; no halo, no essential fix-up) */
 int  cdm_operator_time_kernel(cdm_op *op, const double *x_dev, double *y_dev, int reps, int constrained,
                               double *mean_ms);
+/* ------------------------------ linear forms, projection and error norms */
+/* Points per direction of MFEM's IntRules.Get(SEGMENT/SQUARE/CUBE, order): order/2 + 1. */
+int  cdm_rule_points(int order);
+/* Physical coordinates of the tensor Gauss-Legendre rule with q1d points per direction in every
+   element, xyz[(e*q1d^dim + q)*dim + c], x fastest: what Coefficient::Eval(T, ip) sees for that rule
+   (forcing_coeff / exact_coeff, linear_convection_diffusion_2D.cpp:159-215).  q1d = 0 selects the
+   operator's rule.  xyz may be a host or a device pointer (computed on the device either way). */
+int  cdm_space_rule_coords(const cdm_space *space, int q1d, double *xyz);
+/* ParLinearForm b; b.AddDomainIntegrator(new DomainLFIntegrator(f)); b.Assemble(); (+ ParallelAssemble)
+   (linear_convection_diffusion_2D.cpp:341-343; once per step at diffusion_mms.cpp:433-437):
+     b_dev = (accumulate ? b_dev : 0) + scale * P^T sum_e B^T (w |J| f)
+   f_q[e*q1d^dim + q]: f at cdm_space_rule_coords(space, q1d) (host or device pointer).
+   q1d = 0 selects DomainLFIntegrator's default rule (order 2p -> p+1 points). b_dev: true-dof vector. */
+int  cdm_domain_lf(cdm_space *space, int q1d, const double *f_q, double scale, int accumulate,
+                   double *b_dev);
+/* u.ComputeL2Error(exact, irs) / ComputeGlobalLpNorm(2, exact, mesh, irs)
+   (linear_convection_diffusion_2D.cpp:383-392, diffusion_mms.cpp:466-470):
+     result = sqrt( sum_e sum_q w |J| (u_h(x_q) - uex_q)^2 ), all-reduced over the ranks.
+   u_dev NULL -> ||uex||, uex_q NULL -> ||u_h||.  q1d = 0 selects the app's rule (order max(2, 2p+3)).
+   uex_q: host or device pointer.  Fixed launch shape: the result is bit-reproducible run to run. */
+int  cdm_l2_error(cdm_space *space, int q1d, const double *u_dev, const double *uex_q,
+                  double *result_host);
+/* u_dev[idx[i]] = vals[i]: u.ProjectBdrCoefficient(g, ess_bdr) with idx = the essential dofs and
+   vals = g at their cdm_space_dof_coords (linear_convection_diffusion_2D.cpp:347; per step at
+   linear_convection_diffusion_1D.cpp:545-546).  idx / vals: host or device pointers. */
+int  cdm_vec_set_indexed(cdm_ctx *ctx, int64_t n, const int32_t *idx, const double *vals,
+                         double *u_dev);
+
 /* number of kernel launches issued by this context so far */
 int64_t cdm_launch_count(const cdm_ctx *ctx);
 

@@ -15,7 +15,10 @@
 // not converge is NOT an exception: query GetConverged() like the app does (:371).
 #pragma once
 #include "cdm_b200.h"
+#include <algorithm>
 #include <cstdint>
+#include <functional>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -159,11 +162,71 @@ public:
       cdm_space_qpt_coords(h_, x.data());
       return x;
    }
+   int GetOrder() const { return order_; }
+   // physical points of the rule IntRules.Get(geom, order) in every element (what Coefficient::Eval sees)
+   const std::vector<double> &RulePoints(int rule_order) const
+   {
+      const int q1d = cdm_rule_points(rule_order);
+      auto it = rule_pts_.find(q1d);
+      if (it != rule_pts_.end()) { return it->second; }
+      size_t nq = 1;
+      for (int d = 0; d < dim_; d++) { nq *= (size_t)q1d; }
+      std::vector<double> x((size_t)ne_ * nq * dim_);
+      check(ctx_, cdm_space_rule_coords(h_, q1d, x.data()), "cdm_space_rule_coords");
+      return rule_pts_.emplace(q1d, std::move(x)).first->second;
+   }
+   // FunctionCoefficient evaluated at the points of a rule
+   std::vector<double> EvalAtRule(int rule_order, const std::function<double(const double *)> &f) const
+   {
+      const std::vector<double> &x = RulePoints(rule_order);
+      std::vector<double> v(x.size() / dim_);
+      for (size_t i = 0; i < v.size(); i++) { v[i] = f(&x[i * dim_]); }
+      return v;
+   }
+   // ParLinearForm b(&fes); b.AddDomainIntegrator(new DomainLFIntegrator(f)); b.Assemble();
+   // b = [b +] scale * (f, v)  (linear_convection_diffusion_2D.cpp:341-343, diffusion_mms.cpp:433-437)
+   void AssembleDomainLF(const std::function<double(const double *)> &f, Vector &b, double scale = 1.0,
+                         bool accumulate = false) const
+   {
+      const int ord = 2 * order_;                              // DomainLFIntegrator(Q, a = 2, b = 0)
+      const std::vector<double> fq = EvalAtRule(ord, f);
+      check(ctx_, cdm_domain_lf(h_, cdm_rule_points(ord), fq.data(), scale, accumulate ? 1 : 0, b.ReadWrite()), "cdm_domain_lf");
+      check(ctx_, cdm_sync(ctx_), "cdm_sync");                 // fq is a temporary
+   }
+   // u.ProjectBdrCoefficient(g, ess_bdr) on the dofs of `ess` (linear_convection_diffusion_2D.cpp:347)
+   void ProjectBdrCoefficient(const std::function<double(const double *)> &g, const std::vector<int32_t> &ess, Vector &u) const
+   {
+      if (dof_x_.empty()) { dof_x_ = DofCoordinates(); }
+      std::vector<double> vals(ess.size());
+      for (size_t i = 0; i < ess.size(); i++) { vals[i] = g(&dof_x_[(size_t)ess[i] * dim_]); }
+      check(ctx_, cdm_vec_set_indexed(ctx_, (int64_t)ess.size(), ess.data(), vals.data(), u.ReadWrite()), "cdm_vec_set_indexed");
+      check(ctx_, cdm_sync(ctx_), "cdm_sync");
+   }
+   // u.ComputeL2Error(exact, irs) with irs of order max(2, 2p+3) (linear_convection_diffusion_2D.cpp:383-390)
+   double ComputeL2Error(const Vector &u, const std::function<double(const double *)> &exact) const
+   {
+      const int ord = std::max(2, 2 * order_ + 3);
+      const std::vector<double> ex = EvalAtRule(ord, exact);
+      double r = 0.0;
+      check(ctx_, cdm_l2_error(h_, cdm_rule_points(ord), u.Read(), ex.data(), &r), "cdm_l2_error");
+      return r;
+   }
+   // ComputeGlobalLpNorm(2, exact, mesh, irs) (:391)
+   double ComputeGlobalL2Norm(const std::function<double(const double *)> &exact) const
+   {
+      const int ord = std::max(2, 2 * order_ + 3);
+      const std::vector<double> ex = EvalAtRule(ord, exact);
+      double r = 0.0;
+      check(ctx_, cdm_l2_error(h_, cdm_rule_points(ord), nullptr, ex.data(), &r), "cdm_l2_error");
+      return r;
+   }
    cdm_space *handle() const { return h_; }
    cdm_ctx *ctx() const { return ctx_; }
 private:
    cdm_ctx *ctx_;
    cdm_space *h_ = nullptr;
+   mutable std::map<int, std::vector<double>> rule_pts_;
+   mutable std::vector<double> dof_x_;
    int dim_ = 0, order_ = 0, d1d_ = 0, q1d_ = 0;
    int64_t ne_ = 0, ndof_ = 0, ntrue_ = 0;
 };

@@ -49,6 +49,17 @@ void orc_restriction(int64_t ne, int nd, int64_t ndof, const int32_t *gather,
 void orc_node_coords(int dim, int p, int64_t ne, const int32_t *ev, const double *vx,
                      double *out);
 
+/* ---- linear forms and error norms (oracle_forms.c) ----
+ * orc_rule_coords: physical coordinates of the q1d^dim tensor Gauss-Legendre rule,
+ *   out[(e*nq+q)*dim + c] -- where the caller evaluates f / u_exact (Coefficient::Eval).
+ * orc_domain_lf: DomainLFIntegrator, b[elem_dof] += scale * w|J| f_q phi_i (MFEM default rule: q1d = p+1).
+ * orc_l2_error: GridFunction::ComputeL2Error (u, uex_q), ComputeGlobalLpNorm(2) (u = NULL). */
+void orc_rule_coords(int dim, int q1d, int64_t ne, const int32_t *ev, const double *vx, double *out);
+void orc_domain_lf(int dim, int p, int q1d, int64_t ne, const int32_t *ev, const double *vx,
+                   const int32_t *elem_dof, const double *f_q, double scale, double *b);
+double orc_l2_error(int dim, int p, int q1d, int64_t ne, const int32_t *ev, const double *vx,
+                    const int32_t *elem_dof, const double *u, const double *uex_q);
+
 /* ---- quadrature data (MFEM bilininteg_{diffusion,convection,mass}_pa) ----
  * coefficient kinds: 0 absent, 1 constant, 2 per-quadrature-point array
  * (point-major: value index = (e*NQ + q)*ncomp + c).

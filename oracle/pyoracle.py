@@ -83,6 +83,10 @@ def lib():
     L.orc_op_eliminate_rhs.argtypes = [vp, f64p, f64p]
     L.orc_gmres.argtypes = [vp, vp, f64p, f64p, C.POINTER(KOpts), C.POINTER(KRes), f64p]
     L.orc_cg.argtypes = [vp, vp, f64p, f64p, C.POINTER(KOpts), C.POINTER(KRes), f64p]
+    L.orc_rule_coords.argtypes = [ci, ci, i64, i32p, f64p, f64p]
+    L.orc_domain_lf.argtypes = [ci, ci, ci, i64, i32p, f64p, i32p, f64p, cd, f64p]
+    L.orc_l2_error.argtypes = [ci, ci, ci, i64, i32p, f64p, i32p, vp, vp]
+    L.orc_l2_error.restype = cd
     L.orc_num_threads.restype = ci
     L.orc_set_num_threads.argtypes = [ci]
     _lib = L
@@ -275,6 +279,29 @@ class Problem:
         out = np.zeros((self.ndof, self.dim))
         out[self.elem_dof.reshape(-1)] = xc.reshape(-1, self.dim)
         return out
+
+    # --- linear forms / error norms (oracle_forms.c)
+    def rule_coords(self, q1d):
+        """physical points of the q1d^dim Gauss-Legendre rule: (ne, q1d^dim, dim)"""
+        out = np.zeros((self.ne, q1d ** self.dim, self.dim))
+        lib().orc_rule_coords(self.dim, q1d, self.ne, self.ev, self.vx, out)
+        return out
+
+    def domain_lf(self, f_q, q1d=None, scale=1.0, b=None):
+        """DomainLFIntegrator with MFEM's default rule (p+1 points per direction)"""
+        q1d = self.p + 1 if q1d is None else q1d
+        b = np.zeros(self.ndof) if b is None else b
+        lib().orc_domain_lf(self.dim, self.p, q1d, self.ne, self.ev, self.vx, self.elem_dof,
+                            np.ascontiguousarray(f_q, np.float64).reshape(-1), float(scale), b)
+        return b
+
+    def l2_error(self, u, uex_q, q1d=None):
+        """ComputeL2Error with the reference's rule order max(2, 2p+3) -> p+2 points"""
+        q1d = max(2, 2 * self.p + 3) // 2 + 1 if q1d is None else q1d
+        uu = None if u is None else np.ascontiguousarray(u, np.float64)
+        qq = None if uex_q is None else np.ascontiguousarray(uex_q, np.float64).reshape(-1)
+        return lib().orc_l2_error(self.dim, self.p, q1d, self.ne, self.ev, self.vx, self.elem_dof,
+                                  _opt(uu), _opt(qq))
 
 
 class CSR:

@@ -130,6 +130,17 @@ def main():
         print(f"[rank {rank}] diag err {err:.2e} gmres iters {s.GetNumIterations()}/{info['iters']} hist err {herr:.2e} sol err {serr:.2e}", flush=True)
         nrm = ctx.norm2(xd)
         ok &= abs(nrm - np.linalg.norm(xg)) < 1e-12 * np.linalg.norm(xg)      # all-reduced dot over T-dofs
+        # linear form (P^T-assembled) and L2 error (ghost values via P, all-reduced) on the partitioned space
+        fn = lambda x: 1.0 + np.sin(2.3 * x[..., 0]) * np.cos(1.7 * x[..., 1]) + 0.5 * x[..., 2] ** 2
+        lf_g = P.domain_lf(fn(P.rule_coords(p + 1)))
+        lf = torch.zeros(nt, dtype=torch.float64, device="cuda")
+        sp.domain_lf(fn(sp.rule_coords(p + 1)), lf)
+        ctx.sync()
+        lerr = np.linalg.norm(lf.cpu().numpy() - lf_g[mine[:nt]]) / np.linalg.norm(lf_g)
+        e_g = P.l2_error(xg, fn(P.rule_coords(p + 2)))
+        e_l = sp.l2_error(xd, fn(sp.rule_coords(p + 2)))
+        ok &= lerr < 1e-12 and abs(e_l - e_g) < 1e-12 * e_g
+        print(f"[rank {rank}] linear form err {lerr:.2e}  L2 error {e_l:.12e} vs {e_g:.12e}", flush=True)
     else:
         # host emulation of cdm_halo_P / cdm_halo_PT with gloo, element work by the oracle
         lvx, lev, lbv, lba = lm.arrays()
