@@ -34,5 +34,5 @@ def test_steady_driver_converges_to_manufactured_solution(dim, n, order, tol):
     r = subprocess.run([EXE, str(dim), str(n), str(order)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     its = int(re.search(r"GMRES iterations: (\d+)", r.stdout).group(1))
-    err = float(re.search(r"nodal l2 error \(relative\): ([0-9.e+-]+)", r.stdout).group(1))
+    err = float(re.search(r"L2 error: abs [0-9.e+-]+\s+rel ([0-9.e+-]+)", r.stdout).group(1))
     assert 0 < its < 500 and err < tol, r.stdout
