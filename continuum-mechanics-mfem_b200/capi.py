@@ -18,7 +18,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcdm_b200.so")
+# CDM_B200_LIB: load another build of the same library (kernel-tuning experiments, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("CDM_B200_LIB") or os.path.join(_HERE, "libcdm_b200.so")
 
 OK, EINVAL, ENOGPU, ECUDA, ENOMEM, ENCCL, EUNSUP = 0, -1, -2, -3, -4, -5, -6
 COEFF_NONE, COEFF_CONST, COEFF_QPT = 0, 1, 2

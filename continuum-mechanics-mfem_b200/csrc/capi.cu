@@ -529,7 +529,8 @@ int cdm_operator_create(cdm_space *sp, const cdm_coeff *kappa, const cdm_coeff *
    if (rc) { cdm_operator_destroy(op); return rc; }
    // default kernel per order (measured, profiles/): p=3 hand-specialised register-z kernel,
    // p>=4 the generic group kernel, p<=2 and 2D the block kernel
-   op->kernel_variant = (sp->dim == 3 && sp->p == 3) ? 3 : ((sp->dim == 3 && sp->p >= 4) ? 4 : 0);
+   // 3D defaults: sub-warp kernel (5) for orders 1-2, warp kernel (3) for order 3, group kernel (4) above
+   op->kernel_variant = (sp->dim != 3) ? 0 : (sp->p <= 2 ? 5 : (sp->p == 3 ? 3 : 4));
    *out = op;
    return CDM_OK;
 }
@@ -598,7 +599,7 @@ int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained)
    // option "overlap" = 2 forces it.
    if (par && (op->overlap == 2 || (op->overlap == 1 && sp->peers.size() <= 3)) && ctx->stream_halo &&
        op->scatter_mode == 1 && sp->dim == 3 &&
-       (op->kernel_variant == 3 || op->kernel_variant == 4) && sp->n_bdr_elems > 0 && sp->n_bdr_elems < sp->ne)
+       (op->kernel_variant >= 3 && op->kernel_variant <= 5) && sp->n_bdr_elems > 0 && sp->n_bdr_elems < sp->ne)
    {
       cudaStream_t C = ctx->stream, H = ctx->stream_halo;
       cudaEvent_t *ev = ctx->ev_h;
@@ -816,7 +817,7 @@ int cdm_operator_mult_host(cdm_op *op, const double *x_host, double *y_host, int
    cdm_ctx *ctx = sp->ctx;
    int rc = ensure_L(op); if (rc) { return rc; }
    if (op->host_pipeline && ctx->nranks == 1 && sp->dim == 3 && sp->class_off.size() == 5 && op->scatter_mode == 1 &&
-       (op->kernel_variant == 3 || op->kernel_variant == 4) && sp->ne >= 8192)
+       (op->kernel_variant >= 3 && op->kernel_variant <= 5) && sp->ne >= 8192)
    {
       return mult_host_pipelined(op, x_host, y_host, constrained != 0);
    }

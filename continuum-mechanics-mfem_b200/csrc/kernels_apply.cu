@@ -621,6 +621,7 @@ static int ensure_yE(cdm_op *op)
 
 int cdm_k_apply_p3(cdm_op *op, const int32_t *gmap, const double *xL, double *yL);   // kernels_apply_p3.cu
 int cdm_k_apply_group(cdm_op *op, const int32_t *gmap, const double *xL, double *yL);   // kernels_apply_warp.cu
+int cdm_k_apply_sub(cdm_op *op, const int32_t *gmap, const double *xL, double *yL);     // kernels_apply_sub.cu
 
 #define LAUNCH3D(P, NBZ)                                                                              \
    case P: {                                                                                          \
@@ -646,6 +647,11 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
    if (sp->dim == 3 && op->kernel_variant == 4)
    {
       const int rc = cdm_k_apply_group(op, gmap, xL, yL);
+      if (rc != 1) { return rc; }
+   }
+   else if (sp->dim == 3 && op->kernel_variant == 5)
+   {
+      const int rc = cdm_k_apply_sub(op, gmap, xL, yL);
       if (rc != 1) { return rc; }
    }
    else if (sp->dim == 3 && sp->p == 3 && op->kernel_variant >= 1)

@@ -173,6 +173,28 @@ def test_group_kernel_all_orders(torch, ctx, orc, p, n, which):
         assert rel(D.down(yd), P.pa_op(True).mult(x)) < APPLY_TOL
 
 
+@pytest.mark.parametrize("p,n", [(1, 5), (1, 8), (2, 4), (2, 7)])
+@pytest.mark.parametrize("which", ["full", "mass", "diff+mass", "diff"])
+def test_subwarp_kernel_low_orders(torch, ctx, orc, p, n, which):
+    """kernel option 5: two elements per warp (one per half warp) for orders 1 and 2; odd element counts
+    leave the last warp with a single element"""
+    kw = dict(full=dict(), mass=dict(kappa=None, vel=None, mass=1.3), diff=dict(kappa=0.3, vel=None, mass=None))
+    kw["diff+mass"] = dict(kappa=0.3, vel=None, mass=2.0)
+    P, mesh, sp = make(ctx, orc, 3, p, [n, n, n + 2], perturb=0.12, shuffle_seed=p, **kw[which])
+    assert P.ne % 2 == 1 or n % 2 == 0
+    D = Dev(torch, ctx)
+    x = np.random.default_rng(13).uniform(-1, 1, P.ndof)
+    for scatter in (0, 1):
+        op = make_op(P, sp)
+        op.set_option("kernel", 5)
+        op.set_option("scatter", scatter)
+        xd, yd = D.up(x), D.zeros(P.ndof)
+        op.MultUnconstrained(xd, yd)
+        assert rel(D.down(yd), P.pa_apply(x)) < APPLY_TOL
+        op.Mult(xd, yd)
+        assert rel(D.down(yd), P.pa_op(True).mult(x)) < APPLY_TOL
+
+
 @pytest.mark.parametrize("dim,p,n", [(2, 2, 4), (3, 2, 3), (3, 3, 3)])
 @pytest.mark.parametrize("which", ["mass", "diff", "diff+mass", "conv", "heat"])
 def test_integrator_subsets(torch, ctx, orc, dim, p, n, which):
