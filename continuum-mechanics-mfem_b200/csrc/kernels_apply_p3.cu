@@ -65,6 +65,17 @@ __device__ __forceinline__ void red_add_f64(double *addr, double v)
 {
    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
+// y[g] += v unless g < 0 (essential dof).  A predicated red (-DCDM_P3_PREDICATED_RED) measured the same as
+// the branch within run-to-run noise on config 2, so the branch stays.
+__device__ __forceinline__ void red_add_f64_if(double *y, int g, double v)
+{
+#ifndef CDM_P3_PREDICATED_RED
+   if (g >= 0) { red_add_f64(y + g, v); }
+#else
+   asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %2, 0;\n@p red.global.add.f64 [%0], %1;\n}\n"
+                ::"l"(y + g), "d"(v), "r"(g) : "memory");
+#endif
+}
 
 // Lane roles (D1D = 4, Q1D = 5):
 //   L1 lanes (dy,dz)  l < 16 : own one x-line of nodal values (gather / scatter, x contraction)
@@ -607,10 +618,10 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
          }
          if (ATOMIC)
          {
-            if (g.x >= 0) { red_add_f64(y + g.x, yv[0]); }
-            if (g.y >= 0) { red_add_f64(y + g.y, yv[1]); }
-            if (g.z >= 0) { red_add_f64(y + g.z, yv[2]); }
-            if (g.w >= 0) { red_add_f64(y + g.w, yv[3]); }
+            red_add_f64_if(y, g.x, yv[0]);
+            red_add_f64_if(y, g.y, yv[1]);
+            red_add_f64_if(y, g.z, yv[2]);
+            red_add_f64_if(y, g.w, yv[3]);
          }
          else
          {
