@@ -598,8 +598,7 @@ int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained)
    // with the persistent element kernel for SM slots), so by default only used up to 3 neighbours;
    // option "overlap" = 2 forces it.
    if (par && (op->overlap == 2 || (op->overlap == 1 && sp->peers.size() <= 3)) && ctx->stream_halo &&
-       op->scatter_mode == 1 && sp->dim == 3 &&
-       (op->kernel_variant >= 3 && op->kernel_variant <= 5) && sp->n_bdr_elems > 0 && sp->n_bdr_elems < sp->ne)
+       op->scatter_mode == 1 && cdm_k_range_capable(op) && sp->n_bdr_elems > 0 && sp->n_bdr_elems < sp->ne)
    {
       cudaStream_t C = ctx->stream, H = ctx->stream_halo;
       cudaEvent_t *ev = ctx->ev_h;
@@ -817,7 +816,7 @@ int cdm_operator_mult_host(cdm_op *op, const double *x_host, double *y_host, int
    cdm_ctx *ctx = sp->ctx;
    int rc = ensure_L(op); if (rc) { return rc; }
    if (op->host_pipeline && ctx->nranks == 1 && sp->dim == 3 && sp->class_off.size() == 5 && op->scatter_mode == 1 &&
-       (op->kernel_variant >= 3 && op->kernel_variant <= 5) && sp->ne >= 8192)
+       cdm_k_range_capable(op) && sp->ne >= 8192)
    {
       return mult_host_pipelined(op, x_host, y_host, constrained != 0);
    }

@@ -171,6 +171,7 @@ void cdm_host_restriction(int64_t ne, int nd, int64_t ndof, const std::vector<in
 int cdm_k_setup_qdata(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel, double alpha,
                       const cdm_coeff *mass);
 int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained);
+bool cdm_k_range_capable(const cdm_op *op);   // does the selected kernel honour op->range_on?
 int cdm_k_diag(cdm_op *op, double *dL);
 int cdm_k_get_qdata(const cdm_op *op, double *Ddiff, double *Dconv, double *Dmass);
 int cdm_k_upload_basis(cdm_space *sp);

@@ -626,17 +626,27 @@ int cdm_k_apply_sub(cdm_op *op, const int32_t *gmap, const double *xL, double *y
 #define LAUNCH3D(P, NBZ)                                                                              \
    case P: {                                                                                          \
       dim3 blk(P + 2, P + 2, NBZ);                                                                    \
-      const unsigned nb = (unsigned)((sp->ne + NBZ - 1) / NBZ);                                       \
+      const unsigned nb = (unsigned)((n_el + NBZ - 1) / NBZ);                                         \
       k_apply3d_generic<P + 1, P + 2, NBZ><<<nb, blk, 0, ctx->stream>>>(                              \
-         bt, sp->ne, gmap, xL, op->D_dev, op->slab, op->has_diff, op->has_conv, op->has_mass, out, atomic); \
+         bt, n_el, gmap + e0 * sp->nd, xL, op->D_dev + e0 * (int64_t)sp->q1d * op->slab, op->slab,    \
+         op->has_diff, op->has_conv, op->has_mass, atomic ? out : out + e0 * sp->nd, atomic);         \
    } break
 #define LAUNCH2D(P, NBZ)                                                                              \
    case P: {                                                                                          \
       dim3 blk(P + 1, P + 1, NBZ);                                                                    \
-      const unsigned nb = (unsigned)((sp->ne + NBZ - 1) / NBZ);                                       \
+      const unsigned nb = (unsigned)((n_el + NBZ - 1) / NBZ);                                         \
       k_apply2d_generic<P + 1, P + 1, NBZ><<<nb, blk, 0, ctx->stream>>>(                              \
-         bt, sp->ne, gmap, xL, op->D_dev, op->slab, op->has_diff, op->has_conv, op->has_mass, out, atomic); \
+         bt, n_el, gmap + e0 * sp->nd, xL, op->D_dev + e0 * (int64_t)op->slab, op->slab,              \
+         op->has_diff, op->has_conv, op->has_mass, atomic ? out : out + e0 * sp->nd, atomic);         \
    } break
+
+// true when the kernel cdm_k_apply will pick honours op->range_on (everything except the collocated
+// order-3 variants 1 and 2, which always sweep the whole mesh)
+bool cdm_k_range_capable(const cdm_op *op)
+{
+   const cdm_space *sp = op->sp;
+   return !(sp->dim == 3 && sp->p == 3 && (op->kernel_variant == 1 || op->kernel_variant == 2));
+}
 
 // yL = G^T B^T D B G xL on this rank's L-vector (no halo, no essential fix-up)
 int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
@@ -661,7 +671,11 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
    }
    const int atomic = op->scatter_mode == 1;
    double *out = yL;
-   if (atomic) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); }
+   // element range [e0, e0 + n_el) (overlapped multi-GPU schedule, pipelined host apply): like the
+   // specialised kernels, a ranged launch accumulates into a y the caller has zeroed
+   const int64_t e0 = op->range_on ? op->e_begin : 0, n_el = (op->range_on ? op->e_end : sp->ne) - e0;
+   if (n_el <= 0) { return CDM_OK; }
+   if (atomic) { if (!op->range_on) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); } }
    else { int rc = ensure_yE(op); if (rc) { return rc; } out = op->yE_dev; }
    const BasisTables bt = make_tables(sp);
    if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }

@@ -378,7 +378,9 @@ int cdm_domain_lf(cdm_space *sp, int q1d, const double *f_q, double scale, int a
    const int nq = (dim == 3) ? q1d * q1d * q1d : q1d * q1d;
    Staged f(c);
    if ((rc = f.in(f_q, sizeof(double) * (size_t)sp->ne * nq))) { return rc; }
-   const bool part = sp->ntrue != sp->ndof;
+   // every rank of a partitioned space takes part in the exchange, also one that holds no ghosts itself
+   // (the lowest rank owns all the dofs it shares)
+   const bool part = !sp->peers.empty();
    double *target = b_dev;
    if (part)
    {
@@ -416,7 +418,7 @@ int cdm_l2_error(cdm_space *sp, int q1d, const double *u_dev, const double *uex_
    Staged ex(c);
    if ((rc = ex.in(uex_q, sizeof(double) * (size_t)sp->ne * nq))) { return rc; }
    const double *uL = u_dev;
-   if (u_dev && sp->ntrue != sp->ndof)
+   if (u_dev && !sp->peers.empty())
    {
       // u_L = P u_T: ghost values come from their owners
       if ((rc = ensure_work(sp))) { return rc; }

@@ -100,7 +100,8 @@ def main():
         yd = torch.zeros(nt, dtype=torch.float64, device="cuda")
         torch.cuda.synchronize()
         # overlap: 0 serial halo exchange, 1 automatic (by neighbour count), 2 forced overlapped schedule
-        for kernel, scatter, overlap in ((0, 0, 0), (0, 1, 0), (1, 1, 0), (3, 0, 0), (3, 1, 0), (3, 1, 1), (3, 1, 2), (4, 1, 2)):
+        for kernel, scatter, overlap in ((0, 0, 0), (0, 1, 0), (1, 1, 0), (3, 0, 0), (3, 1, 0), (3, 1, 1), (3, 1, 2), (4, 1, 2),
+                                         (5, 0, 0), (5, 1, 1), (5, 1, 2)):       # 5: sub-warp kernel (orders 1-2; else block kernel)
             op.set_option("kernel", kernel)
             op.set_option("scatter", scatter)
             op.set_option("overlap", overlap)
@@ -110,7 +111,8 @@ def main():
             err = np.linalg.norm(yd.cpu().numpy() - yg[mine[:nt]]) / np.linalg.norm(yg)
             ok &= err < 1e-12
             print(f"[rank {rank}] apply kernel={kernel} scatter={scatter} overlap={overlap} rel err {err:.2e}", flush=True)
-        op.set_option("kernel", 3)
+        op.set_option("kernel", 3 if p == 3 else (5 if p < 3 else 4))     # the defaults
+        op.set_option("overlap", 1)
         # Jacobi diagonal (P^T-summed) and distributed GMRES
         dd = torch.zeros(nt, dtype=torch.float64, device="cuda")
         op.AssembleDiagonal(dd)
