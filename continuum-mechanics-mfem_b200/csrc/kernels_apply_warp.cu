@@ -57,10 +57,24 @@ template <int P> struct GroupCfg
    static constexpr int WPG = (T <= 32) ? 1 : 2;                   // warps per group
    static constexpr int GPB = (P <= 3) ? 4 * EPW : (P == 4 ? 2 : 1);   // groups per block
    static constexpr int THREADS = (WPG == 1) ? 32 * (GPB / EPW) : 64 * GPB;
-   static constexpr int MINB = (P <= 4) ? 4 : (P == 5 ? 5 : 3);        // resident blocks per SM the register budget is sized for
-   static constexpr int RSTR = (P == 3) ? 28 : (Q * Q + ((Q * Q) % 2 == 0 ? 1 : 2));   // dz stride of the R layout
+// resident blocks per SM the register budget is sized for.  p=5: 5 blocks fit the shared memory, but the
+// 204-register cap of MINB = 5 made ptxas spill 200 B inside the element loop (53 % of the roofline);
+// MINB = 4 -> 160 registers, no spills, 73 %.  p=4: MINB 3 / 4 / 5 -> 46 % / 76 % / 56 %.
+#ifndef CDM_G5_MINB
+#define CDM_G5_MINB 4
+#endif
+#ifndef CDM_G4_MINB
+#define CDM_G4_MINB 4
+#endif
+   static constexpr int MINB = (P < 4) ? 4 : (P == 4 ? CDM_G4_MINB : (P == 5 ? CDM_G5_MINB : 3));        // resident blocks per SM the register budget is sized for
+   // strides of the exchange layouts P(qx, line) = qx + PST line, R(qx,qy,dz) = qx + Q qy + RSTR dz.  For the
+   // two-warp groups they come from a brute-force search over the 64-bit bank pattern of the four access
+   // shapes (F1 write / F2 read of P, F2 write / F3 read of R): wavefronts per access, old -> new:
+   // p=4  P 8 -> 4, R 4 -> 2 (ideal 4, 2);  p=6  P 41 -> 8, R 11 -> 4 (ideal 8, 4);  p=5 unchanged (8 / 5, ideal 6 / 3).
+   static constexpr int RSTR = (P == 3) ? 28 : (P == 4 ? 45 : (P == 6 ? 71 : (Q * Q + ((Q * Q) % 2 == 0 ? 1 : 2))));
+   static constexpr int PST = (P == 4) ? 9 : (P == 6 ? 17 : Q);
    static constexpr int RS = ((D - 1) * RSTR + Q * Q + 1) & ~1;
-   static constexpr int PS = (Q * D * D + 1) & ~1;
+   static constexpr int PS = (PST * D * D + 1) & ~1;
 };
 
 template <int P, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
@@ -71,7 +85,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
 {
    using C = GroupCfg<P>;
    constexpr int D = C::D, Q = C::Q, T = C::T, ND = C::ND, Q2 = Q * Q;
-   constexpr int RS = C::RS, PS = C::PS, RSTR = C::RSTR;
+   constexpr int RS = C::RS, PS = C::PS, RSTR = C::RSTR, PST = C::PST;
    constexpr bool GRAD = DIFF || CONV;
    extern __shared__ __align__(128) unsigned char smraw[];
    const int group_doubles = (Q * slab + 3 * RS + 2 * PS + 1) & ~1;
@@ -161,8 +175,8 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
             double tB = 0.0, tG = 0.0;
             #pragma unroll
             for (int d = 0; d < D; d++) { tB += tb.B[q * D + d] * px[d]; if (GRAD) { tG += tb.G[q * D + d] * px[d]; } }
-            sP0[q + Q * t1] = tB;
-            if (GRAD) { sP1[q + Q * t1] = tG; }
+            sP0[q + PST * t1] = tB;
+            if (GRAD) { sP1[q + PST * t1] = tG; }
          }
       }
       if (l1 && more)
@@ -185,8 +199,8 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
          #pragma unroll
          for (int dy = 0; dy < D; dy++)
          {
-            tB[dy] = sP0[qx2 + Q * (dy + D * dz2)];
-            if (GRAD) { tG[dy] = sP1[qx2 + Q * (dy + D * dz2)]; }
+            tB[dy] = sP0[qx2 + PST * (dy + D * dz2)];
+            if (GRAD) { tG[dy] = sP1[qx2 + PST * (dy + D * dz2)]; }
          }
          #pragma unroll
          for (int q = 0; q < Q; q++)
@@ -296,8 +310,8 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
                a2 += tb.B[q * D + dy] * wb[q];
                if (DIFF) { a1 += tb.B[q * D + dy] * wx[q]; a2 += tb.G[q * D + dy] * wy[q]; }
             }
-            sP1[qx2 + Q * (dy + D * dz2)] = a2;
-            if (DIFF) { sP0[qx2 + Q * (dy + D * dz2)] = a1; }
+            sP1[qx2 + PST * (dy + D * dz2)] = a2;
+            if (DIFF) { sP0[qx2 + PST * (dy + D * dz2)] = a1; }
          }
       }
       gsync();
@@ -306,7 +320,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       {
          double a1[Q], a2[Q];
          #pragma unroll
-         for (int q = 0; q < Q; q++) { a2[q] = sP1[q + Q * t1]; if (DIFF) { a1[q] = sP0[q + Q * t1]; } }
+         for (int q = 0; q < Q; q++) { a2[q] = sP1[q + PST * t1]; if (DIFF) { a1[q] = sP0[q + PST * t1]; } }
          #pragma unroll
          for (int dx = 0; dx < D; dx++)
          {
