@@ -87,6 +87,10 @@ int cdm_finalize(cdm_ctx *c)
       if (c->ev1) { cudaEventDestroy(c->ev1); }
       if (c->evk0) { cudaEventDestroy(c->evk0); }
       if (c->evk1) { cudaEventDestroy(c->evk1); }
+      // the NCCL communicators are left to process teardown: ncclCommDestroy from an arbitrary point of the
+      // host language's shutdown sequence can block on peers that are already gone
+      for (int i = 0; i < 6; i++) { if (c->ev_h[i]) { cudaEventDestroy(c->ev_h[i]); } }
+      if (c->stream_halo) { cudaStreamSynchronize(c->stream_halo); cudaStreamDestroy(c->stream_halo); }
       if (c->own_stream && c->stream) { cudaStreamDestroy(c->stream); }
    }
    delete c;

@@ -421,6 +421,14 @@ def test_golden_fixture(torch, ctx, orc):
         dd = D.zeros(sp.ndof)
         op.AssembleDiagonal(dd)
         assert abs(D.down(dd).sum() - case["diag_sum"]) <= 1e-12 * abs(case["diag_sum"])
+        # linear form / L2 error (default rules) against the committed vectors
+        fn = lambda c: 1.0 + np.sin(2.3 * c[..., 0]) * np.cos(1.7 * c[..., 1]) + 0.5 * c[..., -1] ** 2
+        lf = D.zeros(sp.ndof)
+        sp.domain_lf(fn(sp.rule_coords(case["p"] + 1)), lf)
+        lf = D.down(lf)
+        assert abs(np.linalg.norm(lf) - case["lf_norm"]) <= 1e-12 * case["lf_norm"]
+        assert np.allclose(lf[:8], case["lf_head"], rtol=1e-11, atol=1e-14)
+        assert abs(sp.l2_error(xd, fn(sp.rule_coords(case["p"] + 2))) - case["l2_error"]) <= 1e-12 * case["l2_error"]
 
 
 @pytest.mark.parametrize("kernel", [0, 1, 2, 3])

@@ -261,3 +261,8 @@ def test_golden_fixture_matches(orc):
         assert abs(np.linalg.norm(y) - case["y_norm"]) <= 1e-13 * case["y_norm"]
         assert np.allclose(y[:8], case["y_head"], rtol=1e-12, atol=1e-14)
         assert abs(P.pa_diag().sum() - case["diag_sum"]) <= 1e-12 * abs(case["diag_sum"])
+        fn = lambda c: 1.0 + np.sin(2.3 * c[..., 0]) * np.cos(1.7 * c[..., 1]) + 0.5 * c[..., -1] ** 2
+        lf = P.domain_lf(fn(P.rule_coords(P.p + 1)))
+        assert abs(np.linalg.norm(lf) - case["lf_norm"]) <= 1e-13 * case["lf_norm"]
+        assert np.allclose(lf[:8], case["lf_head"], rtol=1e-12, atol=1e-15)
+        assert abs(P.l2_error(x, fn(P.rule_coords(P.p + 2))) - case["l2_error"]) <= 1e-13 * case["l2_error"]
