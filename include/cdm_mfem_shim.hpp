@@ -76,6 +76,7 @@ public:
    void GetToHost(double *h) const { check(ctx_, cdm_vec_download(ctx_, n_, d_, h), "cdm_vec_download"); }
    std::vector<double> HostCopy() const { std::vector<double> h(n_); GetToHost(h.data()); return h; }
    void Add(double a, const Vector &x) { check(ctx_, cdm_axpy(ctx_, n_, a, x.d_, d_), "cdm_axpy"); }   // *this += a x
+   void Assign(const Vector &x) { *this = 0.0; Add(1.0, x); }                                          // *this = x (device copy)
    double operator*(const Vector &y) const { double r; check(ctx_, cdm_dot(ctx_, n_, d_, y.d_, &r), "cdm_dot"); return r; }
    double Norml2() const { double r; check(ctx_, cdm_norm2(ctx_, n_, d_, &r), "cdm_norm2"); return r; }
 private:
