@@ -156,6 +156,11 @@ def main():
         # the halo messages (<= 0.7 MB) and the Krylov all-reduces (<= 31 doubles) are latency-bound:
         # NCCL's LL protocol is 5.6 % faster per Krylov iteration at 8 GPUs (profiles/r01_scaling.md)
         os.environ.setdefault("NCCL_PROTO", "LL")
+    # stdout carries exactly one JSON line: anything a library writes to fd 1 (NCCL prints its version
+    # banner there on some boxes) is sent to stderr, and the result goes to a private copy of the real stdout
+    sys.stdout.flush()
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     cdm = importlib.import_module("continuum-mechanics-mfem_b200")
@@ -313,7 +318,8 @@ def main():
                            "scatter": "fp64 red.add" if op_scatter(op, args) == 1 else "E-vector + gather transpose"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "krylov": krylov, "setup": setup, "clocks": clocks}
-        print(json.dumps(line))
+        print(json.dumps(line), file=result_out)
+        result_out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
