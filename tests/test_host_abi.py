@@ -48,6 +48,26 @@ def test_compute_fails_loudly_without_gpu(hctx):
     with pytest.raises(cdm.CdmError) as ei:
         cdm.ConvectionDiffusionOperator(sp, kappa=1.0)
     assert ei.value.code == cdm.ENOGPU
+    # the form kernels (linear form, L2 error, rule points, projection) have no CPU path either
+    b = np.zeros(sp.ndof)
+    for call in (lambda: sp.rule_coords(2),
+                 lambda: sp.domain_lf(np.ones((sp.ne, 4)), b),
+                 lambda: sp.l2_error(None, np.ones((sp.ne, 9))),
+                 lambda: sp.project_dofs(np.zeros(1, np.int32), np.zeros(1), b)):
+        with pytest.raises(cdm.CdmError) as ei:
+            call()
+        assert ei.value.code == cdm.ENOGPU
+
+
+def test_rule_points_follow_mfem_intrules():
+    """IntRules.Get(geom, order) on segments / squares / cubes: order/2 + 1 Gauss-Legendre points per direction"""
+    L = cdm.lib()
+    assert [L.cdm_rule_points(o) for o in (0, 1, 2, 3, 4, 5, 8, 9)] == [1, 1, 2, 2, 3, 3, 5, 5]
+    for p in range(1, 7):
+        assert L.cdm_rule_points(2 * p) == p + 1                      # DomainLFIntegrator default (order 2p)
+        assert L.cdm_rule_points(max(2, 2 * p + 3)) == p + 2          # the app's error rule (:383)
+        assert L.cdm_rule_points(2 * p + 3 - 1) == p + 2              # Diffusion/Mass/Convection rule in 3D (2p + dim - 1)
+    assert L.cdm_rule_points(-1) == cdm.EINVAL
 
 
 def test_bad_arguments_are_errors_not_crashes(hctx):
