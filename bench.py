@@ -126,6 +126,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=-1)
     ap.add_argument("--scatter", type=int, default=-1)
     ap.add_argument("--overlap", type=int, default=1, help="multi-GPU: overlap the halo exchange with interior elements")
+    ap.add_argument("--halo", type=int, default=0, help="multi-GPU: 0 NCCL send/recv, 1 peer-memory stores + flags (experimental)")
     ap.add_argument("--krylov-iters", type=int, default=60)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -187,7 +188,9 @@ def main():
     if args.scatter >= 0:
         op.set_option("scatter", args.scatter)
     op.set_option("overlap", args.overlap)
-    op.set_option("tail", 1)        # x, y are allocated with the local (L-vector) size: no T<->L copies
+    if world > 1 and args.halo:
+        op.set_option("halo", args.halo)
+    op.set_option("tail", 1)       # x, y are allocated with the local (L-vector) size: no T<->L copies
     n_true = sp.ntrue
     tot = torch.tensor([n_true, sp.ne], dtype=torch.int64, device="cuda")
     if world > 1:
@@ -313,7 +316,8 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "global_dofs": n_global, "global_elements": ne_global,
                            "partition": "x".join(map(str, parts)),
-                           "nccl_proto": os.environ.get("NCCL_PROTO") if world > 1 else None, "l2_policy": "inputs larger than L2 "
+                           "nccl_proto": os.environ.get("NCCL_PROTO") if world > 1 else None,
+                           "halo": ("peer memory" if args.halo else "nccl send/recv") if world > 1 else None, "l2_policy": "inputs larger than L2 "
                            f"({bytes_launch / 1e9:.2f} GB streamed per apply per GPU vs 126 MB L2)",
                            "scatter": "fp64 red.add" if op_scatter(op, args) == 1 else "E-vector + gather transpose"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,

@@ -466,6 +466,7 @@ int cdm_space_destroy(cdm_space *sp)
    {
       cudaFree(sp->gather_dev); cudaFree(sp->offsets_dev); cudaFree(sp->indices_dev); cudaFree(sp->elem_x_dev);
       cudaFree(sp->work_dev); cudaFree(sp->elem_part_dev);
+      cdm_halo_p2p_destroy(sp);
       cdm_halo_plan &hp = sp->halo;
       cudaFree(hp.own_all_dev); cudaFree(hp.ghost_all_dev); cudaFree(hp.pt_dof_dev); cudaFree(hp.pt_off_dev);
       cudaFree(hp.pt_src_dev); cudaFree(hp.send_dev); cudaFree(hp.recv_dev);
@@ -569,6 +570,14 @@ int cdm_operator_set_option(cdm_op *op, const char *name, int value)
    if (!op || !name) { return CDM_EINVAL; }
    if (!std::strcmp(name, "scatter")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->scatter_mode = value; return CDM_OK; }
    if (!std::strcmp(name, "kernel")) { op->kernel_variant = value; return CDM_OK; }
+   if (!std::strcmp(name, "halo"))
+   {
+      // 1: exchange the shared dofs through peer memory (collective: every rank must make this call)
+      if (value != 0 && value != 1) { return CDM_EINVAL; }
+      if (value == 1) { const int rc = cdm_halo_p2p_setup(op->sp); if (rc) { return rc; } }
+      op->halo_mode = value;
+      return CDM_OK;
+   }
    if (!std::strcmp(name, "tail")) { op->tail = value != 0; return CDM_OK; }
    if (!std::strcmp(name, "host_pipeline")) { op->host_pipeline = value; return CDM_OK; }
    if (!std::strcmp(name, "overlap")) { if (value < 0 || value > 2) { return CDM_EINVAL; } op->overlap = value; return CDM_OK; }
@@ -591,6 +600,13 @@ int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained)
    cdm_ctx *ctx = sp->ctx;
    int rc;
    const bool par = ctx->nranks > 1 && !sp->peers.empty();
+   // the P / P^T pair of an apply may go through peer memory (option "halo" = 1); any other exchange uses NCCL
+   struct P2PScope
+   {
+      cdm_halo_plan &hp;
+      P2PScope(cdm_halo_plan &h, bool on) : hp(h) { hp.p2p_active = on; }
+      ~P2PScope() { hp.p2p_active = false; }
+   } p2p_scope(sp->halo, par && op->halo_mode == 1 && sp->halo.p2p != nullptr);
    // Overlapped schedule (atomic scatter, range-capable kernels): the halo exchange runs on a
    // high-priority stream with its own communicator while the compute stream works on interior
    // elements:   H: pack, P exchange, unpack      | C: memset y, interior A

@@ -74,6 +74,10 @@ struct cdm_halo_plan
    int32_t *own_all_dev = nullptr, *ghost_all_dev = nullptr;
    int32_t *pt_dof_dev = nullptr, *pt_off_dev = nullptr, *pt_src_dev = nullptr;
    double *send_dev = nullptr, *recv_dev = nullptr;
+   // peer-memory exchange (halo_p2p.cu, option "halo" = 1): the pack kernel stores straight into the
+   // neighbours' receive buffers over NVLink and raises a flag there; the unpack kernel waits on its flags
+   struct p2p_state *p2p = nullptr;
+   bool p2p_active = false;         // set by the operator apply around its P / P^T pair
 };
 
 struct cdm_space
@@ -125,6 +129,7 @@ struct cdm_op
    int overlap = 1;                // 1: overlap the halo exchange with interior elements when possible
    bool tail = false;             // caller vectors have room for the ghost tail (length >= ndof)
    int scatter_mode = 1;           // 0: E-vector + gather transpose, 1: FP64 red.add
+   int halo_mode = 0;              // 0: NCCL send/recv, 1: peer-memory stores + flags (halo_p2p.cu)
    int kernel_variant = 0;
    // pipelined host-vector apply (cdm_operator_mult_host): element chunks, per-class upload / download bounds
    struct host_pipe
@@ -211,6 +216,12 @@ int cdm_halo_PT(cdm_op *op, double *yL);           // ghost partial sums -> owne
 int cdm_halo_P_space(cdm_space *sp, double *xL);   // the same exchanges for callers without an operator
 int cdm_halo_PT_space(cdm_space *sp, double *yL);
 int cdm_allreduce_sum(cdm_ctx *c, double *buf_dev, int k);
+int cdm_allgather_bytes(cdm_ctx *c, const void *send_dev, void *recv_dev, size_t bytes_per_rank);
+// ---- peer-memory halo exchange (halo_p2p.cu)
+int cdm_halo_p2p_setup(cdm_space *sp);              // collective over the ranks of the communicator
+void cdm_halo_p2p_destroy(cdm_space *sp);
+int cdm_halo_p2p_P(cdm_space *sp, double *xL, cudaStream_t s, cudaEvent_t ev_packed);
+int cdm_halo_p2p_PT(cdm_space *sp, double *yL, cudaStream_t s, cudaEvent_t ev_packed);
 // same exchanges on the halo stream / communicator; ev_packed is recorded right after the pack kernel
 int cdm_halo_P_async(cdm_op *op, double *xL, cudaEvent_t ev_packed);
 int cdm_halo_PT_async(cdm_op *op, double *yL, cudaEvent_t ev_packed);

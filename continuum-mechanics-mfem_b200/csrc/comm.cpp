@@ -21,6 +21,7 @@ struct NcclApi
    nccl_result (*CommInitRank)(ncclComm **, int, nccl_uid, int) = nullptr;
    nccl_result (*CommDestroy)(ncclComm *) = nullptr;
    nccl_result (*AllReduce)(const void *, void *, size_t, int, int, ncclComm *, cudaStream_t) = nullptr;
+   nccl_result (*AllGather)(const void *, void *, size_t, int, ncclComm *, cudaStream_t) = nullptr;
    nccl_result (*Send)(const void *, size_t, int, int, ncclComm *, cudaStream_t) = nullptr;
    nccl_result (*Recv)(void *, size_t, int, int, ncclComm *, cudaStream_t) = nullptr;
    nccl_result (*GroupStart)() = nullptr;
@@ -28,7 +29,7 @@ struct NcclApi
    const char *(*GetErrorString)(nccl_result) = nullptr;
    nccl_result (*CommSplit)(ncclComm *, int, int, ncclComm **, void *) = nullptr;   // optional (NCCL >= 2.18)
 };
-const int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+const int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_UINT8 = 1;
 
 NcclApi *api()
 {
@@ -41,7 +42,7 @@ NcclApi *api()
    if (!a.h) { return nullptr; }
 #define SYM(field, name) *(void **)(&a.field) = dlsym(a.h, name); if (!a.field) { a.h = nullptr; return nullptr; }
    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-   SYM(AllReduce, "ncclAllReduce") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+   SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
    *(void **)(&a.CommSplit) = dlsym(a.h, "ncclCommSplit");
@@ -107,6 +108,14 @@ int cdm_allreduce_sum(cdm_ctx *c, double *buf_dev, int k)
    return CDM_OK;
 }
 
+// setup-time exchange of small records between the ranks (peer-memory halo: IPC handles and offsets)
+int cdm_allgather_bytes(cdm_ctx *c, const void *send_dev, void *recv_dev, size_t bytes_per_rank)
+{
+   if (c->nranks <= 1 || !c->comm) { return cdm_fail(c, CDM_ENCCL, "cdm_allgather_bytes: no communicator"); }
+   NCCL_CALL(c, api()->AllGather(send_dev, recv_dev, bytes_per_rank, NCCL_UINT8, c->comm, c->stream));
+   return CDM_OK;
+}
+
 // Run `body` with the context's stream temporarily replaced (the kernel launchers read c->stream).
 struct StreamSwap
 {
@@ -121,6 +130,7 @@ static int halo_P_impl(cdm_space *sp, double *xL, bool halo_stream, cudaEvent_t 
 {
    cdm_ctx *c = sp->ctx;
    if (!c->comm) { return cdm_fail(c, CDM_ENCCL, "partitioned space used without cdm_comm_init"); }
+   if (sp->halo.p2p && sp->halo.p2p_active) { return cdm_halo_p2p_P(sp, xL, halo_stream ? c->stream_halo : c->stream, ev_packed); }
    NcclApi *a = api();
    cdm_halo_plan &hp = sp->halo;
    StreamSwap sw(c, halo_stream ? c->stream_halo : c->stream);
@@ -147,6 +157,7 @@ static int halo_PT_impl(cdm_space *sp, double *yL, bool halo_stream, cudaEvent_t
 {
    cdm_ctx *c = sp->ctx;
    if (!c->comm) { return cdm_fail(c, CDM_ENCCL, "partitioned space used without cdm_comm_init"); }
+   if (sp->halo.p2p && sp->halo.p2p_active) { return cdm_halo_p2p_PT(sp, yL, halo_stream ? c->stream_halo : c->stream, ev_packed); }
    NcclApi *a = api();
    cdm_halo_plan &hp = sp->halo;
    StreamSwap sw(c, halo_stream ? c->stream_halo : c->stream);

@@ -176,7 +176,12 @@ int  cdm_eliminate_rhs(cdm_op *op, const double *x_dev, double *b_dev);
 /* raw quadrature data (tests): host copy in MFEM layout, q fastest:
    Ddiff[(e*nsym+c)*nq+q], Dconv[(e*dim+c)*nq+q], Dmass[e*nq+q]; pointers may be NULL */
 int  cdm_operator_get_qdata(const cdm_op *op, double *Ddiff, double *Dconv, double *Dmass);
-/* tuning knobs (benchmarks): name in {"scatter" (0 E-vector+gather, 1 atomics), "kernel" (variant id), "tail" (0/1)} */
+/* tuning knobs (benchmarks): "scatter" (0 E-vector + deterministic gather transpose, 1 fp64 red.add, default),
+   "kernel" (0 block kernel, 1-3 order-3 warp kernels, 4 group kernel, 5 sub-warp kernel; default by order),
+   "tail" (1: caller vectors have the local size, see cdm_operator_local_size),
+   "overlap" (multi-GPU: 0 serial halo exchange, 1 overlapped with interior elements up to 3 neighbours, 2 always),
+   "halo" (multi-GPU: 0 NCCL send/recv, 1 peer-memory stores + flags over NVLink; setting it to 1 is a
+   collective call: every rank must make it), "host_pipeline" (0/1, or a chunk count for cdm_operator_mult_host) */
 int  cdm_operator_set_option(cdm_op *op, const char *name, int value);
 /* measurement hook: run the element kernel of the apply `reps` times on this rank's
    L-vectors and return its mean device time (CUDA events recorded on the context's

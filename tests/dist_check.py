@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--mode", default="cpu", choices=["cpu", "gpu"])
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--mesh", type=int, nargs=3, default=[6, 5, 4])
+    ap.add_argument("--p2p", action="store_true", help="also check the peer-memory halo exchange (option halo=1)")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
@@ -143,6 +144,26 @@ def main():
         e_l = sp.l2_error(xd, fn(sp.rule_coords(p + 2)))
         ok &= lerr < 1e-12 and abs(e_l - e_g) < 1e-12 * e_g
         print(f"[rank {rank}] linear form err {lerr:.2e}  L2 error {e_l:.12e} vs {e_g:.12e}", flush=True)
+        if args.p2p:
+            # the same apply / GMRES with the shared dofs exchanged through peer memory (NVLink stores + flags)
+            op.set_option("halo", 1)
+            for overlap in (0, 2):
+                op.set_option("overlap", overlap)
+                for rep in range(6):
+                    op.Mult(xd, yd)
+                ctx.sync()
+                err = np.linalg.norm(yd.cpu().numpy() - yg[mine[:nt]]) / np.linalg.norm(yg)
+                ok &= err < 1e-12
+                print(f"[rank {rank}] peer-memory halo: apply overlap={overlap} rel err {err:.2e}", flush=True)
+            op.set_option("overlap", 1)
+            xs.zero_()
+            torch.cuda.synchronize()
+            s.Mult(bd, xs)
+            ctx.sync()
+            herr = np.max(np.abs(s.history - info["hist"][:len(s.history)]) / info["hist"][0]) if len(s.history) == len(info["hist"]) else 1.0
+            ok &= s.GetConverged() and s.GetNumIterations() == info["iters"] and herr < 1e-10
+            print(f"[rank {rank}] peer-memory halo: gmres iters {s.GetNumIterations()}/{info['iters']} hist err {herr:.2e}", flush=True)
+            op.set_option("halo", 0)
     else:
         # host emulation of cdm_halo_P / cdm_halo_PT with gloo, element work by the oracle
         lvx, lev, lbv, lba = lm.arrays()
