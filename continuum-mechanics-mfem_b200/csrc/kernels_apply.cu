@@ -27,6 +27,8 @@ struct SetupArgs
    double qx[CDM_MAX_Q1D], qw[CDM_MAX_Q1D];
 };
 
+constexpr int SETUP_EPB = 8;      // elements per block column of k_setup_qdata
+
 template <int DIM>
 __global__ void __launch_bounds__(256)
 k_setup_qdata(SetupArgs a, int64_t ne, const double *__restrict__ elem_x, double *__restrict__ Dq)
@@ -34,10 +36,14 @@ k_setup_qdata(SetupArgs a, int64_t ne, const double *__restrict__ elem_x, double
    const int q1d = a.q1d;
    const int q2 = q1d * q1d;
    const int nq = (DIM == 3) ? q2 * q1d : q2;
-   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (gid >= ne * nq) { return; }
-   const int64_t e = gid / nq;
-   const int q = (int)(gid - e * nq);
+   // a block owns SETUP_EPB consecutive elements: the (element, point) split is a 32-bit division of a small
+   // block-local index instead of a 64-bit division of the global one
+   const unsigned l = blockIdx.y * blockDim.x + threadIdx.x;
+   if (l >= (unsigned)(SETUP_EPB * nq)) { return; }
+   const unsigned el = l / (unsigned)nq;
+   const int64_t e = (int64_t)blockIdx.x * SETUP_EPB + el;
+   if (e >= ne) { return; }
+   const int q = (int)(l - el * (unsigned)nq);
    const int qx = q % q1d, qy = (q / q1d) % q1d, qz = (DIM == 3) ? q / q2 : 0;
    const double x = a.qx[qx], y = a.qx[qy], z = (DIM == 3) ? a.qx[qz] : 0.0;
    const double w = a.qw[qx] * a.qw[qy] * ((DIM == 3) ? a.qw[qz] : 1.0);
@@ -196,9 +202,9 @@ int cdm_k_setup_qdata(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel, 
    if (rc == CDM_OK)
    {
       const int bs = 256;
-      const int64_t nb = (npts + bs - 1) / bs;
-      if (sp->dim == 2) { k_setup_qdata<2><<<(unsigned)nb, bs, 0, ctx->stream>>>(a, sp->ne, sp->elem_x_dev, op->D_dev); }
-      else { k_setup_qdata<3><<<(unsigned)nb, bs, 0, ctx->stream>>>(a, sp->ne, sp->elem_x_dev, op->D_dev); }
+      const dim3 grid((unsigned)((sp->ne + SETUP_EPB - 1) / SETUP_EPB), (unsigned)((SETUP_EPB * sp->nq + bs - 1) / bs));
+      if (sp->dim == 2) { k_setup_qdata<2><<<grid, bs, 0, ctx->stream>>>(a, sp->ne, sp->elem_x_dev, op->D_dev); }
+      else { k_setup_qdata<3><<<grid, bs, 0, ctx->stream>>>(a, sp->ne, sp->elem_x_dev, op->D_dev); }
       ctx->launches++;
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) { rc = cdm_fail(ctx, CDM_ECUDA, std::string("k_setup_qdata: ") + cudaGetErrorString(e)); }
