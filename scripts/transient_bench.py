@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""BASELINE config 3 in its own terms: backward-Euler convection-diffusion, 3D hex order 2, ~30 M dofs, one GPU.
+The time loop of linear_convection_diffusion_1D.cpp:537-572 for one Peclet block:
+    (M + dt C(beta) + (dt/Pe) K) c^{n+1} = M c^n,   Dirichlet (analytic erfc profile) on x = 0, 1,
+per step: mass apply, boundary projection, RHS elimination, GMRES(30)+Jacobi (rtol 1e-10, atol 1e-12), all on
+the device.  Prints one JSON line: per-step time and its split, Krylov iterations, time per iteration.
+
+  python scripts/transient_bench.py [--n 155] [--order 2] [--steps 4] [--pe 10] [--dt 1e-3]
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+from scipy.special import erfc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import cdm_b200 as cdm  # noqa: E402
+
+
+def exact_concentration(x, t, pe):
+    """ExactConcentration (linear_convection_diffusion_1D.cpp:146-166)"""
+    diff = t / pe
+    root = math.sqrt(diff)
+    a1, a2 = (x - t) / (2 * root), (x + t) / (2 * root)
+    t3 = 0.5 * (1 + pe * x + pe * t) * np.exp(np.minimum(pe * x, 700.0)) * erfc(a2)
+    c = 0.5 * erfc(a1) + math.sqrt(t * pe / math.pi) * np.exp(-((x - t) ** 2) / (4 * diff)) - t3
+    return np.where(np.isfinite(c), c, 0.0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=155)
+    ap.add_argument("--order", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--pe", type=float, default=10.0)
+    ap.add_argument("--dt", type=float, default=1e-3)
+    args = ap.parse_args()
+    ctx = cdm.Context(0)
+    t0 = time.perf_counter()
+    mesh = cdm.Mesh.cartesian(ctx, 3, args.n, perturb=0.0)
+    sp = cdm.H1Space(mesh, args.order)
+    marker = np.zeros(6, np.int32)
+    marker[[2, 4]] = 1                                               # attributes 3, 5: x = 1 and x = 0 (:214-258)
+    ess = sp.essential_dofs(marker)
+    X = sp.dof_coords()[ess, 0]
+    t_host = time.perf_counter() - t0
+    beta, dt, pe = (1.0, 0.0, 0.0), args.dt, args.pe
+    mass_form = cdm.ConvectionDiffusionOperator(sp, mass=1.0)                                   # (:375-378)
+    form = cdm.ConvectionDiffusionOperator(sp, kappa=dt / pe, vel=beta, alpha=dt, mass=1.0, ess_dofs=ess)   # (:391-400)
+    solver = cdm.GMRESSolver()                                       # Input/petsc.opts: gmres, 1e-10, 1e-12, 500, jacobi
+    solver.SetOperator(form)
+    n = sp.ndof
+    c = torch.zeros(n, dtype=torch.float64, device="cuda")           # c^0 = 0 (:402-407)
+    rhs, sol, g = torch.zeros_like(c), torch.zeros_like(c), torch.zeros_like(c)
+    essd = torch.from_numpy(ess).cuda()
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    its, t_step, t_solve = [], [], []
+    for step in range(1, args.steps + 1):
+        t = step * dt
+        gv = exact_concentration(X, t, pe)                           # host evaluation of the Dirichlet data
+        ctx.sync()
+        w0 = time.perf_counter()
+        mass_form.MultUnconstrained(c, rhs)                          # rhs = M c^n (:544)
+        sp.project_dofs(essd, gv, g)                                 # ProjectBdrCoefficient (:545-546)
+        form.EliminateRHS(g, rhs)                                    # FormLinearSystem (:547-548)
+        solver.Mult(rhs, sol)                                        # (:553-566)
+        ctx.sync()
+        w1 = time.perf_counter()
+        if not solver.GetConverged():
+            raise SystemExit(f"solver did not converge at step {step}")
+        with torch.cuda.stream(stream):
+            c.copy_(sol)
+        ctx.sync()
+        its.append(solver.GetNumIterations())
+        t_step.append((w1 - w0) * 1e3)
+        t_solve.append(solver.res.seconds * 1e3)
+    cx = c[essd].cpu().numpy()
+    line = {"workload": f"backward Euler, 3D hex order {args.order}, {args.n}^3 elements, Pe={pe}, dt={dt}",
+            "dofs": n, "elements": sp.ne, "essential_dofs": int(len(ess)), "steps": args.steps,
+            "gmres_iterations_per_step": its, "ms_per_step": [round(v, 3) for v in t_step],
+            "solve_ms_per_step": [round(v, 3) for v in t_solve],
+            "ms_per_krylov_iteration": round(sum(t_solve) / max(sum(its), 1), 4),
+            "gdofs_per_krylov_iteration": round(n / (sum(t_solve) / max(sum(its), 1)) / 1e6, 3),
+            "host_setup_s": round(t_host, 2),
+            "bc_check": float(np.max(np.abs(cx - exact_concentration(X, args.steps * dt, pe))))}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
