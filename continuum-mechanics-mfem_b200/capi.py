@@ -103,6 +103,9 @@ SIGNATURES = {
     "cdm_operator_diag": (_ci, [_vp, _vp]),
     "cdm_eliminate_rhs": (_ci, [_vp, _vp, _vp]),
     "cdm_operator_get_qdata": (_ci, [_vp, _vp, _vp, _vp]),
+    "cdm_operator_assemble_csr": (_ci, [_vp]),
+    "cdm_operator_csr_sizes": (_ci, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "cdm_operator_csr_get": (_ci, [_vp, _vp, _vp, _vp]),
     "cdm_operator_set_option": (_ci, [_vp, C.c_char_p, _ci]),
     "cdm_operator_time_kernel": (_ci, [_vp, _vp, _vp, _ci, _ci, C.POINTER(_cd)]),
     "cdm_rule_points": (_ci, [_ci]),
@@ -445,6 +448,15 @@ class ConvectionDiffusionOperator:
 
     def set_option(self, name, value):
         self.ctx.check(lib().cdm_operator_set_option(self.h, name.encode(), int(value)))
+
+    def assemble_csr(self):
+        """full assembly on the device (the reference's a.Assemble()); returns (rowptr, colind, vals) host copies"""
+        self.ctx.check(lib().cdm_operator_assemble_csr(self.h))
+        n, nnz = _i64(0), _i64(0)
+        self.ctx.check(lib().cdm_operator_csr_sizes(self.h, C.byref(n), C.byref(nnz)))
+        rowptr, colind, vals = np.zeros(n.value + 1, np.int64), np.zeros(nnz.value, np.int32), np.zeros(nnz.value)
+        self.ctx.check(lib().cdm_operator_csr_get(self.h, _ptr(rowptr), _ptr(colind), _ptr(vals)))
+        return rowptr, colind, vals
 
     def Mult(self, x, y):
         self.ctx.check(lib().cdm_operator_apply(self.h, _ptr(x), _ptr(y)))

@@ -548,7 +548,8 @@ int cdm_operator_update(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel
    if (hk < 0 || hv < 0 || hm < 0 || (hk > 0) != op->has_diff || (hv > 0) != op->has_conv || (hm > 0) != op->has_mass)
       return cdm_fail(ctx, CDM_EINVAL, "cdm_operator_update: the set of integrators must not change");
    if (op->dinv_dev) { cudaFree(op->dinv_dev); op->dinv_dev = nullptr; }
-   return cdm_k_setup_qdata(op, kappa, vel, conv_alpha, mass);
+   const int rc = cdm_k_setup_qdata(op, kappa, vel, conv_alpha, mass);
+   return rc ? rc : cdm_csr_refill_if_present(op);        // an assembled matrix follows the new coefficients
 }
 
 int cdm_operator_destroy(cdm_op *op)
@@ -558,6 +559,7 @@ int cdm_operator_destroy(cdm_op *op)
    cudaFree(op->D_dev); cudaFree(op->gather_c_dev); cudaFree(op->ess_dev); cudaFree(op->yE_dev);
    cudaFree(op->xL_dev); cudaFree(op->yL_dev); cudaFree(op->dinv_dev); cudaFree(op->kry_dev);
    for (int i = 0; i < 3; i++) { cudaFree(op->coef_dev[i]); }
+   cdm_csr_destroy(op);
    delete op;
    return CDM_OK;
 }
@@ -570,6 +572,14 @@ int cdm_operator_set_option(cdm_op *op, const char *name, int value)
    if (!op || !name) { return CDM_EINVAL; }
    if (!std::strcmp(name, "scatter")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->scatter_mode = value; return CDM_OK; }
    if (!std::strcmp(name, "kernel")) { op->kernel_variant = value; return CDM_OK; }
+   if (!std::strcmp(name, "assembly"))
+   {
+      // 1: the reference's literal path -- apply = SpMV with the fully assembled CSR matrix (csr_path.cu)
+      if (value != 0 && value != 1) { return CDM_EINVAL; }
+      if (value == 1 && !op->csr) { const int rc = cdm_operator_assemble_csr(op); if (rc) { return rc; } }
+      op->assembly = value;
+      return CDM_OK;
+   }
    if (!std::strcmp(name, "halo"))
    {
       // 1: exchange the shared dofs through peer memory (collective: every rank must make this call)

@@ -130,6 +130,8 @@ struct cdm_op
    bool tail = false;             // caller vectors have room for the ghost tail (length >= ndof)
    int scatter_mode = 1;           // 0: E-vector + gather transpose, 1: FP64 red.add
    int halo_mode = 0;              // 0: NCCL send/recv, 1: peer-memory stores + flags (halo_p2p.cu)
+   int assembly = 0;               // 0: partial assembly (matrix-free), 1: apply = SpMV with the assembled CSR matrix
+   struct cdm_csr *csr = nullptr;  // csr_path.cu (built on demand)
    int kernel_variant = 0;
    // pipelined host-vector apply (cdm_operator_mult_host): element chunks, per-class upload / download bounds
    struct host_pipe
@@ -217,6 +219,10 @@ int cdm_halo_P_space(cdm_space *sp, double *xL);   // the same exchanges for cal
 int cdm_halo_PT_space(cdm_space *sp, double *yL);
 int cdm_allreduce_sum(cdm_ctx *c, double *buf_dev, int k);
 int cdm_allgather_bytes(cdm_ctx *c, const void *send_dev, void *recv_dev, size_t bytes_per_rank);
+// ---- full-assembly path (csr_path.cu)
+void cdm_csr_destroy(cdm_op *op);
+int cdm_csr_refill_if_present(cdm_op *op);          // new coefficient values into an existing pattern
+int cdm_k_csr_spmv(cdm_op *op, const double *x, double *y, bool constrained);
 // ---- peer-memory halo exchange (halo_p2p.cu)
 int cdm_halo_p2p_setup(cdm_space *sp);              // collective over the ranks of the communicator
 void cdm_halo_p2p_destroy(cdm_space *sp);

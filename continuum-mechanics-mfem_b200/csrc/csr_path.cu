@@ -1,0 +1,248 @@
+// csr_path.cu -- the reference's literal path on the device: full assembly of the
+// Diffusion + Convection + Mass form into a CSR matrix and SpMV as the operator apply.
+//
+// Stands behind (reference call sites, linear_convection_diffusion_2D.cpp):
+//   :339   a.Assemble()                      element matrices -> sparse matrix
+//   :351   a.FormLinearSystem(...)           the matrix the solver sees (essential rows / columns eliminated)
+//   :368   PetscLinearSolver(A).Mult(B, X)   MatMult inside KSP
+// It exists so that the partially-assembled operator can be compared with the algorithm the application
+// actually runs, on the same GPU: operator option "assembly" = 1 switches cdm_operator_apply (and therefore
+// cdm_gmres / cdm_cg) to the CSR SpMV.  Single rank, quad / hex meshes; the matrix-free path stays the product.
+//
+// * pattern: on the host from the element restriction (row g = union of the dofs of the elements touching g,
+//   sorted) -- bit-exact with the oracle's pattern;
+// * values: one block per element; thread (i,j) accumulates a_ij = sum_q grad(phi_i).D grad(phi_j)
+//   + phi_i Dc.grad(phi_j) + Dm phi_i phi_j from the SAME quadrature data the matrix-free kernels stream
+//   (so both paths discretise identically), then adds it into its row by binary search (fp64 atomicAdd);
+// * apply: warp per row, essential dofs handled like ConstrainedOperator (row -> identity, column skipped),
+//   which is the matrix FormLinearSystem produces with DIAG_ONE.
+#include "cdm_internal.hpp"
+#include "kernels_common.cuh"
+#include <algorithm>
+
+struct cdm_csr
+{
+   int64_t n = 0, nnz = 0;
+   std::vector<int64_t> rowptr;
+   std::vector<int32_t> colind;
+   int64_t *rowptr_dev = nullptr;
+   int32_t *colind_dev = nullptr;
+   double *vals_dev = nullptr;
+   unsigned char *ess_mark_dev = nullptr;
+};
+
+namespace
+{
+// 1-D factors of basis function i at quadrature point q: value and reference gradient
+template <int DIM>
+__device__ __forceinline__ void basis_at(const BasisTables &t, int d1d, int q1d, int i, int q, double &phi, double *g)
+{
+   const int ix = i % d1d, iy = (i / d1d) % d1d, iz = (DIM == 3) ? i / (d1d * d1d) : 0;
+   const int qx = q % q1d, qy = (q / q1d) % q1d, qz = (DIM == 3) ? q / (q1d * q1d) : 0;
+   const double bx = t.B[qx * d1d + ix], by = t.B[qy * d1d + iy], bz = (DIM == 3) ? t.B[qz * d1d + iz] : 1.0;
+   const double gx = t.G[qx * d1d + ix], gy = t.G[qy * d1d + iy];
+   phi = bx * by * bz;
+   g[0] = gx * by * bz;
+   g[1] = bx * gy * bz;
+   if (DIM == 3) { g[2] = bx * by * t.G[qz * d1d + iz]; }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_csr_assemble(BasisTables t, int d1d, int q1d, int64_t ne, const int32_t *__restrict__ gather,
+               const double *__restrict__ Dq, int slab, int has_diff, int has_conv, int has_mass,
+               const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind, double *__restrict__ vals)
+{
+   const int nd = (DIM == 3) ? d1d * d1d * d1d : d1d * d1d;
+   const int q2 = q1d * q1d, nq = (DIM == 3) ? q2 * q1d : q2;
+   const int oc = has_diff ? DIM * (DIM + 1) / 2 : 0, om = oc + (has_conv ? DIM : 0);
+   for (int64_t e = blockIdx.x; e < ne; e += gridDim.x)
+   {
+      for (int ij = threadIdx.x; ij < nd * nd; ij += blockDim.x)
+      {
+         const int i = ij / nd, j = ij - i * nd;
+         double a = 0.0;
+         for (int q = 0; q < nq; q++)
+         {
+            double pi, pj, gi[3], gj[3];
+            basis_at<DIM>(t, d1d, q1d, i, q, pi, gi);
+            basis_at<DIM>(t, d1d, q1d, j, q, pj, gj);
+            const double *dp = (DIM == 3) ? Dq + ((e * q1d + q / q2) * (int64_t)slab + q % q2)
+                                          : Dq + (e * (int64_t)slab + q);
+            if (has_diff)
+            {
+               if (DIM == 3)
+               {
+                  const double d11 = dp[0], d21 = dp[q2], d31 = dp[2 * q2], d22 = dp[3 * q2], d32 = dp[4 * q2], d33 = dp[5 * q2];
+                  a += gi[0] * (d11 * gj[0] + d21 * gj[1] + d31 * gj[2]) + gi[1] * (d21 * gj[0] + d22 * gj[1] + d32 * gj[2])
+                       + gi[2] * (d31 * gj[0] + d32 * gj[1] + d33 * gj[2]);
+               }
+               else
+               {
+                  const double d11 = dp[0], d21 = dp[q2], d22 = dp[2 * q2];
+                  a += gi[0] * (d11 * gj[0] + d21 * gj[1]) + gi[1] * (d21 * gj[0] + d22 * gj[1]);
+               }
+            }
+            if (has_conv)
+            {
+               double s = dp[oc * q2] * gj[0] + dp[(oc + 1) * q2] * gj[1];
+               if (DIM == 3) { s += dp[(oc + 2) * q2] * gj[2]; }
+               a += pi * s;
+            }
+            if (has_mass) { a += dp[om * q2] * pi * pj; }
+         }
+         const int32_t row = gather[e * nd + i], col = gather[e * nd + j];
+         int64_t lo = rowptr[row], hi = rowptr[row + 1] - 1;
+         while (lo < hi)                                       // the pattern contains col by construction
+         {
+            const int64_t mid = (lo + hi) >> 1;
+            if (colind[mid] < col) { lo = mid + 1; } else { hi = mid; }
+         }
+         atomicAdd(vals + lo, a);
+      }
+   }
+}
+
+// y = A x (unconstrained) or the FormLinearSystem / ConstrainedOperator matrix: essential rows -> identity,
+// essential columns skipped
+__global__ void __launch_bounds__(256)
+k_csr_spmv(int64_t n, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind, const double *__restrict__ vals,
+           const unsigned char *__restrict__ ess, const double *__restrict__ x, double *__restrict__ y)
+{
+   const int lane = threadIdx.x & 31;
+   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   if (row >= n) { return; }
+   if (ess && ess[row]) { if (lane == 0) { y[row] = x[row]; } return; }
+   double s = 0.0;
+   for (int64_t k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32)
+   {
+      const int32_t c = colind[k];
+      if (!ess || !ess[c]) { s += vals[k] * x[c]; }
+   }
+   s = warp_sum(s);
+   if (lane == 0) { y[row] = s; }
+}
+}  // namespace
+
+void cdm_csr_destroy(cdm_op *op)
+{
+   cdm_csr *m = op->csr;
+   if (!m) { return; }
+   cudaFree(m->rowptr_dev); cudaFree(m->colind_dev); cudaFree(m->vals_dev); cudaFree(m->ess_mark_dev);
+   delete m;
+   op->csr = nullptr;
+}
+
+// values only (the pattern is kept): used by cdm_operator_update
+static int csr_fill(cdm_op *op)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *c = sp->ctx;
+   cdm_csr *m = op->csr;
+   CDM_CUDA(c, cudaMemsetAsync(m->vals_dev, 0, sizeof(double) * (size_t)m->nnz, c->stream));
+   BasisTables t;
+   memset(&t, 0, sizeof(t));
+   for (int i = 0; i < sp->q1d * sp->d1d; i++) { t.B[i] = sp->B[i]; t.G[i] = sp->G[i]; }
+   const unsigned nb = (unsigned)std::min<int64_t>(sp->ne, (int64_t)c->sm_count * 16);
+   if (sp->dim == 2)
+   {
+      k_csr_assemble<2><<<nb, 256, 0, c->stream>>>(t, sp->d1d, sp->q1d, sp->ne, sp->gather_dev, op->D_dev, op->slab, op->has_diff,
+                                                   op->has_conv, op->has_mass, m->rowptr_dev, m->colind_dev, m->vals_dev);
+   }
+   else
+   {
+      k_csr_assemble<3><<<nb, 256, 0, c->stream>>>(t, sp->d1d, sp->q1d, sp->ne, sp->gather_dev, op->D_dev, op->slab, op->has_diff,
+                                                   op->has_conv, op->has_mass, m->rowptr_dev, m->colind_dev, m->vals_dev);
+   }
+   c->launches++;
+   CDM_CUDA(c, cudaGetLastError());
+   return CDM_OK;
+}
+
+int cdm_csr_refill_if_present(cdm_op *op) { return op->csr ? csr_fill(op) : CDM_OK; }
+
+int cdm_k_csr_spmv(cdm_op *op, const double *x, double *y, bool constrained)
+{
+   cdm_ctx *c = op->sp->ctx;
+   cdm_csr *m = op->csr;
+   const int64_t threads = m->n * 32;
+   const unsigned nb = (unsigned)((threads + 255) / 256);
+   if (c->time_main) { cudaEventRecord(c->evk0, c->stream); }
+   k_csr_spmv<<<nb, 256, 0, c->stream>>>(m->n, m->rowptr_dev, m->colind_dev, m->vals_dev,
+                                         (constrained && op->n_ess > 0) ? m->ess_mark_dev : nullptr, x, y);
+   if (c->time_main) { cudaEventRecord(c->evk1, c->stream); }
+   c->launches++;
+   CDM_CUDA(c, cudaGetLastError());
+   return CDM_OK;
+}
+
+extern "C" {
+
+int cdm_operator_assemble_csr(cdm_op *op)
+{
+   if (!op) { return CDM_EINVAL; }
+   cdm_space *sp = op->sp;
+   cdm_ctx *c = sp->ctx;
+   CDM_REQUIRE_GPU(c);
+   if (!sp->peers.empty() || sp->ntrue != sp->ndof) { return cdm_fail(c, CDM_EUNSUP, "cdm_operator_assemble_csr: single-rank spaces only"); }
+   if (op->csr) { return csr_fill(op); }
+   cdm_csr *m = new cdm_csr;
+   op->csr = m;
+   const int64_t n = sp->ndof;
+   const int nd = sp->nd;
+   m->n = n;
+   m->rowptr.assign(n + 1, 0);
+   // row g: the dofs of every element that touches g (offsets / indices = transpose of the gather map)
+   std::vector<int32_t> row;
+   for (int64_t g = 0; g < n; g++)
+   {
+      row.clear();
+      for (int32_t k = sp->offsets[g]; k < sp->offsets[g + 1]; k++)
+      {
+         const int64_t e = sp->indices[k] / nd;
+         row.insert(row.end(), sp->gather.begin() + e * nd, sp->gather.begin() + (e + 1) * nd);
+      }
+      std::sort(row.begin(), row.end());
+      row.erase(std::unique(row.begin(), row.end()), row.end());
+      m->colind.insert(m->colind.end(), row.begin(), row.end());
+      m->rowptr[g + 1] = (int64_t)m->colind.size();
+   }
+   m->nnz = (int64_t)m->colind.size();
+   std::vector<unsigned char> mark(n, 0);
+   for (int32_t g : op->ess_host) { mark[g] = 1; }
+   auto fail = [&](int rc) { cdm_csr_destroy(op); return rc; };
+   if (cudaMalloc(&m->rowptr_dev, sizeof(int64_t) * (n + 1)) != cudaSuccess || cudaMalloc(&m->colind_dev, sizeof(int32_t) * (size_t)m->nnz) != cudaSuccess ||
+       cudaMalloc(&m->vals_dev, sizeof(double) * (size_t)m->nnz) != cudaSuccess || cudaMalloc(&m->ess_mark_dev, (size_t)n) != cudaSuccess)
+   { cudaGetLastError(); return fail(cdm_fail(c, CDM_ENOMEM, "cdm_operator_assemble_csr: out of device memory")); }
+   cudaMemcpyAsync(m->rowptr_dev, m->rowptr.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, c->stream);
+   cudaMemcpyAsync(m->colind_dev, m->colind.data(), sizeof(int32_t) * (size_t)m->nnz, cudaMemcpyHostToDevice, c->stream);
+   cudaMemcpyAsync(m->ess_mark_dev, mark.data(), (size_t)n, cudaMemcpyHostToDevice, c->stream);
+   int rc = csr_fill(op);
+   if (cudaStreamSynchronize(c->stream) != cudaSuccess && !rc) { rc = cdm_fail(c, CDM_ECUDA, "cdm_operator_assemble_csr: device failure"); }
+   return rc ? fail(rc) : CDM_OK;
+}
+
+int cdm_operator_csr_sizes(const cdm_op *op, int64_t *nrows, int64_t *nnz)
+{
+   if (!op || !op->csr) { return CDM_EINVAL; }
+   if (nrows) { *nrows = op->csr->n; }
+   if (nnz) { *nnz = op->csr->nnz; }
+   return CDM_OK;
+}
+
+int cdm_operator_csr_get(const cdm_op *op, int64_t *rowptr, int32_t *colind, double *vals)
+{
+   if (!op || !op->csr) { return CDM_EINVAL; }
+   const cdm_csr *m = op->csr;
+   cdm_ctx *c = op->sp->ctx;
+   if (rowptr) { std::copy(m->rowptr.begin(), m->rowptr.end(), rowptr); }
+   if (colind) { std::copy(m->colind.begin(), m->colind.end(), colind); }
+   if (vals)
+   {
+      CDM_CUDA(c, cudaStreamSynchronize(c->stream));
+      CDM_CUDA(c, cudaMemcpy(vals, m->vals_dev, sizeof(double) * (size_t)m->nnz, cudaMemcpyDeviceToHost));
+   }
+   return CDM_OK;
+}
+
+}  // extern "C"

@@ -651,6 +651,7 @@ int cdm_k_apply_sub(cdm_op *op, const int32_t *gmap, const double *xL, double *y
 bool cdm_k_range_capable(const cdm_op *op)
 {
    const cdm_space *sp = op->sp;
+   if (op->assembly == 1 && op->csr) { return false; }      // the SpMV always sweeps all rows
    return !(sp->dim == 3 && sp->p == 3 && (op->kernel_variant == 1 || op->kernel_variant == 2));
 }
 
@@ -659,6 +660,7 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
 {
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
+   if (op->assembly == 1 && op->csr) { return cdm_k_csr_spmv(op, xL, yL, constrained); }   // the reference's literal path
    const int32_t *gmap = (constrained && op->gather_c_dev) ? op->gather_c_dev : sp->gather_dev;
    if (sp->dim == 3 && op->kernel_variant == 4)
    {

@@ -176,7 +176,16 @@ int  cdm_eliminate_rhs(cdm_op *op, const double *x_dev, double *b_dev);
 /* raw quadrature data (tests): host copy in MFEM layout, q fastest:
    Ddiff[(e*nsym+c)*nq+q], Dconv[(e*dim+c)*nq+q], Dmass[e*nq+q]; pointers may be NULL */
 int  cdm_operator_get_qdata(const cdm_op *op, double *Ddiff, double *Dconv, double *Dmass);
-/* tuning knobs (benchmarks): "scatter" (0 E-vector + deterministic gather transpose, 1 fp64 red.add, default),
+/* The reference's literal path on the device, for comparison with the matrix-free operator: a.Assemble()
+   into a sparse matrix (linear_convection_diffusion_2D.cpp:339) from the same quadrature data, and MatMult
+   inside the Krylov solve (:368) as a CSR SpMV; essential rows / columns are treated like the matrix
+   FormLinearSystem hands to the solver (:351).  Single rank.  cdm_operator_set_option(op, "assembly", 1)
+   assembles on demand and switches cdm_operator_apply / cdm_gmres / cdm_cg to the SpMV; cdm_operator_update
+   refills the values.  cdm_operator_csr_get: host copies, any pointer may be NULL (pattern: rows sorted). */
+int  cdm_operator_assemble_csr(cdm_op *op);
+int  cdm_operator_csr_sizes(const cdm_op *op, int64_t *nrows, int64_t *nnz);
+int  cdm_operator_csr_get(const cdm_op *op, int64_t *rowptr, int32_t *colind, double *vals);
+/* tuning knobs (benchmarks): "assembly" (0 partial assembly, default; 1 full assembly + SpMV, see above), "scatter" (0 E-vector + deterministic gather transpose, 1 fp64 red.add, default),
    "kernel" (0 block kernel, 1-3 order-3 warp kernels, 4 group kernel, 5 sub-warp kernel; default by order),
    "tail" (1: caller vectors have the local size, see cdm_operator_local_size),
    "overlap" (multi-GPU: 0 serial halo exchange, 1 overlapped with interior elements up to 3 neighbours, 2 always),
