@@ -5,7 +5,7 @@
 // every step on the device,
 // on an inline-hex (or inline-quad) Cartesian mesh instead of the Gmsh triangle mesh.
 //
-//   ./convdiff_steady [dim=3] [n=16] [order=3]
+//   ./convdiff_steady [dim=3] [n=16] [order=3] [legacy]      (legacy: assembled CSR + SpMV, the app's own algorithm)
 // exit codes as in the reference: 0 ok, 3 runtime failure (:435-442).
 #include "cdm_mfem_shim.hpp"
 #include <cmath>
@@ -17,6 +17,7 @@ int main(int argc, char **argv)
    const int dim = argc > 1 ? std::atoi(argv[1]) : 3;
    const int n = argc > 2 ? std::atoi(argv[2]) : 16;
    const int order = argc > 3 ? std::atoi(argv[3]) : 3;
+   const bool legacy = argc > 4 && std::string(argv[4]) == "legacy";
    const double kappa = 0.1, s = 1.0, c[3] = {1.0, -2.0, 0.5};     // Input/input_2d.yaml:7-10
    const int mn = 3;                                                 // mode_n = mode_m = 3 (:13-14)
    try
@@ -50,6 +51,7 @@ int main(int argc, char **argv)
       a.AddConvectionIntegrator(std::vector<double>(c, c + dim));
       a.AddMassIntegrator(s);
       a.SetEssentialTrueDofs(ess_tdof_list);
+      if (legacy) { a.SetAssemblyLevel(cdm::ConvectionDiffusionForm::AssemblyLevel::LEGACY); }   // default: PARTIAL
       a.Assemble();
 
       // ParLinearForm b: DomainLFIntegrator(f) (:341-343)

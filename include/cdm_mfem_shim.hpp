@@ -251,12 +251,21 @@ public:
    void AddMassIntegrator(double s) { mass_c_ = {s}; mass_ = {CDM_COEFF_CONST, 1, mass_c_.data()}; }
    void AddMassIntegrator(const std::vector<double> &per_qpt) { mass_c_ = per_qpt; mass_ = {CDM_COEFF_QPT, 1, mass_c_.data()}; }
    void SetEssentialTrueDofs(const std::vector<int32_t> &ess) { ess_ = ess; }
-   // a.Assemble(): quadrature data on the device
+   // a.SetAssemblyLevel(AssemblyLevel::PARTIAL / LEGACY): PARTIAL (default) is the matrix-free operator;
+   // LEGACY assembles the sparse matrix the application builds today and applies it as a CSR SpMV
+   enum class AssemblyLevel { LEGACY, PARTIAL };
+   void SetAssemblyLevel(AssemblyLevel level)
+   {
+      level_ = level;
+      if (op_) { check(fes_.ctx(), cdm_operator_set_option(op_, "assembly", level_ == AssemblyLevel::LEGACY ? 1 : 0), "cdm_operator_set_option"); }
+   }
+   // a.Assemble(): quadrature data on the device (and the CSR matrix for AssemblyLevel::LEGACY)
    void Assemble()
    {
       if (op_) { cdm_operator_destroy(op_); op_ = nullptr; }
       check(fes_.ctx(), cdm_operator_create(fes_.handle(), &kap_, &vel_, alpha_, &mass_, ess_.data(), (int64_t)ess_.size(), &op_),
             "cdm_operator_create");
+      if (level_ == AssemblyLevel::LEGACY) { check(fes_.ctx(), cdm_operator_set_option(op_, "assembly", 1), "cdm_operator_set_option"); }
    }
    // Operator::Mult of the constrained system operator
    void Mult(const Vector &x, Vector &y) const override
@@ -277,6 +286,7 @@ private:
    cdm_coeff kap_{CDM_COEFF_NONE, 0, nullptr}, vel_{CDM_COEFF_NONE, 0, nullptr}, mass_{CDM_COEFF_NONE, 0, nullptr};
    double alpha_ = 1.0;
    std::vector<int32_t> ess_;
+   AssemblyLevel level_ = AssemblyLevel::PARTIAL;
 };
 
 // mfem::IterativeSolver surface
