@@ -26,9 +26,10 @@ def _run(nproc, mode, order, n=(6, 5, 4)):
     return r.stdout
 
 
-@pytest.mark.parametrize("nproc,order", [(2, 3), (4, 2)])
-def test_partitioned_apply_gloo(nproc, order):
-    out = _run(nproc, "cpu", order)
+@pytest.mark.parametrize("nproc,order,mesh", [(2, 3, (6, 5, 4)), (4, 2, (6, 5, 4)), (8, 2, (4, 4, 4))])
+def test_partitioned_apply_gloo(nproc, order, mesh):
+    """2x1x1, 2x2x1 and 2x2x2 boxes (the last one has face, edge and corner neighbours: 7 peers per rank)"""
+    out = _run(nproc, "cpu", order, n=mesh)
     assert out.count("host-emulated partitioned apply") == nproc
 
 
