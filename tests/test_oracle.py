@@ -266,3 +266,25 @@ def test_golden_fixture_matches(orc):
         assert abs(np.linalg.norm(lf) - case["lf_norm"]) <= 1e-13 * case["lf_norm"]
         assert np.allclose(lf[:8], case["lf_head"], rtol=1e-12, atol=1e-15)
         assert abs(P.l2_error(x, fn(P.rule_coords(P.p + 2))) - case["l2_error"]) <= 1e-13 * case["l2_error"]
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_identity_ale_map_reduces_to_the_static_mesh_operator(orc, dim):
+    """The reference's own verification step for the ALE driver (diffusion_mms_ale_plan.tex:486-491): with the
+    identity map (J = 1, CofA = I, phi_hat = 0, div phi_hat = 0) the per-step form
+    Mass(J) + Diffusion((alpha dt / J) CofA CofA^T) + Convection(phi_hat, -1) + Mass(-div phi_hat)
+    (diffusion_mms_ale.cpp:1017-1023) is exactly the static-mesh backward-Euler form M + alpha dt K of
+    diffusion_mms.cpp:301-305.  Per-point coefficient arrays vs constants, both oracle formulations."""
+    alpha, dt, p, n = 0.1, 0.05, 2, 3
+    static = orc.Problem(dim, p, n, perturb=0.1, kappa=alpha * dt, vel=None, mass=1.0)
+    nsym = dim * (dim + 1) // 2
+    eye = np.zeros(nsym)
+    eye[[0, 2] if dim == 2 else [0, 3, 5]] = 1.0                       # packed symmetric identity
+    metric = np.broadcast_to(alpha * dt * eye, (static.ne, static.nq, nsym)).copy()
+    phi_hat = np.zeros((static.ne, static.nq, dim))
+    jac = np.ones((static.ne, static.nq))                              # J - div(phi_hat) = 1 - 0 in one mass term
+    ale = orc.Problem(dim, p, n, perturb=0.1, kappa=metric, vel=phi_hat, alpha=-1.0, mass=jac)
+    x = np.sin(1.0 + 0.37 * np.arange(static.ndof))
+    ys = static.pa_apply(x)
+    assert np.linalg.norm(ale.pa_apply(x) - ys) <= 1e-14 * np.linalg.norm(ys)
+    assert np.linalg.norm(ale.csr().spmv(x) - static.csr().spmv(x)) <= 1e-14 * np.linalg.norm(ys)
