@@ -107,6 +107,14 @@ SIGNATURES = {
     "cdm_operator_csr_sizes": (_ci, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "cdm_operator_csr_get": (_ci, [_vp, _vp, _vp, _vp]),
     "cdm_operator_set_option": (_ci, [_vp, C.c_char_p, _ci]),
+    "cdm_integrator_add_mult_pa": (_ci, [_vp, _vp, _vp]),
+    "cdm_integrator_assemble_diagonal_pa": (_ci, [_vp, _vp]),
+    "cdm_restriction_mult": (_ci, [_vp, _vp, _vp]),
+    "cdm_restriction_mult_transpose": (_ci, [_vp, _vp, _vp]),
+    "cdm_prolongate": (_ci, [_vp, _vp, _vp]),
+    "cdm_prolongate_transpose": (_ci, [_vp, _vp, _vp]),
+    "cdm_space_local_size": (_i64, [_vp]),
+    "cdm_space_true_size": (_i64, [_vp]),
     "cdm_operator_time_kernel": (_ci, [_vp, _vp, _vp, _ci, _ci, C.POINTER(_cd)]),
     "cdm_rule_points": (_ci, [_ci]),
     "cdm_space_rule_coords": (_ci, [_vp, _ci, _vp]),
@@ -350,6 +358,23 @@ class H1Space:
         lib().cdm_space_dof_global(self.h, _ptr(k))
         return k
 
+    # --- ElementRestriction / prolongation on device vectors
+    def restrict(self, xL, xE):
+        """ElementRestriction::Mult: xE[e, d] = xL[gather[e, d]]"""
+        self.ctx.check(lib().cdm_restriction_mult(self.h, _ptr(xL), _ptr(xE)))
+
+    def restrict_transpose(self, yE, yL):
+        """ElementRestriction::MultTranspose (deterministic gather)"""
+        self.ctx.check(lib().cdm_restriction_mult_transpose(self.h, _ptr(yE), _ptr(yL)))
+
+    def prolongate(self, xT, uL):
+        """RecoverFEMSolution: u_L = P x_T (ghost entries from their owners)"""
+        self.ctx.check(lib().cdm_prolongate(self.h, _ptr(xT), _ptr(uL)))
+
+    def prolongate_transpose(self, bL, bT=None):
+        """ParallelAssemble: b_T = P^T b_L"""
+        self.ctx.check(lib().cdm_prolongate_transpose(self.h, _ptr(bL), _ptr(bT)))
+
     def qpt_coords(self):
         out = np.zeros((self.ne, self.nq, self.dim))
         lib().cdm_space_qpt_coords(self.h, _ptr(out))
@@ -477,6 +502,14 @@ class ConvectionDiffusionOperator:
         self.ctx.check(lib().cdm_operator_time_kernel(self.h, _ptr(x), _ptr(y), reps, 1 if constrained else 0,
                                                       C.byref(ms)))
         return ms.value
+
+    def AddMultPA(self, xE, yE):
+        """BilinearFormIntegrator::AddMultPA on E-vectors: yE += B^T D B xE"""
+        self.ctx.check(lib().cdm_integrator_add_mult_pa(self.h, _ptr(xE), _ptr(yE)))
+
+    def AssembleDiagonalPA(self, dE):
+        """BilinearFormIntegrator::AssembleDiagonalPA: dE += element-wise diagonal"""
+        self.ctx.check(lib().cdm_integrator_assemble_diagonal_pa(self.h, _ptr(dE)))
 
     def AssembleDiagonal(self, d):
         self.ctx.check(lib().cdm_operator_diag(self.h, _ptr(d)))

@@ -83,6 +83,7 @@ int cdm_finalize(cdm_ctx *c)
       if (c->stream) { cudaStreamSynchronize(c->stream); }
       if (c->red_dev) { cudaFree(c->red_dev); }
       if (c->red_host) { cudaFreeHost(c->red_host); }
+      if (c->p2p_err_host) { cudaFreeHost(c->p2p_err_host); }
       if (c->ev0) { cudaEventDestroy(c->ev0); }
       if (c->ev1) { cudaEventDestroy(c->ev1); }
       if (c->evk0) { cudaEventDestroy(c->evk0); }
@@ -105,7 +106,7 @@ int cdm_sync(cdm_ctx *c)
 {
    CDM_REQUIRE_GPU(c);
    CDM_CUDA(c, cudaStreamSynchronize(c->stream));
-   return CDM_OK;
+   return cdm_check_p2p(c);
 }
 
 // ------------------------------------------------------------------ space
@@ -465,7 +466,7 @@ int cdm_space_destroy(cdm_space *sp)
    if (sp->ctx && sp->ctx->device >= 0)
    {
       cudaFree(sp->gather_dev); cudaFree(sp->offsets_dev); cudaFree(sp->indices_dev); cudaFree(sp->elem_x_dev);
-      cudaFree(sp->work_dev); cudaFree(sp->elem_part_dev);
+      cudaFree(sp->work_dev); cudaFree(sp->elem_part_dev); cudaFree(sp->iota_dev);
       cdm_halo_p2p_destroy(sp);
       cdm_halo_plan &hp = sp->halo;
       cudaFree(hp.own_all_dev); cudaFree(hp.ghost_all_dev); cudaFree(hp.pt_dof_dev); cudaFree(hp.pt_off_dev);
@@ -544,6 +545,7 @@ int cdm_operator_update(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel
 {
    if (!op) { return CDM_EINVAL; }
    cdm_ctx *ctx = op->sp->ctx;
+   CDM_REQUIRE_GPU(ctx);
    const int hk = check_coeff(kappa, op->sp->dim, 0), hv = check_coeff(vel, op->sp->dim, 1), hm = check_coeff(mass, op->sp->dim, 2);
    if (hk < 0 || hv < 0 || hm < 0 || (hk > 0) != op->has_diff || (hv > 0) != op->has_conv || (hm > 0) != op->has_mass)
       return cdm_fail(ctx, CDM_EINVAL, "cdm_operator_update: the set of integrators must not change");
@@ -552,6 +554,8 @@ int cdm_operator_update(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel
    return rc ? rc : cdm_csr_refill_if_present(op);        // an assembled matrix follows the new coefficients
 }
 
+static void destroy_host_pipe(cdm_op *op);
+
 int cdm_operator_destroy(cdm_op *op)
 {
    if (!op) { return CDM_OK; }
@@ -559,6 +563,7 @@ int cdm_operator_destroy(cdm_op *op)
    cudaFree(op->D_dev); cudaFree(op->gather_c_dev); cudaFree(op->ess_dev); cudaFree(op->yE_dev);
    cudaFree(op->xL_dev); cudaFree(op->yL_dev); cudaFree(op->dinv_dev); cudaFree(op->kry_dev);
    for (int i = 0; i < 3; i++) { cudaFree(op->coef_dev[i]); }
+   destroy_host_pipe(op);
    cdm_csr_destroy(op);
    delete op;
    return CDM_OK;
@@ -589,6 +594,7 @@ int cdm_operator_set_option(cdm_op *op, const char *name, int value)
       return CDM_OK;
    }
    if (!std::strcmp(name, "tail")) { op->tail = value != 0; return CDM_OK; }
+   if (!std::strcmp(name, "grid_cap")) { if (value < 0) { return CDM_EINVAL; } op->grid_cap = value; return CDM_OK; }
    if (!std::strcmp(name, "host_pipeline")) { op->host_pipeline = value; return CDM_OK; }
    if (!std::strcmp(name, "overlap")) { if (value < 0 || value > 2) { return CDM_EINVAL; } op->overlap = value; return CDM_OK; }
    return cdm_fail(op->sp->ctx, CDM_EINVAL, std::string("unknown option ") + name);
@@ -690,6 +696,7 @@ int cdm_operator_apply(cdm_op *op, const double *x_dev, double *y_dev)
 {
    if (!op || !x_dev || !y_dev) { return CDM_EINVAL; }
    if (x_dev == y_dev) { return cdm_fail(op->sp->ctx, CDM_EINVAL, "cdm_operator_apply: x and y must not alias"); }
+   CDM_REQUIRE_GPU(op->sp->ctx);
    return apply_T(op, x_dev, y_dev, true);
 }
 
@@ -697,6 +704,7 @@ int cdm_operator_apply_unconstrained(cdm_op *op, const double *x_dev, double *y_
 {
    if (!op || !x_dev || !y_dev) { return CDM_EINVAL; }
    if (x_dev == y_dev) { return cdm_fail(op->sp->ctx, CDM_EINVAL, "cdm_operator_apply_unconstrained: x and y must not alias"); }
+   CDM_REQUIRE_GPU(op->sp->ctx);
    return apply_T(op, x_dev, y_dev, false);
 }
 
@@ -706,6 +714,18 @@ int cdm_operator_apply_unconstrained(cdm_op *op, const double *x_dev, double *y_
 // uploaded part of each class, and the dofs whose last element lies in chunk c a block at the front of the not
 // yet downloaded part.  ub[c+1][k] = one past the largest class-k dof touched by chunks <= c (upload bound),
 // db[c+1][k] = the smallest class-k dof still touched by a chunk > c (download bound).
+static void destroy_host_pipe(cdm_op *op)
+{
+   cdm_op::host_pipe &hp = op->pipe;
+   if (hp.su) { cudaStreamDestroy(hp.su); hp.su = nullptr; }
+   if (hp.sd) { cudaStreamDestroy(hp.sd); hp.sd = nullptr; }
+   for (cudaEvent_t e : hp.ev_up) { if (e) { cudaEventDestroy(e); } }
+   for (cudaEvent_t e : hp.ev_k) { if (e) { cudaEventDestroy(e); } }
+   hp.ev_up.clear(); hp.ev_k.clear();
+   cudaFree(hp.ess_by_chunk_dev); hp.ess_by_chunk_dev = nullptr;
+   hp.K = 0;
+}
+
 static int build_host_pipe(cdm_op *op)
 {
    cdm_space *sp = op->sp;
@@ -747,7 +767,7 @@ static int build_host_pipe(cdm_op *op)
    }
    CDM_CUDA(ctx, cudaStreamCreateWithFlags(&hp.su, cudaStreamNonBlocking));
    CDM_CUDA(ctx, cudaStreamCreateWithFlags(&hp.sd, cudaStreamNonBlocking));
-   hp.ev_up.resize(K); hp.ev_k.resize(K);
+   hp.ev_up.assign(K, nullptr); hp.ev_k.assign(K, nullptr);
    for (int c = 0; c < K; c++)
    {
       CDM_CUDA(ctx, cudaEventCreateWithFlags(&hp.ev_up[c], cudaEventDisableTiming));
@@ -783,14 +803,19 @@ static int mult_host_pipelined(cdm_op *op, const double *x_host, double *y_host,
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
    int rc;
-   if (op->pipe.K == 0 && (rc = build_host_pipe(op))) { return rc; }
+   if (op->pipe.K == 0 && (rc = build_host_pipe(op))) { destroy_host_pipe(op); return rc; }
    cdm_op::host_pipe &hp = op->pipe;
    const int K = hp.K;
    cudaStream_t C = ctx->stream;
    static const bool debug = getenv("CDM_PIPE_DEBUG") != nullptr;
    const auto t0 = std::chrono::steady_clock::now();
+   // work already queued on the compute stream may still read xL / yL (cdm_eliminate_rhs returns without a sync):
+   // the upload and download streams start after it
+   CDM_CUDA(ctx, cudaEventRecord(ctx->ev0, C));
+   CDM_CUDA(ctx, cudaStreamWaitEvent(hp.su, ctx->ev0, 0));
+   CDM_CUDA(ctx, cudaStreamWaitEvent(hp.sd, ctx->ev0, 0));
    CDM_CUDA(ctx, cudaMemsetAsync(op->yL_dev, 0, sizeof(double) * (size_t)sp->ndof, C));
-   // all uploads first (they depend on nothing), then per chunk: kernel, download
+   // all uploads first (they depend on nothing else), then per chunk: kernel, download
    for (int c = 0; c < K; c++)
    {
       for (int k = 0; k < 4; k++)
@@ -844,6 +869,7 @@ int cdm_operator_mult_host(cdm_op *op, const double *x_host, double *y_host, int
    if (!op || !x_host || !y_host) { return CDM_EINVAL; }
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
+   CDM_REQUIRE_GPU(ctx);
    int rc = ensure_L(op); if (rc) { return rc; }
    if (op->host_pipeline && ctx->nranks == 1 && sp->dim == 3 && sp->class_off.size() == 5 && op->scatter_mode == 1 &&
        cdm_k_range_capable(op) && sp->ne >= 8192)
@@ -862,6 +888,7 @@ int cdm_operator_diag(cdm_op *op, double *d_dev)
    if (!op || !d_dev) { return CDM_EINVAL; }
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
+   CDM_REQUIRE_GPU(ctx);
    int rc;
    const bool par = ctx->nranks > 1 && !sp->peers.empty();
    double *dst = d_dev;
@@ -878,6 +905,7 @@ int cdm_eliminate_rhs(cdm_op *op, const double *x_dev, double *b_dev)
    if (!op || !x_dev || !b_dev) { return CDM_EINVAL; }
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
+   CDM_REQUIRE_GPU(ctx);
    int rc = ensure_L(op); if (rc) { return rc; }
    // w = 0 ; w[ess] = x[ess]
    CDM_CUDA(ctx, cudaMemsetAsync(op->xL_dev, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream));
@@ -892,6 +920,7 @@ int cdm_operator_time_kernel(cdm_op *op, const double *x_dev, double *y_dev, int
 {
    if (!op || !x_dev || !y_dev || reps < 1 || !mean_ms) { return CDM_EINVAL; }
    cdm_ctx *ctx = op->sp->ctx;
+   CDM_REQUIRE_GPU(ctx);
    if (!ctx->evk0) { CDM_CUDA(ctx, cudaEventCreate(&ctx->evk0)); CDM_CUDA(ctx, cudaEventCreate(&ctx->evk1)); }
    double tot = 0.0;
    ctx->time_main = true;

@@ -3,7 +3,9 @@
 #include "cdm_b200.h"
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #define CDM_MAX_D1D 7
@@ -33,6 +35,12 @@ struct cdm_ctx
    // kernel-only timing (cdm_operator_time_kernel)
    bool time_main = false;
    cudaEvent_t evk0 = nullptr, evk1 = nullptr;
+   // per-context launch configuration of every kernel instantiation that needs the dynamic shared-memory
+   // opt-in: (kernel, shared bytes) -> resident blocks per SM on THIS device (cdm_kernel_cfg)
+   std::map<std::pair<const void *, size_t>, int> kernel_cfg;
+   // device-side error word of the peer-memory halo exchange (mapped pinned host memory): a kernel that gave up
+   // waiting for a neighbour sets it, the next host synchronisation point turns it into CDM_ENCCL
+   unsigned int *p2p_err_host = nullptr, *p2p_err_dev = nullptr;
 };
 
 struct cdm_mesh
@@ -96,6 +104,7 @@ struct cdm_space
    // device
    int32_t *gather_dev = nullptr, *offsets_dev = nullptr, *indices_dev = nullptr;
    double *elem_x_dev = nullptr;
+   int32_t *iota_dev = nullptr;                       // identity gather map [ne*nd] (E-vector input, lazy)
    double *work_dev = nullptr;                        // L-vector scratch of the form kernels (lazy, partitioned spaces)
    double *elem_part_dev = nullptr;                   // per-block partial sums of the error-norm kernel (lazy)
    // multi-GPU
@@ -133,6 +142,9 @@ struct cdm_op
    int assembly = 0;               // 0: partial assembly (matrix-free), 1: apply = SpMV with the assembled CSR matrix
    struct cdm_csr *csr = nullptr;  // csr_path.cu (built on demand)
    int kernel_variant = 0;
+   int64_t grid_cap = 0;           // > 0: upper bound on the persistent grids (tests: forces many elements per warp)
+   double *e_out = nullptr;        // != null: E-vector output of the element kernels goes here and is not transposed
+   const int32_t *gmap_override = nullptr;   // != null: gather map of the next launch (identity map: E-vector input)
    // pipelined host-vector apply (cdm_operator_mult_host): element chunks, per-class upload / download bounds
    struct host_pipe
    {
@@ -153,14 +165,23 @@ struct cdm_op
 
 // ---- error helpers
 int cdm_fail(const cdm_ctx *ctx, int code, const std::string &msg);
+// dynamic shared-memory opt-in + occupancy of one kernel instantiation, cached per context (= per device)
+int cdm_kernel_cfg(cdm_ctx *ctx, const void *kern, int threads, size_t smem, const char *name, int *blocks_per_sm);
+// CDM_ENCCL if a peer-memory halo kernel of this context timed out since the last check (clears the word)
+int cdm_check_p2p(cdm_ctx *ctx);
 #define CDM_CUDA(ctx, call)                                                              \
    do { cudaError_t e_ = (call);                                                         \
         if (e_ != cudaSuccess)                                                           \
            return cdm_fail(ctx, CDM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
    } while (0)
+// every compute entry point starts here: fail without a device, and make the context's device the calling
+// thread's current one (several contexts on different devices may live in one process)
 #define CDM_REQUIRE_GPU(ctx)                                                             \
    do { if (!(ctx) || (ctx)->device < 0)                                                 \
            return cdm_fail(ctx, CDM_ENOGPU, "no CUDA device bound to this context (no CPU fallback)"); \
+        int cur_ = -1;                                                                   \
+        if (cudaGetDevice(&cur_) != cudaSuccess || cur_ != (ctx)->device)                \
+           CDM_CUDA(ctx, cudaSetDevice((ctx)->device));                                  \
    } while (0)
 
 // ---- host-side builders (host_*.cpp)
@@ -180,6 +201,9 @@ int cdm_k_setup_qdata(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel, 
 int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained);
 bool cdm_k_range_capable(const cdm_op *op);   // does the selected kernel honour op->range_on?
 int cdm_k_diag(cdm_op *op, double *dL);
+int cdm_k_diag_evec(cdm_op *op, double *dE);     // element-wise diagonal, E-vector layout
+int cdm_k_ensure_yE(cdm_op *op);
+int cdm_k_restrict_transpose(cdm_space *sp, const double *yE, double *yL);
 int cdm_k_get_qdata(const cdm_op *op, double *Ddiff, double *Dconv, double *Dmass);
 int cdm_k_upload_basis(cdm_space *sp);
 

@@ -50,6 +50,12 @@ NcclApi *api()
 }
 }  // namespace
 
+// inside ncclGroupStart ... ncclGroupEnd: close the group before reporting the error
+#define NCCL_GROUP_CALL(ctx, call)                                                             \
+   do { nccl_result r_ = (call);                                                               \
+        if (r_ != 0) { api()->GroupEnd();                                                      \
+           return cdm_fail(ctx, CDM_ENCCL, std::string(#call) + ": " + api()->GetErrorString(r_)); } \
+   } while (0)
 #define NCCL_CALL(ctx, call)                                                                   \
    do { nccl_result r_ = (call);                                                               \
         if (r_ != 0) { return cdm_fail(ctx, CDM_ENCCL, std::string(#call) + ": " + api()->GetErrorString(r_)); } \
@@ -141,8 +147,8 @@ static int halo_P_impl(cdm_space *sp, double *xL, bool halo_stream, cudaEvent_t 
    NCCL_CALL(c, a->GroupStart());
    for (auto &pr : sp->peers)
    {
-      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Send(hp.send_dev + pr.own_off, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
-      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Recv(hp.recv_dev + pr.ghost_off, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
+      if (!pr.own_idx.empty()) { NCCL_GROUP_CALL(c, a->Send(hp.send_dev + pr.own_off, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
+      if (!pr.ghost_idx.empty()) { NCCL_GROUP_CALL(c, a->Recv(hp.recv_dev + pr.ghost_off, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
    }
    NCCL_CALL(c, a->GroupEnd());
    return cdm_k_unpack(c, (int64_t)hp.ghost_all.size(), hp.ghost_all_dev, hp.recv_dev, xL, 0);
@@ -168,8 +174,8 @@ static int halo_PT_impl(cdm_space *sp, double *yL, bool halo_stream, cudaEvent_t
    NCCL_CALL(c, a->GroupStart());
    for (auto &pr : sp->peers)
    {
-      if (!pr.ghost_idx.empty()) { NCCL_CALL(c, a->Send(hp.send_dev + pr.ghost_off, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
-      if (!pr.own_idx.empty()) { NCCL_CALL(c, a->Recv(hp.recv_dev + pr.own_off, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
+      if (!pr.ghost_idx.empty()) { NCCL_GROUP_CALL(c, a->Send(hp.send_dev + pr.ghost_off, pr.ghost_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
+      if (!pr.own_idx.empty()) { NCCL_GROUP_CALL(c, a->Recv(hp.recv_dev + pr.own_off, pr.own_idx.size(), NCCL_FLOAT64, pr.rank, comm, c->stream)); }
    }
    NCCL_CALL(c, a->GroupEnd());
    return cdm_k_unpack_add_csr(c, (int64_t)hp.pt_dof.size(), hp.pt_dof_dev, hp.pt_off_dev, hp.pt_src_dev, hp.recv_dev, yL);

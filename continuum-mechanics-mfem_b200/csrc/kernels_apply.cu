@@ -661,7 +661,8 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
    if (op->assembly == 1 && op->csr) { return cdm_k_csr_spmv(op, xL, yL, constrained); }   // the reference's literal path
-   const int32_t *gmap = (constrained && op->gather_c_dev) ? op->gather_c_dev : sp->gather_dev;
+   const int32_t *gmap = op->gmap_override ? op->gmap_override
+                                           : ((constrained && op->gather_c_dev) ? op->gather_c_dev : sp->gather_dev);
    if (sp->dim == 3 && op->kernel_variant == 4)
    {
       const int rc = cdm_k_apply_group(op, gmap, xL, yL);
@@ -684,7 +685,7 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
    const int64_t e0 = op->range_on ? op->e_begin : 0, n_el = (op->range_on ? op->e_end : sp->ne) - e0;
    if (n_el <= 0) { return CDM_OK; }
    if (atomic) { if (!op->range_on) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); } }
-   else { int rc = ensure_yE(op); if (rc) { return rc; } out = op->yE_dev; }
+   else { int rc = ensure_yE(op); if (rc) { return rc; } out = op->e_out ? op->e_out : op->yE_dev; }
    const BasisTables bt = make_tables(sp);
    if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }
    if (sp->dim == 3)
@@ -705,7 +706,7 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
    }
    if (ctx->time_main) { cudaEventRecord(ctx->evk1, ctx->stream); }
    ctx->launches++;
-   if (!atomic)
+   if (!atomic && !op->e_out)
    {
       const unsigned nb = (unsigned)((sp->ndof + 255) / 256);
       k_restrict_transpose<<<nb, 256, 0, ctx->stream>>>(sp->ndof, sp->offsets_dev, sp->indices_dev, op->yE_dev, yL);
@@ -715,11 +716,11 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
    return CDM_OK;
 }
 
-int cdm_k_diag(cdm_op *op, double *dL)
+// element-wise diagonal (E-vector layout [ne][nd]) written to dE
+int cdm_k_diag_evec(cdm_op *op, double *dE)
 {
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
-   int rc = ensure_yE(op); if (rc) { return rc; }
    const BasisTables bt = make_tables(sp);
    const int64_t n = sp->ne * sp->nd;
    const unsigned nb = (unsigned)((n + 127) / 128);
@@ -727,22 +728,46 @@ int cdm_k_diag(cdm_op *op, double *dL)
    {
       const unsigned nb3 = (unsigned)((sp->ne * sp->d1d * sp->d1d + 127) / 128);
 #define DIAG3(P) case P: k_diag3d_sumfact<P + 1, P + 2><<<nb3, 128, 0, ctx->stream>>>(                    \
-         bt, sp->ne, op->D_dev, op->slab, op->has_diff, op->has_conv, op->has_mass, op->yE_dev); break
+         bt, sp->ne, op->D_dev, op->slab, op->has_diff, op->has_conv, op->has_mass, dE); break
       switch (sp->p)
       {
          DIAG3(1); DIAG3(2); DIAG3(3); DIAG3(4); DIAG3(5); DIAG3(6);
          default:
             k_diag_elem<3><<<nb, 128, 0, ctx->stream>>>(bt, sp->d1d, sp->q1d, sp->ne, op->D_dev, op->slab,
-                                                        op->has_diff, op->has_conv, op->has_mass, op->yE_dev);
+                                                        op->has_diff, op->has_conv, op->has_mass, dE);
       }
 #undef DIAG3
    }
    else
       k_diag_elem<2><<<nb, 128, 0, ctx->stream>>>(bt, sp->d1d, sp->q1d, sp->ne, op->D_dev, op->slab,
-                                                  op->has_diff, op->has_conv, op->has_mass, op->yE_dev);
+                                                  op->has_diff, op->has_conv, op->has_mass, dE);
+   ctx->launches++;
+   CDM_CUDA(ctx, cudaGetLastError());
+   return CDM_OK;
+}
+
+int cdm_k_diag(cdm_op *op, double *dL)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   int rc = ensure_yE(op); if (rc) { return rc; }
+   if ((rc = cdm_k_diag_evec(op, op->yE_dev))) { return rc; }
    const unsigned nb2 = (unsigned)((sp->ndof + 255) / 256);
    k_restrict_transpose<<<nb2, 256, 0, ctx->stream>>>(sp->ndof, sp->offsets_dev, sp->indices_dev, op->yE_dev, dL);
-   ctx->launches += 2;
+   ctx->launches++;
+   CDM_CUDA(ctx, cudaGetLastError());
+   return CDM_OK;
+}
+
+int cdm_k_ensure_yE(cdm_op *op) { return ensure_yE(op); }
+
+// ElementRestriction::MultTranspose: yL[g] = sum of the E-vector entries that map to g (fixed order)
+int cdm_k_restrict_transpose(cdm_space *sp, const double *yE, double *yL)
+{
+   cdm_ctx *ctx = sp->ctx;
+   const unsigned nb = (unsigned)((sp->ndof + 255) / 256);
+   k_restrict_transpose<<<nb, 256, 0, ctx->stream>>>(sp->ndof, sp->offsets_dev, sp->indices_dev, yE, yL);
+   ctx->launches++;
    CDM_CUDA(ctx, cudaGetLastError());
    return CDM_OK;
 }

@@ -642,15 +642,8 @@ int launch_bg(cdm_op *op, const WarpTablesBG &tb, const int32_t *gmap, const dou
    auto kern = k_apply3d_warp_bg<NW, DIFF, CONV, MASS, ATOMIC>;
    const int warp_doubles = (5 * op->slab + 3 * 112 + 2 * 80 + 15) & ~15;
    const size_t smem = (size_t)(NW * warp_doubles) * sizeof(double) + (size_t)NW * 5 * sizeof(uint64_t);
-   static size_t configured = 0;
-   static int blocks_per_sm = 0;
-   if (configured != smem)
-   {
-      CDM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CDM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NW * 32, smem));
-      if (blocks_per_sm < 1) { return cdm_fail(ctx, CDM_ECUDA, "k_apply3d_warp_bg does not fit on an SM"); }
-      configured = smem;
-   }
+   int blocks_per_sm = 0;
+   { const int rc = cdm_kernel_cfg(ctx, (const void *)kern, NW * 32, smem, "k_apply3d_warp_bg", &blocks_per_sm); if (rc) { return rc; } }
    // element range [e0, e1): the kernel sees a shifted view of the per-element arrays
    const int64_t e0 = op->range_on ? op->e_begin : 0, e1 = op->range_on ? op->e_end : sp->ne;
    const int64_t n = e1 - e0;
@@ -658,6 +651,7 @@ int launch_bg(cdm_op *op, const WarpTablesBG &tb, const int32_t *gmap, const dou
    int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
    const int64_t need = (n + NW - 1) / NW;
    if (grid > need) { grid = need; }
+   if (op->grid_cap > 0 && grid > op->grid_cap) { grid = op->grid_cap; }
    if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }
    kern<<<(unsigned)grid, NW * 32, smem, ctx->stream>>>(tb, n, gmap + e0 * 64, xL, op->D_dev + e0 * 5 * (int64_t)op->slab,
                                                         op->slab, ATOMIC ? out : out + e0 * 64);
@@ -699,18 +693,12 @@ int launch(cdm_op *op, const WarpTables &tb, const int32_t *gmap, const double *
    const int warp_doubles = PH ? ((Q * op->slab + Q * Q * Q + 2 * Q * Q * Q + 15) & ~15)
                                : ((Q * op->slab + Q * Q * Q + 2 * 2 * Q * Q + (28 * (D - 1) + Q * Q + 3) + 15) & ~15);
    const size_t smem = (size_t)(NW * warp_doubles) * sizeof(double) + (size_t)NW * Q * sizeof(uint64_t);
-   static size_t configured = 0;
-   static int blocks_per_sm = 0;
-   if (configured != smem)
-   {
-      CDM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CDM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NW * 32, smem));
-      if (blocks_per_sm < 1) { return cdm_fail(ctx, CDM_ECUDA, "k_apply3d_warp does not fit on an SM"); }
-      configured = smem;
-   }
+   int blocks_per_sm = 0;
+   { const int rc = cdm_kernel_cfg(ctx, (const void *)kern, NW * 32, smem, "k_apply3d_warp", &blocks_per_sm); if (rc) { return rc; } }
    int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
    const int64_t need = (sp->ne + NW - 1) / NW;
    if (grid > need) { grid = need; }
+   if (op->grid_cap > 0 && grid > op->grid_cap) { grid = op->grid_cap; }
    if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }
    kern<<<(unsigned)grid, NW * 32, smem, ctx->stream>>>(tb, sp->ne, gmap, xL, op->D_dev, op->slab, out);
    if (ctx->time_main) { cudaEventRecord(ctx->evk1, ctx->stream); }
@@ -763,7 +751,7 @@ int cdm_k_apply_p3(cdm_op *op, const int32_t *gmap, const double *xL, double *yL
    else
    {
       if (!op->yE_dev) { CDM_CUDA(ctx, cudaMalloc(&op->yE_dev, sizeof(double) * (size_t)sp->ne * sp->nd)); }
-      out = op->yE_dev;
+      out = op->e_out ? op->e_out : op->yE_dev;
    }
    int rc = 0;
    if (op->kernel_variant >= 3)
@@ -786,7 +774,7 @@ int cdm_k_apply_p3(cdm_op *op, const int32_t *gmap, const double *xL, double *yL
       DISPATCH_FLAGS(4, 5)
    }
    if (rc) { return rc; }
-   if (!atomic)
+   if (!atomic && !op->e_out)
    {
       const unsigned nb = (unsigned)((sp->ndof + 255) / 256);
       k_restrict_transpose_p3<<<nb, 256, 0, ctx->stream>>>(sp->ndof, sp->offsets_dev, sp->indices_dev, op->yE_dev, yL);

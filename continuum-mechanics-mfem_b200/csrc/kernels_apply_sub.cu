@@ -349,21 +349,15 @@ int launch_sub(cdm_op *op, const SubTables &tb, const int32_t *gmap, const doubl
    auto kern = k_apply3d_sub<D, Q, NW, DIFF, CONV, MASS, ATOMIC>;
    const int warp_doubles = (EPW * sub_elem_doubles<D, Q>(op->slab) + 15) & ~15;
    const size_t smem = (size_t)(NW * warp_doubles) * sizeof(double) + (size_t)NW * Q * sizeof(uint64_t);
-   static size_t configured = 0;
-   static int blocks_per_sm = 0;
-   if (configured != smem)
-   {
-      CDM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CDM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, NW * 32, smem));
-      if (blocks_per_sm < 1) { return cdm_fail(ctx, CDM_ECUDA, "k_apply3d_sub does not fit on an SM"); }
-      configured = smem;
-   }
+   int blocks_per_sm = 0;
+   { const int rc = cdm_kernel_cfg(ctx, (const void *)kern, NW * 32, smem, "k_apply3d_sub", &blocks_per_sm); if (rc) { return rc; } }
    const int64_t e0 = op->range_on ? op->e_begin : 0, e1 = op->range_on ? op->e_end : sp->ne;
    const int64_t n = e1 - e0;
    if (n <= 0) { return CDM_OK; }
    int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
    const int64_t need = (n + NW * EPW - 1) / (NW * EPW);
    if (grid > need) { grid = need; }
+   if (op->grid_cap > 0 && grid > op->grid_cap) { grid = op->grid_cap; }
    if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }
    kern<<<(unsigned)grid, NW * 32, smem, ctx->stream>>>(tb, n, gmap + e0 * ND, xL, op->D_dev + e0 * Q * (int64_t)op->slab,
                                                         op->slab, ATOMIC ? out : out + e0 * ND);
@@ -409,13 +403,13 @@ int cdm_k_apply_sub(cdm_op *op, const int32_t *gmap, const double *xL, double *y
    if (!atomic)
    {
       if (!op->yE_dev) { CDM_CUDA(ctx, cudaMalloc(&op->yE_dev, sizeof(double) * (size_t)sp->ne * sp->nd)); }
-      out = op->yE_dev;
+      out = op->e_out ? op->e_out : op->yE_dev;
    }
    // red.add accumulates: the caller of a ranged launch (overlapped multi-GPU schedule) zeroes y itself
    else if (!op->range_on) { CDM_CUDA(ctx, cudaMemsetAsync(yL, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream)); }
    int rc = (sp->p == 2) ? (SUB_FLAGS(3, 4)) : (SUB_FLAGS(2, 3));
    if (rc) { return rc; }
-   if (!atomic)
+   if (!atomic && !op->e_out)
    {
       const int64_t nb = (sp->ndof + 255) / 256;
       k_restrict_transpose_sub<<<(unsigned)nb, 256, 0, ctx->stream>>>(sp->ndof, sp->offsets_dev, sp->indices_dev, op->yE_dev, yL);

@@ -344,15 +344,8 @@ int launch_group(cdm_op *op, const GroupTables &tb, const int32_t *gmap, const d
    auto kern = k_apply3d_group<P, DIFF, CONV, MASS, ATOMIC>;
    const int group_doubles = (C::Q * op->slab + 3 * C::RS + 2 * C::PS + 1) & ~1;
    const size_t smem = (size_t)C::GPB * group_doubles * sizeof(double) + (size_t)C::GPB * C::Q * sizeof(uint64_t);
-   static size_t configured = 0;
-   static int blocks_per_sm = 0;
-   if (configured != smem)
-   {
-      CDM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CDM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, C::THREADS, smem));
-      if (blocks_per_sm < 1) { return cdm_fail(ctx, CDM_ECUDA, "k_apply3d_group does not fit on an SM"); }
-      configured = smem;
-   }
+   int blocks_per_sm = 0;
+   { const int rc = cdm_kernel_cfg(ctx, (const void *)kern, C::THREADS, smem, "k_apply3d_group", &blocks_per_sm); if (rc) { return rc; } }
    // element range [e0, e1): the kernel sees a shifted view of the per-element arrays
    const int64_t e0 = op->range_on ? op->e_begin : 0, e1 = op->range_on ? op->e_end : sp->ne;
    const int64_t n = e1 - e0;
@@ -360,6 +353,7 @@ int launch_group(cdm_op *op, const GroupTables &tb, const int32_t *gmap, const d
    int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
    const int64_t need = (n + C::GPB - 1) / C::GPB;
    if (grid > need) { grid = need; }
+   if (op->grid_cap > 0 && grid > op->grid_cap) { grid = op->grid_cap; }
    if (ctx->time_main) { cudaEventRecord(ctx->evk0, ctx->stream); }
    kern<<<(unsigned)grid, C::THREADS, smem, ctx->stream>>>(tb, n, gmap + e0 * C::ND, xL,
                                                            op->D_dev + e0 * C::Q * (int64_t)op->slab, op->slab,
@@ -412,7 +406,7 @@ int cdm_k_apply_group(cdm_op *op, const int32_t *gmap, const double *xL, double 
    else
    {
       if (!op->yE_dev) { CDM_CUDA(ctx, cudaMalloc(&op->yE_dev, sizeof(double) * (size_t)sp->ne * sp->nd)); }
-      out = op->yE_dev;
+      out = op->e_out ? op->e_out : op->yE_dev;
    }
    int rc = 1;
    switch (sp->p)
@@ -425,7 +419,7 @@ int cdm_k_apply_group(cdm_op *op, const int32_t *gmap, const double *xL, double 
       case 6: rc = dispatch_order<6>(op, tb, gmap, xL, out, atomic); break;
    }
    if (rc) { return rc; }
-   if (!atomic)
+   if (!atomic && !op->e_out)
    {
       const unsigned nb = (unsigned)((sp->ndof + 255) / 256);
       k_restrict_transpose_g<<<nb, 256, 0, ctx->stream>>>(sp->ndof, sp->offsets_dev, sp->indices_dev, op->yE_dev, yL);

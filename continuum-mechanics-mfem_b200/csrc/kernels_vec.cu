@@ -41,7 +41,7 @@ __global__ void k_pmult(int64_t n, const double *__restrict__ d, const double *_
 __global__ void k_recip(int64_t n, const double *__restrict__ d, double *__restrict__ r)
 {
    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-   if (i < n) { r[i] = 1.0 / d[i]; }
+   if (i < n) { const double v = d[i]; r[i] = (v != 0.0) ? 1.0 / v : 1.0; }      // PCJacobi: zero diagonal -> 1
 }
 __global__ void k_scale(int64_t n, double a, const double *__restrict__ w, double *__restrict__ v)
 {

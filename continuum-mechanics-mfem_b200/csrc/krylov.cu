@@ -34,8 +34,10 @@ int ensure_dinv(cdm_op *op)
    cdm_ctx *ctx = op->sp->ctx;
    if (op->dinv_dev) { return CDM_OK; }
    CDM_CUDA(ctx, cudaMalloc(&op->dinv_dev, sizeof(double) * (size_t)op->sp->ndof));
-   int rc = cdm_operator_diag(op, op->dinv_dev); if (rc) { return rc; }
-   return cdm_k_recip(ctx, op->sp->ntrue, op->dinv_dev, op->dinv_dev);
+   int rc = cdm_operator_diag(op, op->dinv_dev);
+   if (!rc) { rc = cdm_k_recip(ctx, op->sp->ntrue, op->dinv_dev, op->dinv_dev); }     // a zero diagonal entry -> 1 (PCJacobi)
+   if (rc) { cudaFree(op->dinv_dev); op->dinv_dev = nullptr; }                          // never keep a half-built diagonal
+   return rc;
 }
 
 // fetch k doubles of the device result area to the host (one sync)
@@ -56,6 +58,7 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
    if (!op || !b || !x || !o || !res) { return CDM_EINVAL; }
    cdm_space *sp = op->sp;
    cdm_ctx *c = sp->ctx;
+   CDM_REQUIRE_GPU(c);
    const int64_t n = sp->ntrue;
    const int64_t ld = (sp->ndof + 31) & ~(int64_t)31;     // room for the ghost tail
    const int m = o->restart > 0 ? o->restart : (o->variant == CDM_GMRES_PETSC ? 30 : 50);
@@ -95,7 +98,18 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
       rnorm = beta;
       if (first)
       {
-         ttol = std::fmax(o->rtol * beta, o->atol);
+         // KSPConvergedDefault: with a non-zero initial guess PETSc scales rtol by ||M^{-1} b||, the preconditioned
+         // norm of the right-hand side; mfem::GMRESSolver always uses the initial residual
+         double ref = beta;
+         if (!o->zero_guess && o->variant == CDM_GMRES_PETSC)
+         {
+            if (dinv) { RC(cdm_k_pmult(c, n, dinv, b, w)); }
+            RC(cdm_k_mdot_dev(c, n, 1, dinv ? w : b, dinv ? w : b, ld, h_dev));
+            RC(cdm_allreduce_sum(c, h_dev, 1));
+            double nb2; RC(fetch(c, h_dev, 1, &nb2));
+            ref = std::sqrt(nb2);
+         }
+         ttol = std::fmax(o->rtol * ref, o->atol);
          if (hist) { hist[hl] = beta; } hl++;
          first = false;
       }
@@ -180,6 +194,7 @@ extern "C" int cdm_cg(cdm_op *op, const double *b, double *x, const cdm_krylov_o
    if (!op || !b || !x || !o || !res) { return CDM_EINVAL; }
    cdm_space *sp = op->sp;
    cdm_ctx *c = sp->ctx;
+   CDM_REQUIRE_GPU(c);
    const int64_t n = sp->ntrue;
    const int64_t ld = (sp->ndof + 31) & ~(int64_t)31;
    RC(ensure_ws(op, 4 * ld));

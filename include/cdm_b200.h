@@ -190,8 +190,34 @@ int  cdm_operator_csr_get(const cdm_op *op, int64_t *rowptr, int32_t *colind, do
    "tail" (1: caller vectors have the local size, see cdm_operator_local_size),
    "overlap" (multi-GPU: 0 serial halo exchange, 1 overlapped with interior elements up to 3 neighbours, 2 always),
    "halo" (multi-GPU: 0 NCCL send/recv, 1 peer-memory stores + flags over NVLink; setting it to 1 is a
-   collective call: every rank must make it), "host_pipeline" (0/1, or a chunk count for cdm_operator_mult_host) */
+   collective call: every rank must make it), "host_pipeline" (0/1, or a chunk count for cdm_operator_mult_host),
+   "grid_cap" (> 0: upper bound on the persistent grids, so that a small test mesh runs many elements per warp) */
 int  cdm_operator_set_option(cdm_op *op, const char *name, int value);
+/* ------------------- integrator-level (E-vector) and prolongation entry points */
+/* MFEM: BilinearFormIntegrator::AddMultPA(const Vector &x_E, Vector &y_E) -- what a ParBilinearForm under
+   AssemblyLevel::PARTIAL dispatches to after its own ElementRestriction (a.Assemble(),
+   linear_convection_diffusion_2D.cpp:339; the Mult of :368 / linear_convection_diffusion_1D.cpp:544):
+     y_E += B^T D B x_E   for all integrators of `op` at once.
+   E-vectors are MFEM's: [ne][nd], dof fastest (lexicographic in the element), device pointers. */
+int  cdm_integrator_add_mult_pa(cdm_op *op, const double *xE_dev, double *yE_dev);
+/* MFEM: BilinearFormIntegrator::AssembleDiagonalPA(Vector &diag_E): diag_E += diag(B^T D B), element by element */
+int  cdm_integrator_assemble_diagonal_pa(cdm_op *op, double *diagE_dev);
+/* MFEM: ElementRestriction::Mult / MultTranspose (fem/restriction.cpp) with the space's index arrays:
+     xE[i] = xL[gather_map[i]]  ;  yL[g] = sum_{j in [offsets[g], offsets[g+1])} yE[indices[j]]   (fixed order) */
+int  cdm_restriction_mult(cdm_space *space, const double *xL_dev, double *xE_dev);
+int  cdm_restriction_mult_transpose(cdm_space *space, const double *yE_dev, double *yL_dev);
+/* MFEM: a.RecoverFEMSolution(X, b, u) (linear_convection_diffusion_2D.cpp:377; per step and block at
+   linear_convection_diffusion_1D.cpp:569-572) = u_L = P X: the true dofs are the first
+   cdm_space_true_size entries of the local vector, the ghost entries are fetched from their owners.
+   uL_dev has cdm_space_local_size entries; xT_dev may alias it.  Collective over the ranks. */
+int  cdm_prolongate(cdm_space *space, const double *xT_dev, double *uL_dev);
+/* MFEM: ParLinearForm::ParallelAssemble (linear_convection_diffusion_2D.cpp:343) = b_T = P^T b_L: partial sums
+   held in ghost entries are added into their owners (fixed peer order).  bL_dev is updated in place; bT_dev
+   (may be NULL or alias bL_dev) receives the first cdm_space_true_size entries.  Collective. */
+int  cdm_prolongate_transpose(cdm_space *space, double *bL_dev, double *bT_dev);
+int64_t cdm_space_local_size(const cdm_space *space);
+int64_t cdm_space_true_size(const cdm_space *space);
+
 /* measurement hook: run the element kernel of the apply `reps` times on this rank's
    L-vectors and return its mean device time (CUDA events recorded on the context's
    stream directly around each launch; no halo, no essential fix-up) */

@@ -124,7 +124,11 @@ void orc_gmres(const orc_op *A, const double *dinv, const double *b, double *x,
       rnorm = beta;
       if (first)
       {
-         ttol = fmax(o->rtol * beta, o->atol);
+         /* KSPConvergedDefault: with a non-zero initial guess PETSc scales rtol by the preconditioned norm
+            of the right-hand side, ||M^{-1} b||; mfem::GMRESSolver always uses the initial residual */
+         double ref = beta;
+         if (!o->zero_guess && o->variant == 0) { pc(n, dinv, b, w); ref = sqrt(dot(n, w, w)); }
+         ttol = fmax(o->rtol * ref, o->atol);
          hist[hl++] = beta;
          first = 0;
       }
