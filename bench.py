@@ -76,38 +76,48 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference(order, n_csr, n_pa, steps, warmup, budget_s=25.0):
-    """The reference's CPU path on this box's host cores, from the oracle port:
-    (i) assembled CSR SpMV = what the app executes (full assembly -> ParCSR -> PETSc MatMult),
-    (ii) CPU sum-factorised PA apply.  Bounded sample of the same operator."""
+def cpu_reference(order, n_pa, n_csr, steps, warmup, budget_s=25.0, want_csr=True):
+    """The reference's CPU path on this box's host cores, from the oracle port (MFEM / hypre / PETSc cannot be
+    built here): (i) CPU sum-factorised PA apply on the SAME n_pa^3 mesh as the GPU arm -- the faster of the two
+    CPU formulations, so ratios against it are conservative; (ii) the app's own algorithm, assembled-CSR SpMV
+    (full assembly -> ParCSR -> PETSc MatMult), at n_csr^3: the largest size whose assembly fits the time budget.
+    All host cores, whatever OMP_NUM_THREADS the launcher exported."""
     from oracle import pyoracle as orc
-    cores = orc.num_threads()
+    cores = orc.set_num_threads(os.cpu_count() or 1)
     out = {"cores": cores, "kind": "port"}
-    P = orc.Problem(3, order, n_csr, perturb=PERTURB, kappa=KAPPA, vel=VEL, mass=MASS)
-    x = np.sin(1.0 + 0.37 * np.arange(P.ndof))
-    A = P.csr()
-    for _ in range(max(1, warmup)):
-        A.spmv(x)
-    t0, k = time.perf_counter(), 0
-    while k < steps and (k < 3 or time.perf_counter() - t0 < budget_s / 2):
-        A.spmv(x)
-        k += 1
-    t_csr = (time.perf_counter() - t0) / k
-    out.update(csr_spmv_gdofs=P.ndof / t_csr / 1e9, csr_ms=t_csr * 1e3, csr_steps=k, csr_ndof=P.ndof)
     P2 = orc.Problem(3, order, n_pa, perturb=PERTURB, kappa=KAPPA, vel=VEL, mass=MASS)
     x2 = np.sin(1.0 + 0.37 * np.arange(P2.ndof))
     y2 = np.zeros(P2.ndof)
-    P2.pa_apply_fast(x2, y2)
+    for _ in range(max(1, min(warmup, 3))):
+        P2.pa_apply_fast(x2, y2)
     t0, k2 = time.perf_counter(), 0
-    while k2 < steps and (k2 < 3 or time.perf_counter() - t0 < budget_s / 2):
+    while k2 < steps and (k2 < 3 or time.perf_counter() - t0 < budget_s):
         P2.pa_apply_fast(x2, y2)          # fused, order-specialised CPU partial-assembly apply
         k2 += 1
     t_pa = (time.perf_counter() - t0) / k2
-    out.update(pa_apply_gdofs=P2.ndof / t_pa / 1e9, pa_ms=t_pa * 1e3, pa_steps=k2, pa_ndof=P2.ndof)
-    out["value"] = out["csr_spmv_gdofs"]
+    out.update(pa_apply_gdofs=P2.ndof / t_pa / 1e9, pa_ms=t_pa * 1e3, pa_steps=k2, pa_ndof=P2.ndof, pa_n=n_pa)
+    del P2, x2, y2
+    sample = f"CPU sum-factorised PA apply on the full {n_pa}^3 hex p={order} mesh ({out['pa_ndof']} dofs), {k2} applies"
+    if want_csr:
+        P = orc.Problem(3, order, n_csr, perturb=PERTURB, kappa=KAPPA, vel=VEL, mass=MASS)
+        x = np.sin(1.0 + 0.37 * np.arange(P.ndof))
+        ta = time.perf_counter()
+        A = P.csr()
+        t_asm = time.perf_counter() - ta
+        A.spmv(x)
+        t0, k = time.perf_counter(), 0
+        while k < steps and (k < 3 or time.perf_counter() - t0 < budget_s / 2):
+            A.spmv(x)
+            k += 1
+        t_csr = (time.perf_counter() - t0) / k
+        out.update(csr_spmv_gdofs=P.ndof / t_csr / 1e9, csr_ms=t_csr * 1e3, csr_steps=k, csr_ndof=P.ndof, csr_n=n_csr,
+                   csr_nnz=int(len(A.vals)), csr_assembly_s=t_asm)
+        sample += (f"; assembled CSR SpMV (the app's own algorithm) on {n_csr}^3 ({P.ndof} dofs, {len(A.vals)} nnz, "
+                   f"{len(A.vals) * 12 / 1e9:.1f} GB, assembly {t_asm:.0f} s), {k} applies")
+    out["value"] = out["pa_apply_gdofs"]
+    out["ms_per_step"] = out["pa_ms"]
     out["unit"] = "GDOF/s"
-    out["sample"] = (f"assembled CSR SpMV on {n_csr}^3 hex p={order} ({P.ndof} dofs, {len(A.vals)} nnz), {k} applies; "
-                     f"CPU PA apply on {n_pa}^3 ({P2.ndof} dofs), {k2} applies; OpenMP over rows/elements")
+    out["sample"] = sample + f"; OpenMP over elements / rows on {cores} threads"
     return out
 
 
@@ -118,17 +128,22 @@ def parts_for(n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=66, help="elements per axis per GPU (66 -> 7 880 599 dofs, config 2)")
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--kernel", type=int, default=-1)
     ap.add_argument("--scatter", type=int, default=-1)
-    ap.add_argument("--overlap", type=int, default=1, help="multi-GPU: overlap the halo exchange with interior elements")
-    ap.add_argument("--halo", type=int, default=0, help="multi-GPU: 0 NCCL send/recv, 1 peer-memory stores + flags (experimental)")
+    ap.add_argument("--overlap", type=int, default=1, help="multi-GPU: overlap the shared-dof exchange with interior elements")
+    ap.add_argument("--halo", type=int, default=2, help="multi-GPU shared-dof protocol: 2 one symmetric peer-memory exchange per "
+                    "apply (default), 0 P / P^T over NCCL send/recv, 1 P / P^T over peer-memory stores")
+    ap.add_argument("--allreduce", type=int, default=1, help="multi-GPU Krylov scalars: 1 peer-memory all-reduce, 0 ncclAllReduce")
     ap.add_argument("--krylov-iters", type=int, default=60)
+    ap.add_argument("--config5-n", type=int, default=97, help="second block measured beside the headline one: BASELINE config 5 "
+                    "(97^3 elements = 24.9 M dofs per GPU); 0 disables it")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-csr-n", type=int, default=32)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -141,21 +156,24 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ref = cpu_reference(args.order, 24, 32, K, W)
-        t_ms = ref["csr_ms"]
+        # a step = one apply of the same operator on the same n^3 mesh (one GPU's block), CPU PA formulation; bounded
+        # by a time budget so that the arm ends within minutes whatever --steps says
+        ref = cpu_reference(args.order, args.n, args.cpu_csr_n, K, W, budget_s=30.0)
         line = {"impl": "reference", "metric": "operator_apply_gdofs", "value": ref["value"], "unit": "GDOF/s",
-                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": t_ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "reference_path": "assembled CSR SpMV (what the app executes), CPU oracle port; "
-                           "MFEM/hypre/PETSc cannot be built here"},
+                "n_gpus": args.gpus, "steps": ref["pa_steps"], "warmup": min(W, 3), "ms_per_step": ref["pa_ms"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload,
+                           "reference_path": f"CPU oracle port (MFEM/hypre/PETSc cannot be built here) on {ref['cores']} host threads of "
+                                             f"rank 0: `value` = sum-factorised PA apply on the same {args.n}^3 mesh (one GPU's block; the "
+                                             f"faster CPU formulation); the app's own assembled-CSR SpMV is in cpu_baseline.csr_* at "
+                                             f"{ref.get('csr_n')}^3, the largest size whose assembly fits the time budget"},
                 "cpu_baseline": ref,
                 "e2e": {"value": ref["value"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
     if world > 1:
-        # the halo messages (<= 0.7 MB) and the Krylov all-reduces (<= 31 doubles) are latency-bound:
-        # NCCL's LL protocol is 5.6 % faster per Krylov iteration at 8 GPUs (profiles/r01_scaling.md)
+        # the NCCL messages that remain (setup, optional fall-back paths) are latency-bound: LL protocol
         os.environ.setdefault("NCCL_PROTO", "LL")
     # stdout carries exactly one JSON line: anything a library writes to fd 1 (NCCL prints its version
     # banner there on some boxes) is sent to stderr, and the result goes to a private copy of the real stdout
@@ -178,29 +196,14 @@ def main():
         dist.broadcast(uid, 0)
         ctx.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
     parts = parts_for(world)
-    gmesh = cdm.Mesh.cartesian(ctx, 3, [args.n * parts[0], args.n * parts[1], args.n * parts[2]], perturb=PERTURB)
-    mesh = gmesh.partition_box(parts, rank) if world > 1 else gmesh
-    sp = cdm.H1Space(mesh, args.order)
-    ess = sp.essential_dofs(np.ones(6, np.int32))
-    op = cdm.ConvectionDiffusionOperator(sp, kappa=KAPPA, vel=VEL, mass=MASS, ess_dofs=ess)
-    if args.kernel >= 0:
-        op.set_option("kernel", args.kernel)
-    if args.scatter >= 0:
-        op.set_option("scatter", args.scatter)
-    op.set_option("overlap", args.overlap)
-    if world > 1 and args.halo:
-        op.set_option("halo", args.halo)
-    op.set_option("tail", 1)       # x, y are allocated with the local (L-vector) size: no T<->L copies
-    n_true = sp.ntrue
-    tot = torch.tensor([n_true, sp.ne], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tot)
-    n_global, ne_global = int(tot[0]), int(tot[1])
-    ld = sp.ndof
-    x = torch.sin(1.0 + 0.37 * torch.arange(ld, dtype=torch.float64, device="cuda"))
-    y = torch.zeros(ld, dtype=torch.float64, device="cuda")
-    torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(ctx.stream)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
 
     def barrier():
         ctx.sync()
@@ -209,48 +212,111 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident apply: K steps, CUDA events on the launching stream, max over ranks
-    for _ in range(W):
-        op.Mult(x, y)
-    barrier()
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def build(n):
+        gmesh = cdm.Mesh.cartesian(ctx, 3, [n * parts[0], n * parts[1], n * parts[2]], perturb=PERTURB)
+        mesh = gmesh.partition_box(parts, rank) if world > 1 else gmesh
+        del gmesh
+        sp = cdm.H1Space(mesh, args.order)
+        ess = sp.essential_dofs(np.ones(6, np.int32))
+        op = cdm.ConvectionDiffusionOperator(sp, kappa=KAPPA, vel=VEL, mass=MASS, ess_dofs=ess)
+        if args.kernel >= 0:
+            op.set_option("kernel", args.kernel)
+        if args.scatter >= 0:
+            op.set_option("scatter", args.scatter)
+        op.set_option("overlap", args.overlap)
+        if world > 1:
+            op.set_option("halo", args.halo)
+            op.set_option("allreduce", args.allreduce)
+        op.set_option("tail", 1)       # x, y are allocated with the local (L-vector) size: no T<->L copies
+        tot = torch.tensor([sp.ntrue, sp.ne], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+        x = torch.sin(1.0 + 0.37 * torch.arange(sp.ndof, dtype=torch.float64, device="cuda"))
+        y = torch.zeros(sp.ndof, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        if world > 1:
+            sp.prolongate(x, x)        # x ghost-consistent, as every vector inside the Krylov loop is
+            ctx.sync()
+        return mesh, sp, op, x, y, int(tot[0]), int(tot[1])
+
+    def time_applies(op, x, y, k, w):
+        """k constrained applies, CUDA events on the launching stream, barrier + sync on both sides, max over ranks"""
+        for _ in range(w):
+            op.Mult(x, y)
+        barrier()
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            op.Mult(x, y)
+        e1.record(stream)
+        barrier()
+        return allmax(e0.elapsed_time(e1)) / k, ctx.launches - l0
+
+    def krylov_iter(sp, op, n_true, ld):
+        b = torch.sin(0.5 + 0.11 * torch.arange(n_true, dtype=torch.float64, device="cuda"))
+        xs = torch.zeros(ld, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        s = cdm.GMRESSolver(cdm.GMRES_PETSC, 0, args.krylov_iters, 0.0, 0.0, jacobi=True)
+        s.SetOperator(op)
+        s.Mult(b, xs)            # warm-up (allocates the basis)
+        barrier()
+        l1 = ctx.launches
+        s.Mult(b, xs)
+        barrier()
+        its = max(1, s.GetNumIterations())
+        return {"iters": s.GetNumIterations(), "ms_per_iter": allmax(s.res.seconds) * 1e3 / its,
+                "launches": ctx.launches - l1, "config": "GMRES(30) classical Gram-Schmidt, left Jacobi, x0=0; lazily normalised "
+                "basis, host scalars pipelined behind the next apply"}
+
+    # ------------------------------------------------------------------ headline block (N=1: BASELINE config 2)
+    mesh, sp, op, x, y, n_global, ne_global = build(args.n)
+    n_true, ld = sp.ntrue, sp.ndof
+    if world > 1:
+        op.set_option("ghost_in", 1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(K):
-        op.Mult(x, y)
-    e1.record(stream)
-    barrier()
-    launches = ctx.launches - l0
-    t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_step = float(t_ms[0]) / K
+    ms_step, launches = time_applies(op, x, y, K, W)
     gdofs = n_global / (ms_step * 1e-3) / 1e9
+    halo_used = op.get_option("halo") if world > 1 else None
+    # a longer run of the same step (>= 400 applies ~ 0.2 s) so that the 100 ms clock samples fall inside timed work
+    ms_long, _ = time_applies(op, x, y, max(400, K), 0)
+    # the same apply as a stand-alone Operator::Mult on true-dof vectors: P on x first (its ghost entries are unknown)
+    ms_tt = None
+    if world > 1:
+        op.set_option("ghost_in", 0)
+        ms_tt, _ = time_applies(op, x, y, max(50, K // 4), 3)
+        op.set_option("ghost_in", 1)
+    # deterministic scatter (E-vector + gather transpose = MFEM's MultTranspose) beside the default red.add
+    scat_default = op.get_option("scatter")
+    op.set_option("scatter", 0)
+    ms_det, _ = time_applies(op, x, y, max(50, K // 4), 3)
+    op.set_option("scatter", scat_default)
 
     # ---- kernel-only time of the dominant kernel (roofline)
-    k_ms = op.time_kernel(x, y, reps=min(K, 20), constrained=True)
+    k_ms = op.time_kernel(x, y, reps=20, constrained=True)
     bytes_launch = algorithmic_bytes(sp.ndof, sp.ne, args.order)
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            peaks = json.load(fh)
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bytes_launch / (k_ms * 1e-3) / 1e9
-    traffic = None                     # DRAM bytes per launch from the committed ncu --set full capture (same config only)
+    traffic = None       # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             tj = json.load(fh)
-        if args.n == 66 and args.order == 3 and world == 1:
-            traffic = tj["dram_bytes_per_launch"]
+        key = f"n{args.n}_p{args.order}_k{op.get_option('kernel')}"
+        if world == 1 and key in tj.get("per_config", {}):
+            traffic = tj["per_config"][key]["dram_bytes_per_launch"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": bytes_launch,
+                "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel on this "
+                "configuration)" if traffic else None, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": bytes_launch,
+                "whole_step_frac": bytes_launch / (ms_step * 1e-3) / 1e9 / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"}
 
     # ---- setup kernels (a.Assemble(): quadrature data; Jacobi diagonal), device time of one call each
@@ -273,42 +339,43 @@ def main():
     yh = torch.empty(n_true, dtype=torch.float64).pin_memory()
     xh.copy_(x[:n_true].cpu())
     xh_np, yh_np = xh.numpy(), yh.numpy()
-    K2 = max(3, min(K, 10))
-    for _ in range(2):
+    K2 = max(5, min(K, 20))
+    for _ in range(3):
         op.mult_host(xh_np, yh_np)
     barrier()
     t0 = time.perf_counter()
     for _ in range(K2):
         op.mult_host(xh_np, yh_np)
     barrier()
-    t_e2e = torch.tensor([(time.perf_counter() - t0) / K2], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e = {"value": n_global / float(t_e2e[0]) / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_true,
-           "d2h_bytes_per_step": 8 * n_true, "ms_per_step": float(t_e2e[0]) * 1e3, "steps": K2}
+    t_e2e = allmax((time.perf_counter() - t0) / K2)
+    e2e = {"value": n_global / t_e2e / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_true,
+           "d2h_bytes_per_step": 8 * n_true, "ms_per_step": t_e2e * 1e3, "steps": K2,
+           "note": "cdm_operator_mult_host: pinned host x up, apply, y down inside the timed region, per rank"}
 
     # ---- Krylov iteration time: GMRES(30)/CGS + Jacobi (Input/petsc.opts:2-6), fixed iteration count
-    b = torch.sin(0.5 + 0.11 * torch.arange(n_true, dtype=torch.float64, device="cuda"))
-    xs = torch.zeros(ld, dtype=torch.float64, device="cuda")
-    torch.cuda.synchronize()
-    s = cdm.GMRESSolver(cdm.GMRES_PETSC, 0, args.krylov_iters, 0.0, 0.0, jacobi=True)
-    s.SetOperator(op)
-    s.Mult(b, xs)            # warm-up (allocates the basis)
-    barrier()
-    l1 = ctx.launches
-    s.Mult(b, xs)
-    barrier()
-    kry_launches = ctx.launches - l1
-    t_k = torch.tensor([s.res.seconds], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_k, op=dist.ReduceOp.MAX)
-    krylov = {"iters": s.GetNumIterations(), "ms_per_iter": float(t_k[0]) * 1e3 / max(1, s.GetNumIterations()),
-              "launches": kry_launches, "config": "GMRES(30) classical Gram-Schmidt, left Jacobi, x0=0"}
+    krylov = krylov_iter(sp, op, n_true, ld)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ------------------------------------------------------------------ second block: BASELINE config 5 (97^3 per GPU)
+    config5 = None
+    if args.config5_n > 0 and args.config5_n != args.n:
+        del op, sp, mesh, x, y, dvec
+        torch.cuda.empty_cache()
+        mesh, sp, op, x, y, ng5, ne5 = build(args.config5_n)
+        if world > 1:
+            op.set_option("ghost_in", 1)
+        ms5, _ = time_applies(op, x, y, max(50, K // 2), 5)
+        k5 = op.time_kernel(x, y, reps=10, constrained=True)
+        b5 = algorithmic_bytes(sp.ndof, sp.ne, args.order)
+        kr5 = krylov_iter(sp, op, sp.ntrue, sp.ndof)
+        config5 = {"workload": f"{args.config5_n}^3 elements per GPU (BASELINE config 5: weak scaling at ~25 M dofs per GPU)",
+                   "global_dofs": ng5, "global_elements": ne5, "value": ng5 / (ms5 * 1e-3) / 1e9, "unit": "GDOF/s",
+                   "ms_per_step": ms5, "kernel_ms": k5, "roofline_frac": b5 / (k5 * 1e-3) / 1e9 / peak,
+                   "krylov_ms_per_iter": kr5["ms_per_iter"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference(args.order, 24, 32, 50, 2)
+        cpu = cpu_reference(args.order, args.n, args.cpu_csr_n, 40, 2, budget_s=10.0)
 
     if rank == 0:
         line = {"metric": "operator_apply_gdofs", "value": gdofs, "unit": "GDOF/s", "n_gpus": world, "steps": K,
@@ -316,21 +383,25 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload, "global_dofs": n_global, "global_elements": ne_global,
                            "partition": "x".join(map(str, parts)),
-                           "nccl_proto": os.environ.get("NCCL_PROTO") if world > 1 else None,
-                           "halo": ("peer memory" if args.halo else "nccl send/recv") if world > 1 else None, "l2_policy": "inputs larger than L2 "
-                           f"({bytes_launch / 1e9:.2f} GB streamed per apply per GPU vs 126 MB L2)",
-                           "scatter": "fp64 red.add" if op_scatter(op, args) == 1 else "E-vector + gather transpose"},
+                           "shared_dof_protocol": (None if world == 1 else
+                                                   {2: "one symmetric peer-memory exchange per apply (NVLink stores + flags), x ghost-consistent "
+                                                       "on entry as inside the Krylov loop", 1: "P / P^T over peer-memory stores",
+                                                    0: "P / P^T over NCCL send/recv"}[halo_used]),
+                           "allreduce": (None if world == 1 else ("peer memory" if op.get_option("allreduce") else "ncclAllReduce")),
+                           "l2_policy": f"inputs larger than L2 ({bytes_launch / 1e9:.2f} GB streamed per apply per GPU vs 126 MB L2)",
+                           "scatter": "fp64 red.add" if scat_default == 1 else "E-vector + gather transpose"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-                "krylov": krylov, "setup": setup, "clocks": clocks}
+                "sustained": {"applies": max(400, K), "ms_per_step": ms_long, "value": n_global / (ms_long * 1e-3) / 1e9},
+                "deterministic_scatter": {"ms_per_step": ms_det, "value": n_global / (ms_det * 1e-3) / 1e9,
+                                          "note": "option scatter=0: E-vector stores + ElementRestriction::MultTranspose gather, bit-reproducible"},
+                "true_dof_apply": (None if ms_tt is None else {"ms_per_step": ms_tt, "value": n_global / (ms_tt * 1e-3) / 1e9,
+                                                               "note": "stand-alone Operator::Mult on true-dof vectors: P exchange of x + apply"}),
+                "krylov": krylov, "setup": setup, "config5": config5, "clocks": clocks}
         print(json.dumps(line), file=result_out)
         result_out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
-
-
-def op_scatter(op, args):
-    return 1 if args.scatter < 0 else args.scatter
 
 
 if __name__ == "__main__":

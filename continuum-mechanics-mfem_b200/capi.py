@@ -90,6 +90,9 @@ SIGNATURES = {
     "cdm_space_halo_peers": (_ci, [_vp, C.POINTER(_ci)]),
     "cdm_space_halo_peer": (_ci, [_vp, _ci, C.POINTER(_ci), C.POINTER(_i64), C.POINTER(_i64), _vp, _vp]),
     "cdm_space_dof_global": (_ci, [_vp, _vp]),
+    "cdm_space_sym_peers": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_i64), C.POINTER(_i64)]),
+    "cdm_space_sym_peer": (_ci, [_vp, _ci, C.POINTER(_ci), C.POINTER(_i64), C.POINTER(_i64), _vp]),
+    "cdm_space_sym_sum_plan": (_ci, [_vp, _vp, _vp, _vp]),
     "cdm_space_elem_perm": (_ci, [_vp, _vp, C.POINTER(_i64)]),
     "cdm_space_destroy": (_ci, [_vp]),
     "cdm_operator_create": (_ci, [_vp, C.POINTER(Coeff), C.POINTER(Coeff), _cd, C.POINTER(Coeff), _vp, _i64, _pp]),
@@ -107,6 +110,7 @@ SIGNATURES = {
     "cdm_operator_csr_sizes": (_ci, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "cdm_operator_csr_get": (_ci, [_vp, _vp, _vp, _vp]),
     "cdm_operator_set_option": (_ci, [_vp, C.c_char_p, _ci]),
+    "cdm_operator_get_option": (_ci, [_vp, C.c_char_p, C.POINTER(_ci)]),
     "cdm_integrator_add_mult_pa": (_ci, [_vp, _vp, _vp]),
     "cdm_integrator_assemble_diagonal_pa": (_ci, [_vp, _vp]),
     "cdm_restriction_mult": (_ci, [_vp, _vp, _vp]),
@@ -346,6 +350,21 @@ class H1Space:
             out.append((r.value, own, ghost))
         return out
 
+    def sym_plan(self):
+        """symmetric exchange plan: ([(peer rank, offset, shared dof ids)], sum_dof, sum_off, sum_src)"""
+        npe, ns, nc = C.c_int(), C.c_int64(), C.c_int64()
+        lib().cdm_space_sym_peers(self.h, C.byref(npe), C.byref(ns), C.byref(nc))
+        peers = []
+        for i in range(npe.value):
+            r, n, off = C.c_int(), C.c_int64(), C.c_int64()
+            lib().cdm_space_sym_peer(self.h, i, C.byref(r), C.byref(n), C.byref(off), None)
+            idx = np.zeros(n.value, np.int32)
+            lib().cdm_space_sym_peer(self.h, i, C.byref(r), C.byref(n), C.byref(off), _ptr(idx))
+            peers.append((r.value, off.value, idx))
+        dof, off, src = np.zeros(ns.value, np.int32), np.zeros(ns.value + 1, np.int32), np.zeros(nc.value, np.int32)
+        lib().cdm_space_sym_sum_plan(self.h, _ptr(dof), _ptr(off), _ptr(src))
+        return peers, dof, off, src
+
     def elem_perm(self):
         """(perm, n_boundary): perm[e] = mesh index of the space's e-th element"""
         perm = np.zeros(self.ne, np.int64)
@@ -473,6 +492,11 @@ class ConvectionDiffusionOperator:
 
     def set_option(self, name, value):
         self.ctx.check(lib().cdm_operator_set_option(self.h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_int()
+        self.ctx.check(lib().cdm_operator_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
 
     def assemble_csr(self):
         """full assembly on the device (the reference's a.Assemble()); returns (rowptr, colind, vals) host copies"""

@@ -86,6 +86,7 @@ int cdm_finalize(cdm_ctx *c)
       if (c->p2p_err_host) { cudaFreeHost(c->p2p_err_host); }
       if (c->ev0) { cudaEventDestroy(c->ev0); }
       if (c->ev1) { cudaEventDestroy(c->ev1); }
+      if (c->ev_kry) { cudaEventDestroy(c->ev_kry); }
       if (c->evk0) { cudaEventDestroy(c->evk0); }
       if (c->evk1) { cudaEventDestroy(c->evk1); }
       // the NCCL communicators are left to process teardown: ncclCommDestroy from an arbitrary point of the
@@ -164,6 +165,11 @@ static int space_finish(cdm_ctx *ctx, const cdm_mesh *mesh, cdm_space *sp)
          const size_t nb = (std::max(hp.own_all.size(), hp.ghost_all.size()) + 1) * sizeof(double);
          CDM_CUDA(ctx, cudaMalloc(&hp.send_dev, nb));
          CDM_CUDA(ctx, cudaMalloc(&hp.recv_dev, nb));
+         cdm_sym_plan &sy = sp->sym;
+         if ((rc = upload(ctx, sy.all, &sy.all_dev))) { return rc; }
+         if ((rc = upload(ctx, sy.sh_dof, &sy.sh_dof_dev))) { return rc; }
+         if ((rc = upload(ctx, sy.sh_off, &sy.sh_off_dev))) { return rc; }
+         if ((rc = upload(ctx, sy.sh_src, &sy.sh_src_dev))) { return rc; }
       }
       CDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
    }
@@ -215,6 +221,8 @@ static void build_partition(const cdm_mesh *m, cdm_space *sp)
    std::vector<int> owner(sp->ndof, me);
    struct Share { int64_t key; int32_t dof; int peer; bool mine; };
    std::vector<Share> shares;
+   struct SymShare { int64_t key; int32_t dof; int peer; };
+   std::vector<SymShare> sym;                 // (dof, every other rank of its sharing group)
    for (int64_t g = 0; g < sp->ndof; g++)
    {
       const int64_t k = key[g];
@@ -242,6 +250,7 @@ static void build_partition(const cdm_mesh *m, cdm_space *sp)
             }
       owner[g] = own;
       if (cnt == 1) { continue; }
+      for (int i = 0; i < cnt; i++) if (ranks[i] != me) { sym.push_back({k, (int32_t)g, ranks[i]}); }
       if (own == me) { for (int i = 0; i < cnt; i++) if (ranks[i] != me) { shares.push_back({k, (int32_t)g, ranks[i], true}); } }
       else { shares.push_back({k, (int32_t)g, own, false}); }
    }
@@ -280,6 +289,43 @@ static void build_partition(const cdm_mesh *m, cdm_space *sp)
    {
       if (sp->peers.empty() || sp->peers.back().rank != s.peer) { sp->peers.emplace_back(); sp->peers.back().rank = s.peer; }
       (s.mine ? sp->peers.back().own_idx : sp->peers.back().ghost_idx).push_back(newid[s.dof]);
+   }
+   // symmetric plan: per peer the dofs shared with it in key order (both sides of a pair build the same list);
+   // per shared dof the contributions in ascending rank order, the own value at this rank's position
+   std::sort(sym.begin(), sym.end(), [](const SymShare &a, const SymShare &b)
+   { return a.peer != b.peer ? a.peer < b.peer : a.key < b.key; });
+   cdm_sym_plan &sy = sp->sym;
+   for (const SymShare &s : sym)
+   {
+      if (sy.peers.empty() || sy.peers.back().rank != s.peer)
+      { sy.peers.emplace_back(); sy.peers.back().rank = s.peer; sy.peers.back().off = (int64_t)sy.all.size(); }
+      sy.peers.back().idx.push_back(newid[s.dof]);
+      sy.all.push_back(newid[s.dof]);
+   }
+   {
+      // entries of `all` grouped by dof; within a dof they are already in ascending peer rank (peer-major order)
+      std::vector<int32_t> order(sy.all.size());
+      for (size_t i = 0; i < order.size(); i++) { order[i] = (int32_t)i; }
+      std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return sy.all[a] < sy.all[b]; });
+      std::vector<int> peer_of(sy.all.size());
+      for (const cdm_sym_peer &pr : sy.peers) for (size_t i = 0; i < pr.idx.size(); i++) { peer_of[pr.off + i] = pr.rank; }
+      size_t i = 0;
+      while (i < order.size())
+      {
+         size_t j = i;
+         while (j < order.size() && sy.all[order[j]] == sy.all[order[i]]) { j++; }
+         sy.sh_dof.push_back(sy.all[order[i]]);
+         sy.sh_off.push_back((int32_t)sy.sh_src.size());
+         bool own_done = false;
+         for (size_t k = i; k < j; k++)
+         {
+            if (!own_done && peer_of[order[k]] > me) { sy.sh_src.push_back(-1); own_done = true; }
+            sy.sh_src.push_back(order[k]);
+         }
+         if (!own_done) { sy.sh_src.push_back(-1); }
+         i = j;
+      }
+      sy.sh_off.push_back((int32_t)sy.sh_src.size());
    }
 }
 
@@ -444,6 +490,36 @@ int cdm_space_halo_peer(const cdm_space *sp, int i, int *rank, int64_t *n_own, i
    return CDM_OK;
 }
 
+int cdm_space_sym_peers(const cdm_space *sp, int *npeers, int64_t *n_shared, int64_t *n_contrib)
+{
+   if (!sp) { return CDM_EINVAL; }
+   if (npeers) { *npeers = (int)sp->sym.peers.size(); }
+   if (n_shared) { *n_shared = (int64_t)sp->sym.sh_dof.size(); }
+   if (n_contrib) { *n_contrib = (int64_t)sp->sym.sh_src.size(); }
+   return CDM_OK;
+}
+
+int cdm_space_sym_peer(const cdm_space *sp, int i, int *rank, int64_t *n, int64_t *offset, int32_t *idx)
+{
+   if (!sp || i < 0 || i >= (int)sp->sym.peers.size()) { return CDM_EINVAL; }
+   const cdm_sym_peer &pr = sp->sym.peers[i];
+   if (rank) { *rank = pr.rank; }
+   if (n) { *n = (int64_t)pr.idx.size(); }
+   if (offset) { *offset = pr.off; }
+   if (idx && !pr.idx.empty()) { std::memcpy(idx, pr.idx.data(), pr.idx.size() * sizeof(int32_t)); }
+   return CDM_OK;
+}
+
+int cdm_space_sym_sum_plan(const cdm_space *sp, int32_t *dof, int32_t *off, int32_t *src)
+{
+   if (!sp) { return CDM_EINVAL; }
+   const cdm_sym_plan &sy = sp->sym;
+   if (dof && !sy.sh_dof.empty()) { std::memcpy(dof, sy.sh_dof.data(), sy.sh_dof.size() * sizeof(int32_t)); }
+   if (off && !sy.sh_off.empty()) { std::memcpy(off, sy.sh_off.data(), sy.sh_off.size() * sizeof(int32_t)); }
+   if (src && !sy.sh_src.empty()) { std::memcpy(src, sy.sh_src.data(), sy.sh_src.size() * sizeof(int32_t)); }
+   return CDM_OK;
+}
+
 int cdm_space_elem_perm(const cdm_space *sp, int64_t *perm, int64_t *n_boundary)
 {
    if (!sp) { return CDM_EINVAL; }
@@ -468,6 +544,8 @@ int cdm_space_destroy(cdm_space *sp)
       cudaFree(sp->gather_dev); cudaFree(sp->offsets_dev); cudaFree(sp->indices_dev); cudaFree(sp->elem_x_dev);
       cudaFree(sp->work_dev); cudaFree(sp->elem_part_dev); cudaFree(sp->iota_dev);
       cdm_halo_p2p_destroy(sp);
+      cdm_halo_sym_destroy(sp);
+      cudaFree(sp->sym.all_dev); cudaFree(sp->sym.sh_dof_dev); cudaFree(sp->sym.sh_off_dev); cudaFree(sp->sym.sh_src_dev);
       cdm_halo_plan &hp = sp->halo;
       cudaFree(hp.own_all_dev); cudaFree(hp.ghost_all_dev); cudaFree(hp.pt_dof_dev); cudaFree(hp.pt_off_dev);
       cudaFree(hp.pt_src_dev); cudaFree(hp.send_dev); cudaFree(hp.recv_dev);
@@ -526,6 +604,8 @@ int cdm_operator_create(cdm_space *sp, const cdm_coeff *kappa, const cdm_coeff *
          for (auto &g : gc) if (mark[g]) { g = -1 - g; }
          for (int64_t g = 0; g < sp->ntrue; g++) if (mark[g]) { op->ess_host.push_back((int32_t)g); }
          op->n_ess = (int64_t)op->ess_host.size();
+         for (int64_t g = sp->ntrue; g < sp->ndof; g++) if (mark[g]) { op->ess_host.push_back((int32_t)g); }
+         op->n_ess_all = (int64_t)op->ess_host.size();
          if ((rc = upload(ctx, gc, &op->gather_c_dev))) { break; }
          if ((rc = upload(ctx, op->ess_host, &op->ess_dev))) { break; }
          if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = CDM_ECUDA; break; }
@@ -588,15 +668,33 @@ int cdm_operator_set_option(cdm_op *op, const char *name, int value)
    if (!std::strcmp(name, "halo"))
    {
       // 1: exchange the shared dofs through peer memory (collective: every rank must make this call)
-      if (value != 0 && value != 1) { return CDM_EINVAL; }
+      // 2: symmetric exchange (its setup is collective and happens at the first apply)
+      if (value < 0 || value > 2) { return CDM_EINVAL; }
       if (value == 1) { const int rc = cdm_halo_p2p_setup(op->sp); if (rc) { return rc; } }
       op->halo_mode = value;
       return CDM_OK;
    }
    if (!std::strcmp(name, "tail")) { op->tail = value != 0; return CDM_OK; }
+   if (!std::strcmp(name, "ghost_in")) { op->ghost_in = value != 0; return CDM_OK; }
+   if (!std::strcmp(name, "allreduce")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->sp->ctx->allreduce_mode = value; return CDM_OK; }
    if (!std::strcmp(name, "grid_cap")) { if (value < 0) { return CDM_EINVAL; } op->grid_cap = value; return CDM_OK; }
    if (!std::strcmp(name, "host_pipeline")) { op->host_pipeline = value; return CDM_OK; }
    if (!std::strcmp(name, "overlap")) { if (value < 0 || value > 2) { return CDM_EINVAL; } op->overlap = value; return CDM_OK; }
+   return cdm_fail(op->sp->ctx, CDM_EINVAL, std::string("unknown option ") + name);
+}
+
+int cdm_operator_get_option(const cdm_op *op, const char *name, int *value)
+{
+   if (!op || !name || !value) { return CDM_EINVAL; }
+   if (!std::strcmp(name, "scatter")) { *value = op->scatter_mode; return CDM_OK; }
+   if (!std::strcmp(name, "kernel")) { *value = op->kernel_variant; return CDM_OK; }
+   if (!std::strcmp(name, "assembly")) { *value = op->assembly; return CDM_OK; }
+   if (!std::strcmp(name, "overlap")) { *value = op->overlap; return CDM_OK; }
+   if (!std::strcmp(name, "tail")) { *value = op->tail ? 1 : 0; return CDM_OK; }
+   if (!std::strcmp(name, "ghost_in")) { *value = op->ghost_in ? 1 : 0; return CDM_OK; }
+   // the protocol actually in use: 2 falls back to 0 when the peer-memory setup failed on any rank
+   if (!std::strcmp(name, "halo")) { *value = (op->halo_mode == 2 && op->sp->sym.ready == -1) ? 0 : op->halo_mode; return CDM_OK; }
+   if (!std::strcmp(name, "allreduce")) { *value = (op->sp->ctx->allreduce_mode && op->sp->ctx->red_sym) ? 1 : 0; return CDM_OK; }
    return cdm_fail(op->sp->ctx, CDM_EINVAL, std::string("unknown option ") + name);
 }
 
@@ -609,13 +707,63 @@ static int ensure_L(cdm_op *op)
 }
 
 // Apply on buffers that have room for the ghost tail (length >= ndof): used by the
-// Krylov drivers so that no T<->L copies are needed.  x's tail is overwritten.
-int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained)
+// Krylov drivers so that no T<->L copies are needed.
+//   x_ghost_valid : the ghost tail of x already holds the owners' values (a vector produced by a previous
+//                   apply in the symmetric mode, or by cdm_prolongate): the P exchange is skipped.
+//                   Otherwise x's tail is overwritten by P.
+// Multi-GPU protocols (option "halo"): 2 (default) symmetric peer-memory exchange: ONE exchange per apply, y comes
+// back consistent on its ghost tail as well; 0 / 1: P before and P^T after the element kernel, over NCCL
+// send/recv or peer-memory stores (y's ghost tail is then NOT valid).
+int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained, bool x_ghost_valid)
 {
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
    int rc;
    const bool par = ctx->nranks > 1 && !sp->peers.empty();
+   if (par && op->halo_mode == 2 && op->assembly == 0)
+   {
+      if (sp->sym.ready == 0 && (rc = cdm_halo_sym_setup(sp))) { return rc; }      // collective, first apply only
+      if (sp->sym.ready == 1)
+      {
+         if (!x_ghost_valid && (rc = cdm_halo_P(op, x_buf))) { return rc; }
+         cudaStream_t C = ctx->stream, H = ctx->stream_halo;
+         const int64_t nb = sp->n_bdr_elems;
+         // overlapped schedule: boundary elements (the only ones that touch shared dofs) first, then the exchange
+         // on the high-priority stream beside the interior elements:
+         //    C: memset y | boundary | interior ...................| wait H | y[ess] = x[ess]
+         //    H:                     | pack -> NVLink -> wait, add |
+         if (op->overlap != 0 && H && op->scatter_mode == 1 && cdm_k_range_capable(op) && nb > 0 && nb < sp->ne)
+         {
+            cudaEvent_t *ev = ctx->ev_h;
+            CDM_CUDA(ctx, cudaMemsetAsync(y_buf, 0, sizeof(double) * (size_t)sp->ndof, C));
+            op->range_on = true;
+            op->e_begin = 0; op->e_end = nb;
+            rc = cdm_k_apply(op, x_buf, y_buf, constrained);
+            if (!rc)
+            {
+               cudaEventRecord(ev[0], C);
+               cudaStreamWaitEvent(H, ev[0], 0);
+               rc = cdm_halo_sym_exchange(sp, y_buf, H);
+               cudaEventRecord(ev[1], H);
+            }
+            if (!rc)
+            {
+               op->e_begin = nb; op->e_end = sp->ne;
+               rc = cdm_k_apply(op, x_buf, y_buf, constrained);
+               cudaStreamWaitEvent(C, ev[1], 0);
+            }
+            op->range_on = false;
+            if (rc) { return rc; }
+         }
+         else
+         {
+            if ((rc = cdm_k_apply(op, x_buf, y_buf, constrained))) { return rc; }
+            if ((rc = cdm_halo_sym_exchange(sp, y_buf, C))) { return rc; }
+         }
+         if (constrained && op->n_ess_all > 0) { rc = cdm_k_copy_idx(ctx, op->n_ess_all, op->ess_dev, x_buf, y_buf); }
+         return rc;
+      }
+   }
    // the P / P^T pair of an apply may go through peer memory (option "halo" = 1); any other exchange uses NCCL
    struct P2PScope
    {
@@ -634,6 +782,7 @@ int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained)
    // with the persistent element kernel for SM slots), so by default only used up to 3 neighbours;
    // option "overlap" = 2 forces it.
    if (par && (op->overlap == 2 || (op->overlap == 1 && sp->peers.size() <= 3)) && ctx->stream_halo &&
+       (op->halo_mode == 1 || ctx->comm_halo) &&
        op->scatter_mode == 1 && cdm_k_range_capable(op) && sp->n_bdr_elems > 0 && sp->n_bdr_elems < sp->ne)
    {
       cudaStream_t C = ctx->stream, H = ctx->stream_halo;
@@ -680,14 +829,21 @@ int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained)
    return rc;
 }
 
+// does an apply on this operator leave y consistent on its ghost tail (so that y may be the next x without P)?
+bool cdm_apply_keeps_ghosts(const cdm_op *op)
+{
+   const cdm_space *sp = op->sp;
+   return sp->ctx->nranks > 1 && !sp->peers.empty() && op->halo_mode == 2 && op->assembly == 0 && sp->sym.ready == 1;
+}
+
 static int apply_T(cdm_op *op, const double *x, double *y, bool constrained)
 {
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
-   if (sp->ntrue == sp->ndof || op->tail) { return cdm_apply_tail(op, const_cast<double *>(x), y, constrained); }
+   if (sp->ntrue == sp->ndof || op->tail) { return cdm_apply_tail(op, const_cast<double *>(x), y, constrained, op->ghost_in != 0); }
    int rc = ensure_L(op); if (rc) { return rc; }
    CDM_CUDA(ctx, cudaMemcpyAsync(op->xL_dev, x, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyDeviceToDevice, ctx->stream));
-   if ((rc = cdm_apply_tail(op, op->xL_dev, op->yL_dev, constrained))) { return rc; }
+   if ((rc = cdm_apply_tail(op, op->xL_dev, op->yL_dev, constrained, false))) { return rc; }
    CDM_CUDA(ctx, cudaMemcpyAsync(y, op->yL_dev, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyDeviceToDevice, ctx->stream));
    return CDM_OK;
 }
@@ -877,7 +1033,7 @@ int cdm_operator_mult_host(cdm_op *op, const double *x_host, double *y_host, int
       return mult_host_pipelined(op, x_host, y_host, constrained != 0);
    }
    CDM_CUDA(ctx, cudaMemcpyAsync(op->xL_dev, x_host, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyHostToDevice, ctx->stream));
-   if ((rc = cdm_apply_tail(op, op->xL_dev, op->yL_dev, constrained != 0))) { return rc; }
+   if ((rc = cdm_apply_tail(op, op->xL_dev, op->yL_dev, constrained != 0, false))) { return rc; }
    CDM_CUDA(ctx, cudaMemcpyAsync(y_host, op->yL_dev, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyDeviceToHost, ctx->stream));
    CDM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
    return CDM_OK;
@@ -910,7 +1066,7 @@ int cdm_eliminate_rhs(cdm_op *op, const double *x_dev, double *b_dev)
    // w = 0 ; w[ess] = x[ess]
    CDM_CUDA(ctx, cudaMemsetAsync(op->xL_dev, 0, sizeof(double) * (size_t)sp->ndof, ctx->stream));
    if (op->n_ess > 0 && (rc = cdm_k_copy_idx(ctx, op->n_ess, op->ess_dev, x_dev, op->xL_dev))) { return rc; }
-   if ((rc = cdm_apply_tail(op, op->xL_dev, op->yL_dev, false))) { return rc; }
+   if ((rc = cdm_apply_tail(op, op->xL_dev, op->yL_dev, false, false))) { return rc; }
    if ((rc = cdm_k_axpy(ctx, sp->ntrue, -1.0, op->yL_dev, b_dev))) { return rc; }
    if (op->n_ess > 0) { rc = cdm_k_copy_idx(ctx, op->n_ess, op->ess_dev, x_dev, b_dev); }
    return rc;

@@ -28,6 +28,7 @@ struct cdm_ctx
    double *red_host = nullptr;      // pinned, RED_MAXK
    int sm_count = 148;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   cudaEvent_t ev_kry = nullptr;    // "scalars of this Krylov iteration are on the host"
    // halo / compute overlap: a high-priority stream with its own communicator (ncclCommSplit)
    cudaStream_t stream_halo = nullptr;
    ncclComm *comm_halo = nullptr;
@@ -41,6 +42,9 @@ struct cdm_ctx
    // device-side error word of the peer-memory halo exchange (mapped pinned host memory): a kernel that gave up
    // waiting for a neighbour sets it, the next host synchronisation point turns it into CDM_ENCCL
    unsigned int *p2p_err_host = nullptr, *p2p_err_dev = nullptr;
+   // peer-memory all-reduce state (owned by the first partitioned space that set up the symmetric exchange)
+   struct sym_state *red_sym = nullptr;
+   int allreduce_mode = 1;         // 1: peer-memory all-reduce when available, 0: always ncclAllReduce
 };
 
 struct cdm_mesh
@@ -72,6 +76,26 @@ struct cdm_halo_peer
    // dofs the peer owns that I hold as ghosts
    std::vector<int32_t> ghost_idx;  // local dof ids (>= ntrue)
    int64_t own_off = 0, ghost_off = 0;   // offsets of this peer's lists in the fused plan
+};
+
+// symmetric shared-dof exchange ("halo sum"): every rank of a dof's sharing group sends its partial sum to every
+// other rank of the group and all of them add the contributions in ascending rank order, so that after ONE exchange
+// the whole L-vector (ghost entries included) is consistent and bitwise identical on all sharers
+struct cdm_sym_peer
+{
+   int rank = -1;
+   std::vector<int32_t> idx;        // local dofs shared with this rank, ordered by global key (same order on both sides)
+   int64_t off = 0;                 // offset of this peer's segment in the concatenated list / receive buffer
+};
+struct cdm_sym_plan
+{
+   std::vector<cdm_sym_peer> peers;
+   std::vector<int32_t> all;                          // per-peer lists concatenated in peer order
+   std::vector<int32_t> sh_dof, sh_off, sh_src;       // distinct shared dofs; CSR of contributions in rank order, -1 = own value
+   std::vector<int32_t> bdr_dofs;                     // (unused on the device) distinct shared dofs, same as sh_dof
+   int32_t *all_dev = nullptr, *sh_dof_dev = nullptr, *sh_off_dev = nullptr, *sh_src_dev = nullptr;
+   struct sym_state *st = nullptr;                    // peer-memory buffers / flags (halo_p2p.cu)
+   int ready = 0;                                     // 0 not tried, 1 usable, -1 unavailable (fall back to P / P^T over NCCL)
 };
 
 // fused exchange plan over all peers (one pack + one unpack kernel per phase)
@@ -110,6 +134,7 @@ struct cdm_space
    // multi-GPU
    std::vector<cdm_halo_peer> peers;
    cdm_halo_plan halo;
+   cdm_sym_plan sym;
    // partitioned spaces order their elements "boundary first": elements [0, n_bdr_elems) touch a
    // shared dof, the rest are interior; elem_perm[new] = element index in the mesh
    int64_t n_bdr_elems = 0;
@@ -127,8 +152,9 @@ struct cdm_op
    double *D_dev = nullptr;
    int64_t D_len = 0;
    int32_t *gather_c_dev = nullptr; // gather map with essential dofs encoded as -1-g
-   int32_t *ess_dev = nullptr;      // owned essential dofs (y[ess] = x[ess])
-   int64_t n_ess = 0;
+   int32_t *ess_dev = nullptr;      // owned essential dofs (y[ess] = x[ess]), followed by the ghost ones
+   int64_t n_ess = 0;               // owned essential dofs
+   int64_t n_ess_all = 0;           // owned + ghost essential dofs (ghost-consistent apply)
    std::vector<int32_t> ess_host;
    double *yE_dev = nullptr;       // E-vector scratch (scatter mode 0)
    double *xL_dev = nullptr, *yL_dev = nullptr;   // L-vector scratch (multi-GPU / host mult)
@@ -137,8 +163,9 @@ struct cdm_op
    int64_t e_begin = 0, e_end = 0;
    int overlap = 1;                // 1: overlap the halo exchange with interior elements when possible
    bool tail = false;             // caller vectors have room for the ghost tail (length >= ndof)
+   bool ghost_in = false;         // with tail: the caller guarantees that x's ghost tail is already consistent
    int scatter_mode = 1;           // 0: E-vector + gather transpose, 1: FP64 red.add
-   int halo_mode = 0;              // 0: NCCL send/recv, 1: peer-memory stores + flags (halo_p2p.cu)
+   int halo_mode = 2;              // 0: P / P^T over NCCL send/recv, 1: P / P^T over peer memory, 2: one symmetric peer-memory exchange
    int assembly = 0;               // 0: partial assembly (matrix-free), 1: apply = SpMV with the assembled CSR matrix
    struct cdm_csr *csr = nullptr;  // csr_path.cu (built on demand)
    int kernel_variant = 0;
@@ -226,12 +253,20 @@ int cdm_k_mdot_dev(cdm_ctx *c, int64_t n, int k, const double *w, const double *
 // w_out = dinv .* t fused with the k dots of w_out against V
 int cdm_k_mdot_pc_dev(cdm_ctx *c, int64_t n, int k, const double *t, const double *dinv, double *w_out,
                       const double *V, int64_t ldv, double *out_dev);
+// lazily normalised basis (V holds u_i, nrm2[i] = ||u_i||^2): w_out = dinv .* t / sqrt(*sc2), out[i] = (w_out, u_i) / ||u_i||
+int cdm_k_mdot_lazy_dev(cdm_ctx *c, int64_t n, int k, const double *t, const double *dinv, const double *sc2,
+                        double *w_out, const double *V, int64_t ldv, const double *nrm2, double *out_dev);
+int cdm_k_pmult_scaled(cdm_ctx *c, int64_t n, const double *dinv, const double *sc2, const double *x, double *y);
+int cdm_k_maxpy_lazy_dev(cdm_ctx *c, int64_t n, int k, const double *h_dev, const double *nrm2, const double *V, int64_t ldv,
+                         double *w, double *norm2_out_dev);
 // w -= sum_i h_dev[i] V_i ; optionally also out_dev[0] = ||w_new||^2 partial-reduced
 int cdm_k_maxpy_dev(cdm_ctx *c, int64_t n, int k, const double *h_dev, const double *V, int64_t ldv,
                     double *w, double *norm2_out_dev);
 // v = w * (1/sqrt(*norm2_dev))
 int cdm_k_scale_by_rnorm(cdm_ctx *c, int64_t n, const double *norm2_dev, const double *w, double *v);
 int cdm_k_scale(cdm_ctx *c, int64_t n, double a, const double *w, double *v);
+// h[i] /= sqrt(nrm2[i]), i < k (dots against un-normalised basis vectors)
+int cdm_k_scale_dots(cdm_ctx *c, int k, const double *nrm2, double *h);
 // fused CG update: x += a d ; r -= a z ; out = (r,r)
 int cdm_k_cg_update(cdm_ctx *c, int64_t n, double a, const double *d, const double *z, double *x,
                     double *r, double *rr_out_dev);
@@ -252,6 +287,11 @@ int cdm_halo_p2p_setup(cdm_space *sp);              // collective over the ranks
 void cdm_halo_p2p_destroy(cdm_space *sp);
 int cdm_halo_p2p_P(cdm_space *sp, double *xL, cudaStream_t s, cudaEvent_t ev_packed);
 int cdm_halo_p2p_PT(cdm_space *sp, double *yL, cudaStream_t s, cudaEvent_t ev_packed);
+// symmetric exchange + Krylov all-reduce over peer memory (halo_p2p.cu)
+int cdm_halo_sym_setup(cdm_space *sp);              // collective; sets sp->sym.ready to 1 (usable) or -1 (fall back to NCCL)
+void cdm_halo_sym_destroy(cdm_space *sp);
+int cdm_halo_sym_exchange(cdm_space *sp, double *yL, cudaStream_t s);
+bool cdm_allreduce_sym(cdm_ctx *c, double *buf_dev, int k, int *rc_out);
 // same exchanges on the halo stream / communicator; ev_packed is recorded right after the pack kernel
 int cdm_halo_P_async(cdm_op *op, double *xL, cudaEvent_t ev_packed);
 int cdm_halo_PT_async(cdm_op *op, double *yL, cudaEvent_t ev_packed);

@@ -87,7 +87,6 @@ extern "C" int cdm_comm_init(cdm_ctx *ctx, int rank, int nranks, const void *uid
    NCCL_CALL(ctx, a->CommInitRank(&ctx->comm, nranks, id, rank));
    // second communicator + high-priority stream for the halo exchange, so that it can run beside the
    // element kernels of the compute stream (and beside the Krylov all-reduces of the main communicator)
-   if (a->CommSplit && a->CommSplit(ctx->comm, 0, rank, &ctx->comm_halo, nullptr) == 0 && ctx->comm_halo)
    {
       int lo = 0, hi = 0;
       cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -96,6 +95,8 @@ extern "C" int cdm_comm_init(cdm_ctx *ctx, int rank, int nranks, const void *uid
       for (int i = 0; i < 6 && ctx->stream_halo; i++)
          if (cudaEventCreateWithFlags(&ctx->ev_h[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ctx->stream_halo = nullptr; }
    }
+   // the NCCL exchanges that overlap compute need their own communicator; the peer-memory exchange only the stream
+   if (!(a->CommSplit && a->CommSplit(ctx->comm, 0, rank, &ctx->comm_halo, nullptr) == 0 && ctx->comm_halo)) { ctx->comm_halo = nullptr; }
    return CDM_OK;
 }
 
@@ -110,6 +111,9 @@ extern "C" int cdm_comm_rank(const cdm_ctx *ctx, int *rank, int *nranks)
 int cdm_allreduce_sum(cdm_ctx *c, double *buf_dev, int k)
 {
    if (c->nranks <= 1 || !c->comm) { return CDM_OK; }
+   // peer-memory all-reduce (two tiny kernels, rank-ordered sum) once a partitioned space has set it up
+   int rc = CDM_OK;
+   if (c->allreduce_mode != 0 && cdm_allreduce_sym(c, buf_dev, k, &rc)) { return rc; }
    NCCL_CALL(c, api()->AllReduce(buf_dev, buf_dev, (size_t)k, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
    return CDM_OK;
 }

@@ -131,9 +131,12 @@ template <int KB, int UNROLL, bool PC, bool VEC>
 __global__ void __launch_bounds__(CDM_RED_THREADS)
 k_mdot_partial(int64_t n, const double *__restrict__ w, const double *__restrict__ dinv,
                double *__restrict__ w_out, const double *__restrict__ V, int64_t ldv,
-               double *__restrict__ partial)
+               double *__restrict__ partial, const double *__restrict__ sc2)
 {
    __shared__ double red[8];
+   // PC: w_out = sc * dinv .* w with sc = 1/sqrt(*sc2) (lazy normalisation of the Krylov basis: the operator was
+   // applied to the un-normalised vector u_j, sc2 = ||u_j||^2); dinv == nullptr stands for the identity
+   const double sc = (PC && sc2) ? 1.0 / sqrt(*sc2) : 1.0;
    double acc[KB];
    #pragma unroll
    for (int j = 0; j < KB; j++) { acc[j] = 0.0; }
@@ -150,7 +153,11 @@ k_mdot_partial(int64_t n, const double *__restrict__ w, const double *__restrict
          for (int u = 0; u < UNROLL; u++)
          {
             wv[u] = ld2(w, base + u * blockDim.x);
-            if (PC) { const double2 d = ld2(dinv, base + u * blockDim.x); wv[u].x *= d.x; wv[u].y *= d.y; st2(w_out, base + u * blockDim.x, wv[u]); }
+            if (PC)
+            {
+               const double2 d = dinv ? ld2(dinv, base + u * blockDim.x) : make_double2(1.0, 1.0);
+               wv[u].x *= sc * d.x; wv[u].y *= sc * d.y; st2(w_out, base + u * blockDim.x, wv[u]);
+            }
          }
          double2 v[KB][UNROLL];
          #pragma unroll
@@ -172,14 +179,14 @@ k_mdot_partial(int64_t n, const double *__restrict__ w, const double *__restrict
          for (int64_t i = nfull * tile + threadIdx.x; i < n2; i += blockDim.x)
          {
             double2 wv = ld2(w, i);
-            if (PC) { const double2 d = ld2(dinv, i); wv.x *= d.x; wv.y *= d.y; st2(w_out, i, wv); }
+            if (PC) { const double2 d = dinv ? ld2(dinv, i) : make_double2(1.0, 1.0); wv.x *= sc * d.x; wv.y *= sc * d.y; st2(w_out, i, wv); }
             #pragma unroll
             for (int j = 0; j < KB; j++) { const double2 vv = ld2(V + j * ldv, i); acc[j] += wv.x * vv.x + wv.y * vv.y; }
          }
          if ((n & 1) && threadIdx.x == 0)
          {
             double wl = w[n - 1];
-            if (PC) { wl *= dinv[n - 1]; w_out[n - 1] = wl; }
+            if (PC) { wl *= sc * (dinv ? dinv[n - 1] : 1.0); w_out[n - 1] = wl; }
             #pragma unroll
             for (int j = 0; j < KB; j++) { acc[j] += wl * V[j * ldv + n - 1]; }
          }
@@ -191,7 +198,7 @@ k_mdot_partial(int64_t n, const double *__restrict__ w, const double *__restrict
       for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
       {
          double wv = w[i];
-         if (PC) { wv *= dinv[i]; w_out[i] = wv; }
+         if (PC) { wv *= sc * (dinv ? dinv[i] : 1.0); w_out[i] = wv; }
          #pragma unroll
          for (int j = 0; j < KB; j++) { acc[j] += wv * V[j * ldv + i]; }
       }
@@ -205,33 +212,34 @@ k_mdot_partial(int64_t n, const double *__restrict__ w, const double *__restrict
 }
 
 __global__ void __launch_bounds__(CDM_RED_THREADS)
-k_reduce_final(const double *__restrict__ partial, double *__restrict__ out)
+k_reduce_final(const double *__restrict__ partial, double *__restrict__ out, const double *__restrict__ nrm2 = nullptr)
 {
    __shared__ double red[8];
    const double *p = partial + (int64_t)blockIdx.x * CDM_RED_BLOCKS;
    double v = 0.0;
    for (int i = threadIdx.x; i < CDM_RED_BLOCKS; i += CDM_RED_THREADS) { v += p[i]; }
    const double s = block_sum(v, red);
-   if (threadIdx.x == 0) { out[blockIdx.x] = s; }
+   // nrm2: the dots were taken against un-normalised basis vectors u_i; (w, v_i) = (w, u_i) / ||u_i||
+   if (threadIdx.x == 0) { out[blockIdx.x] = nrm2 ? s / sqrt(nrm2[blockIdx.x]) : s; }
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int KB, bool PC>
 static void mdot_one(cdm_ctx *c, bool vec, int64_t n, const double *win, const double *dinv, double *w_out,
-                     const double *Vj, int64_t ldv, double *pj)
+                     const double *Vj, int64_t ldv, double *pj, const double *sc2)
 {
-   if (vec) { k_mdot_partial<KB, (KB <= 4 ? 4 : 2), PC, true><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, win, dinv, w_out, Vj, ldv, pj); }
-   else { k_mdot_partial<KB, 1, PC, false><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, win, dinv, w_out, Vj, ldv, pj); }
+   if (vec) { k_mdot_partial<KB, (KB <= 4 ? 4 : 2), PC, true><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, win, dinv, w_out, Vj, ldv, pj, sc2); }
+   else { k_mdot_partial<KB, 1, PC, false><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, win, dinv, w_out, Vj, ldv, pj, sc2); }
 }
 
 template <bool PC>
 static int mdot_launch(cdm_ctx *c, int64_t n, int k, const double *w, const double *dinv, double *w_out,
-                       const double *V, int64_t ldv, double *out_dev)
+                       const double *V, int64_t ldv, double *out_dev, const double *sc2 = nullptr, const double *nrm2 = nullptr)
 {
    if (k < 1 || k > CDM_RED_MAXK) { return cdm_fail(c, CDM_EINVAL, "mdot: k out of range"); }
    double *partial = c->red_dev;
-   const bool vec = aligned16(w) && aligned16(V) && (ldv % 2 == 0) && (!PC || (aligned16(dinv) && aligned16(w_out)));
+   const bool vec = aligned16(w) && aligned16(V) && (ldv % 2 == 0) && (!PC || ((!dinv || aligned16(dinv)) && aligned16(w_out)));
    for (int j0 = 0; j0 < k; j0 += 8)
    {
       const int kb = (k - j0 < 8) ? k - j0 : 8;
@@ -240,13 +248,13 @@ static int mdot_launch(cdm_ctx *c, int64_t n, int k, const double *w, const doub
       // the preconditioner is applied (and w_out written) by the first pass only
       const bool first = PC && j0 == 0;
       const double *win = (PC && !first) ? w_out : w;
-#define MDOT_CASE(KB) case KB: if (first) { mdot_one<KB, true>(c, vec, n, win, dinv, w_out, Vj, ldv, pj); } \
-                               else { mdot_one<KB, false>(c, vec, n, win, dinv, w_out, Vj, ldv, pj); } break
+#define MDOT_CASE(KB) case KB: if (first) { mdot_one<KB, true>(c, vec, n, win, dinv, w_out, Vj, ldv, pj, sc2); } \
+                               else { mdot_one<KB, false>(c, vec, n, win, dinv, w_out, Vj, ldv, pj, nullptr); } break
       switch (kb) { MDOT_CASE(1); MDOT_CASE(2); MDOT_CASE(3); MDOT_CASE(4); MDOT_CASE(5); MDOT_CASE(6); MDOT_CASE(7); MDOT_CASE(8); }
 #undef MDOT_CASE
       c->launches++;
    }
-   k_reduce_final<<<k, CDM_RED_THREADS, 0, c->stream>>>(partial, out_dev);
+   k_reduce_final<<<k, CDM_RED_THREADS, 0, c->stream>>>(partial, out_dev, nrm2);
    VEC_CHECK(c);
 }
 
@@ -258,15 +266,40 @@ int cdm_k_mdot_pc_dev(cdm_ctx *c, int64_t n, int k, const double *t, const doubl
                       const double *V, int64_t ldv, double *out_dev)
 { return mdot_launch<true>(c, n, k, t, dinv, w_out, V, ldv, out_dev); }
 
+// lazily normalised Krylov basis (V holds u_i, nrm2[i] = ||u_i||^2):
+//   w_out = dinv .* t / sqrt(*sc2)  (dinv may be null), out[i] = (w_out, u_i) / sqrt(nrm2[i]),  i < k
+int cdm_k_mdot_lazy_dev(cdm_ctx *c, int64_t n, int k, const double *t, const double *dinv, const double *sc2,
+                        double *w_out, const double *V, int64_t ldv, const double *nrm2, double *out_dev)
+{ return mdot_launch<true>(c, n, k, t, dinv, w_out, V, ldv, out_dev, sc2, nrm2); }
+
+// y = dinv .* x / sqrt(*sc2) on a short range (ghost tail of the vector above); dinv, sc2 may be null
+__global__ void k_pmult_scaled(int64_t n, const double *__restrict__ dinv, const double *__restrict__ sc2,
+                               const double *__restrict__ x, double *__restrict__ y)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const double sc = sc2 ? 1.0 / sqrt(*sc2) : 1.0;
+   if (i < n) { y[i] = sc * (dinv ? dinv[i] : 1.0) * x[i]; }
+}
+__global__ void k_scale_dots(int k, const double *__restrict__ nrm2, double *__restrict__ h)
+{
+   const int i = threadIdx.x;
+   if (i < k) { h[i] /= sqrt(nrm2[i]); }
+}
+int cdm_k_scale_dots(cdm_ctx *c, int k, const double *nrm2, double *h)
+{ k_scale_dots<<<1, 64, 0, c->stream>>>(k, nrm2, h); VEC_CHECK(c); }
+int cdm_k_pmult_scaled(cdm_ctx *c, int64_t n, const double *dinv, const double *sc2, const double *x, double *y)
+{ if (n > 0) { k_pmult_scaled<<<vec_grid(n), VEC_BLOCK, 0, c->stream>>>(n, dinv, sc2, x, y); } VEC_CHECK(c); }
+
 // w -= sum_j h[j] V_j, and the partial sums of ||w_new||^2
 template <bool VEC>
 __global__ void __launch_bounds__(CDM_RED_THREADS)
 k_maxpy_norm(int64_t n, int k, const double *__restrict__ h, const double *__restrict__ V, int64_t ldv,
-             double *__restrict__ w, double *__restrict__ partial)
+             double *__restrict__ w, double *__restrict__ partial, const double *__restrict__ nrm2)
 {
    __shared__ double sh[CDM_RED_MAXK];
    __shared__ double red[8];
-   if (threadIdx.x < k) { sh[threadIdx.x] = h[threadIdx.x]; }
+   // nrm2: V holds un-normalised vectors u_i, the coefficient of u_i is h_i / ||u_i||
+   if (threadIdx.x < k) { sh[threadIdx.x] = nrm2 ? h[threadIdx.x] / sqrt(nrm2[threadIdx.x]) : h[threadIdx.x]; }
    __syncthreads();
    double acc = 0.0;
    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -326,13 +359,19 @@ k_maxpy_norm(int64_t n, int k, const double *__restrict__ h, const double *__res
 
 int cdm_k_maxpy_dev(cdm_ctx *c, int64_t n, int k, const double *h_dev, const double *V, int64_t ldv,
                     double *w, double *norm2_out_dev)
+{ return cdm_k_maxpy_lazy_dev(c, n, k, h_dev, nullptr, V, ldv, w, norm2_out_dev); }
+
+// w -= sum_i (h[i] / sqrt(nrm2[i])) V_i (nrm2 may be null: plain coefficients); optional ||w_new||^2
+int cdm_k_maxpy_lazy_dev(cdm_ctx *c, int64_t n, int k, const double *h_dev, const double *nrm2, const double *V, int64_t ldv,
+                         double *w, double *norm2_out_dev)
 {
    if (k < 0 || k > CDM_RED_MAXK) { return cdm_fail(c, CDM_EINVAL, "maxpy: k out of range"); }
+   if (n <= 0) { return CDM_OK; }
    double *partial = norm2_out_dev ? c->red_dev : nullptr;
    if (aligned16(w) && aligned16(V) && (ldv % 2 == 0))
-      k_maxpy_norm<true><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, k, h_dev, V, ldv, w, partial);
+      k_maxpy_norm<true><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, k, h_dev, V, ldv, w, partial, nrm2);
    else
-      k_maxpy_norm<false><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, k, h_dev, V, ldv, w, partial);
+      k_maxpy_norm<false><<<CDM_RED_BLOCKS, CDM_RED_THREADS, 0, c->stream>>>(n, k, h_dev, V, ldv, w, partial, nrm2);
    c->launches++;
    if (norm2_out_dev)
    {

@@ -12,7 +12,8 @@
 #include <cmath>
 #include <vector>
 
-extern "C" int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained);   // capi.cu
+extern "C" int cdm_apply_tail(cdm_op *op, double *x_buf, double *y_buf, bool constrained, bool x_ghost_valid);   // capi.cu
+extern "C" bool cdm_apply_keeps_ghosts(const cdm_op *op);
 
 namespace
 {
@@ -29,29 +30,44 @@ int ensure_ws(cdm_op *op, int64_t doubles)
    return CDM_OK;
 }
 
-int ensure_dinv(cdm_op *op)
-{
-   cdm_ctx *ctx = op->sp->ctx;
-   if (op->dinv_dev) { return CDM_OK; }
-   CDM_CUDA(ctx, cudaMalloc(&op->dinv_dev, sizeof(double) * (size_t)op->sp->ndof));
-   int rc = cdm_operator_diag(op, op->dinv_dev);
-   if (!rc) { rc = cdm_k_recip(ctx, op->sp->ntrue, op->dinv_dev, op->dinv_dev); }     // a zero diagonal entry -> 1 (PCJacobi)
-   if (rc) { cudaFree(op->dinv_dev); op->dinv_dev = nullptr; }                          // never keep a half-built diagonal
-   return rc;
-}
-
 // fetch k doubles of the device result area to the host (one sync)
 int fetch(cdm_ctx *c, const double *dev, int k, double *host)
 {
    CDM_CUDA(c, cudaMemcpyAsync(c->red_host, dev, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
    CDM_CUDA(c, cudaStreamSynchronize(c->stream));
    for (int i = 0; i < k; i++) { host[i] = c->red_host[i]; }
-   return CDM_OK;
+   return cdm_check_p2p(c);          // a peer-memory kernel that timed out invalidates what was just read
 }
 }  // namespace
 
 #define RC(call) do { int rc_ = (call); if (rc_) { return rc_; } } while (0)
 
+// Jacobi inverse diagonal on the whole local vector: on partitioned spaces the ghost entries are filled from their
+// owners so that dinv .* (ghost-consistent vector) stays ghost-consistent
+static int ensure_dinv(cdm_op *op)
+{
+   cdm_space *sp = op->sp;
+   cdm_ctx *ctx = sp->ctx;
+   if (op->dinv_dev) { return CDM_OK; }
+   CDM_CUDA(ctx, cudaMalloc(&op->dinv_dev, sizeof(double) * (size_t)sp->ndof));
+   int rc = cdm_operator_diag(op, op->dinv_dev);
+   if (!rc && ctx->nranks > 1 && !sp->peers.empty()) { rc = cdm_halo_P_space(sp, op->dinv_dev); }
+   if (!rc) { rc = cdm_k_recip(ctx, sp->ndof, op->dinv_dev, op->dinv_dev); }            // a zero diagonal entry -> 1 (PCJacobi)
+   if (rc) { cudaFree(op->dinv_dev); op->dinv_dev = nullptr; }                          // never keep a half-built diagonal
+   return rc;
+}
+
+// Restarted GMRES with a LAZILY NORMALISED basis: V_i holds the un-normalised vector u_i, nrm2[i] = ||u_i||^2 stays on
+// the device, v_i = u_i / ||u_i|| is never written.  One iteration is
+//     t = A u_j                                          (element kernel + one shared-dof exchange)
+//     u_{j+1} <- dinv .* t / ||u_j||,  h_i = (u_{j+1}, u_i) / ||u_i||      (fused multi-dot, Jacobi and scaling in its first pass)
+//     u_{j+1} -= sum_i (h_i / ||u_i||) u_i,  nrm2[j+1] = ||u_{j+1}||^2      (fused multi-axpy + norm)
+// i.e. classical Gram-Schmidt exactly as KSPGMRES does it, without the separate normalisation pass.  The host needs the
+// j+2 scalars of iteration j only for the Givens rotations and the convergence test; they are copied to pinned
+// memory behind an event, and the operator apply of iteration j+1 (which does not depend on them) is queued BEFORE the
+// host waits for that event: the device never idles on the host.
+// On partitioned spaces all vector updates run over the whole local vector (ghost tail included) and the dots over
+// the true dofs only, so every basis vector stays ghost-consistent and the apply needs no P exchange.
 extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylov_opts *o,
                          cdm_krylov_result *res, double *hist)
 {
@@ -62,39 +78,42 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
    const int64_t n = sp->ntrue;
    const int64_t ld = (sp->ndof + 31) & ~(int64_t)31;     // room for the ghost tail
    const int m = o->restart > 0 ? o->restart : (o->variant == CDM_GMRES_PETSC ? 30 : 50);
-   if (m + 1 > CDM_RED_MAXK) { return cdm_fail(c, CDM_EINVAL, "cdm_gmres: restart too large"); }
+   if (m + 2 > CDM_RED_MAXK) { return cdm_fail(c, CDM_EINVAL, "cdm_gmres: restart too large"); }
    RC(ensure_ws(op, (int64_t)(m + 3) * ld));
    double *V = op->kry_dev, *w = V + (int64_t)(m + 1) * ld, *t = w + ld;
+   const bool par = c->nranks > 1 && !sp->peers.empty();
+   if (par && op->halo_mode == 2 && op->assembly == 0 && sp->sym.ready == 0) { RC(cdm_halo_sym_setup(sp)); }
+   const bool gh = cdm_apply_keeps_ghosts(op);            // applies return ghost-consistent vectors
+   const int64_t nall = gh ? sp->ndof : n, ntail = nall - n;
    const double *dinv = nullptr;
    if (o->jacobi) { RC(ensure_dinv(op)); dinv = op->dinv_dev; }
-   double *h_dev = red_out(c);                 // [m+1] dots, then ||w||^2 at h_dev[m+1]
+   double *h_dev = red_out(c);                            // [m+1] dots of the current iteration
+   double *nrm2 = red_out(c) + CDM_RED_MAXK;              // [m+2] squared norms of u_0 .. u_m
    double *y_dev = red_out(c) + 2 * CDM_RED_MAXK;
-   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), s(m + 1), yv(m), hc(m + 2);
+   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), s(m + 1), yv(m), hc(m + 2), unorm(m + 2, 1.0);
    int it = 0, conv = 0, hl = 0;
    double rnorm = 0.0, ttol = 0.0;
    bool first = true;
+   if (!c->ev_kry) { CDM_CUDA(c, cudaEventCreateWithFlags(&c->ev_kry, cudaEventDisableTiming)); }
    CDM_CUDA(c, cudaEventRecord(c->ev0, c->stream));
    if (o->zero_guess) { RC(cdm_k_set(c, n, 0.0, x)); }
    while (true)
    {
-      // V0 = M^{-1}(b - A x)
-      if (first && o->zero_guess)
-      {
-         if (dinv) { RC(cdm_k_pmult(c, n, dinv, b, V)); }
-         else { CDM_CUDA(c, cudaMemcpyAsync(V, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream)); }
-      }
+      // u_0 = M^{-1}(b - A x)
+      if (first && o->zero_guess) { RC(cdm_k_pmult_scaled(c, n, dinv, nullptr, b, V)); }
       else
       {
          CDM_CUDA(c, cudaMemcpyAsync(w, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-         RC(cdm_apply_tail(op, w, t, true));
+         RC(cdm_apply_tail(op, w, t, true, false));
          RC(cdm_k_add(c, n, b, -1.0, t, t));
-         if (dinv) { RC(cdm_k_pmult(c, n, dinv, t, V)); }
-         else { CDM_CUDA(c, cudaMemcpyAsync(V, t, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream)); }
+         RC(cdm_k_pmult_scaled(c, n, dinv, nullptr, t, V));
       }
-      RC(cdm_k_mdot_dev(c, n, 1, V, V, ld, h_dev));
-      RC(cdm_allreduce_sum(c, h_dev, 1));
-      double b2; RC(fetch(c, h_dev, 1, &b2));
+      if (gh) { RC(cdm_halo_P_space(sp, V)); }             // once per cycle: make u_0 ghost-consistent
+      RC(cdm_k_mdot_dev(c, n, 1, V, V, ld, nrm2));
+      RC(cdm_allreduce_sum(c, nrm2, 1));
+      double b2; RC(fetch(c, nrm2, 1, &b2));
       const double beta = std::sqrt(b2);
+      unorm[0] = beta;
       rnorm = beta;
       if (first)
       {
@@ -103,8 +122,8 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
          double ref = beta;
          if (!o->zero_guess && o->variant == CDM_GMRES_PETSC)
          {
-            if (dinv) { RC(cdm_k_pmult(c, n, dinv, b, w)); }
-            RC(cdm_k_mdot_dev(c, n, 1, dinv ? w : b, dinv ? w : b, ld, h_dev));
+            RC(cdm_k_pmult_scaled(c, n, dinv, nullptr, b, w));
+            RC(cdm_k_mdot_dev(c, n, 1, w, w, ld, h_dev));
             RC(cdm_allreduce_sum(c, h_dev, 1));
             double nb2; RC(fetch(c, h_dev, 1, &nb2));
             ref = std::sqrt(nb2);
@@ -115,38 +134,48 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
       }
       if (rnorm <= ttol) { conv = 1; break; }
       if (it >= o->max_it) { break; }
-      RC(cdm_k_scale(c, n, 1.0 / beta, V, V));
       std::fill(s.begin(), s.end(), 0.0);
       s[0] = beta;
       int j = 0;
+      bool applied = false;                                // t already holds A u_j (queued ahead of the host wait)
       while (j < m && it < o->max_it)
       {
-         double *vj = V + (int64_t)j * ld, *vn = V + (int64_t)(j + 1) * ld;
-         RC(cdm_apply_tail(op, vj, dinv ? t : w, true));
-         if (dinv && o->variant != CDM_GMRES_PETSC) { RC(cdm_k_pmult(c, n, dinv, t, w)); }
+         double *uj = V + (int64_t)j * ld, *un = V + (int64_t)(j + 1) * ld;
+         if (!applied) { RC(cdm_apply_tail(op, uj, t, true, gh)); }
+         applied = false;
          if (o->variant == CDM_GMRES_PETSC)
          {
-            // classical Gram-Schmidt: all j+1 dots against the same w, one all-reduce; the Jacobi
-            // scaling w = dinv .* (A v_j) is fused into the first pass of the multi-dot
-            if (dinv) { RC(cdm_k_mdot_pc_dev(c, n, j + 1, t, dinv, w, V, ld, h_dev)); }
-            else { RC(cdm_k_mdot_dev(c, n, j + 1, w, V, ld, h_dev)); }
+            // classical Gram-Schmidt: all j+1 dots against the same vector, one all-reduce
+            RC(cdm_k_mdot_lazy_dev(c, n, j + 1, t, dinv, nrm2 + j, un, V, ld, nrm2, h_dev));
+            if (ntail > 0) { RC(cdm_k_pmult_scaled(c, ntail, dinv ? dinv + n : nullptr, nrm2 + j, t + n, un + n)); }
             RC(cdm_allreduce_sum(c, h_dev, j + 1));
-            RC(cdm_k_maxpy_dev(c, n, j + 1, h_dev, V, ld, w, h_dev + (j + 1)));
+            RC(cdm_k_maxpy_lazy_dev(c, n, j + 1, h_dev, nrm2, V, ld, un, nrm2 + (j + 1)));
+            if (ntail > 0) { RC(cdm_k_maxpy_lazy_dev(c, ntail, j + 1, h_dev, nrm2, V + n, ld, un + n, nullptr)); }
          }
          else
          {
-            // modified Gram-Schmidt, scalars stay on the device
+            // modified Gram-Schmidt (mfem::GMRESSolver), scalars stay on the device
+            RC(cdm_k_pmult_scaled(c, nall, dinv, nrm2 + j, t, un));
             for (int i = 0; i <= j; i++)
             {
-               RC(cdm_k_mdot_dev(c, n, 1, w, V + (int64_t)i * ld, ld, h_dev + i));
+               RC(cdm_k_mdot_dev(c, n, 1, un, V + (int64_t)i * ld, ld, h_dev + i));
+               RC(cdm_k_scale_dots(c, 1, nrm2 + i, h_dev + i));
                RC(cdm_allreduce_sum(c, h_dev + i, 1));
-               RC(cdm_k_maxpy_dev(c, n, 1, h_dev + i, V + (int64_t)i * ld, ld, w, i == j ? h_dev + (j + 1) : nullptr));
+               RC(cdm_k_maxpy_lazy_dev(c, n, 1, h_dev + i, nrm2 + i, V + (int64_t)i * ld, ld, un, i == j ? nrm2 + (j + 1) : nullptr));
+               if (ntail > 0) { RC(cdm_k_maxpy_lazy_dev(c, ntail, 1, h_dev + i, nrm2 + i, V + (int64_t)i * ld + n, ld, un + n, nullptr)); }
             }
          }
-         RC(cdm_allreduce_sum(c, h_dev + (j + 1), 1));
-         RC(cdm_k_scale_by_rnorm(c, n, h_dev + (j + 1), w, vn));
-         RC(fetch(c, h_dev, j + 2, hc.data()));
+         RC(cdm_allreduce_sum(c, nrm2 + (j + 1), 1));
+         CDM_CUDA(c, cudaMemcpyAsync(c->red_host, h_dev, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, c->stream));
+         CDM_CUDA(c, cudaMemcpyAsync(c->red_host + (j + 1), nrm2 + (j + 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+         CDM_CUDA(c, cudaEventRecord(c->ev_kry, c->stream));
+         // the next apply does not depend on the host: queue it before waiting (not across a restart / the last step)
+         if (j + 1 < m && it + 1 < o->max_it) { RC(cdm_apply_tail(op, un, t, true, gh)); applied = true; }
+         CDM_CUDA(c, cudaEventSynchronize(c->ev_kry));
+         RC(cdm_check_p2p(c));
+         for (int i = 0; i < j + 2; i++) { hc[i] = c->red_host[i]; }
          const double hn = std::sqrt(hc[j + 1]);
+         unorm[j + 1] = hn;
          hc[j + 1] = hn;
          for (int i = 0; i < j; i++)
          {
@@ -172,8 +201,8 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
          for (int k = i + 1; k < j; k++) { a -= H[(size_t)k * (m + 1) + i] * yv[k]; }
          yv[i] = a / H[(size_t)i * (m + 1) + i];
       }
-      // x += V y  (maxpy subtracts, so upload -y)
-      for (int i = 0; i < j; i++) { c->red_host[2 * CDM_RED_MAXK + i] = -yv[i]; }
+      // x += V y = sum_i (y_i / ||u_i||) u_i  (maxpy subtracts, so upload the negated coefficients)
+      for (int i = 0; i < j; i++) { c->red_host[2 * CDM_RED_MAXK + i] = -yv[i] / unorm[i]; }
       CDM_CUDA(c, cudaMemcpyAsync(y_dev, c->red_host + 2 * CDM_RED_MAXK, sizeof(double) * j, cudaMemcpyHostToDevice, c->stream));
       RC(cdm_k_maxpy_dev(c, n, j, y_dev, V, ld, x, nullptr));
       CDM_CUDA(c, cudaStreamSynchronize(c->stream));   // red_host is reused
@@ -181,6 +210,7 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
    }
    CDM_CUDA(c, cudaEventRecord(c->ev1, c->stream));
    CDM_CUDA(c, cudaEventSynchronize(c->ev1));
+   RC(cdm_check_p2p(c));
    float ms = 0.f;
    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
    res->iters = it; res->converged = conv; res->final_norm = rnorm; res->hist_len = hl;
@@ -188,6 +218,8 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
    return CDM_OK;
 }
 
+// mfem::CGSolver.  On partitioned spaces r, z, d are kept ghost-consistent (updates over the whole local vector, dots
+// over the true dofs), so the apply inside the loop needs no P exchange.
 extern "C" int cdm_cg(cdm_op *op, const double *b, double *x, const cdm_krylov_opts *o,
                       cdm_krylov_result *res, double *hist)
 {
@@ -199,6 +231,10 @@ extern "C" int cdm_cg(cdm_op *op, const double *b, double *x, const cdm_krylov_o
    const int64_t ld = (sp->ndof + 31) & ~(int64_t)31;
    RC(ensure_ws(op, 4 * ld));
    double *r = op->kry_dev, *d = r + ld, *z = d + ld, *zz = z + ld;
+   const bool par = c->nranks > 1 && !sp->peers.empty();
+   if (par && op->halo_mode == 2 && op->assembly == 0 && sp->sym.ready == 0) { RC(cdm_halo_sym_setup(sp)); }
+   const bool gh = cdm_apply_keeps_ghosts(op);
+   const int64_t nall = gh ? sp->ndof : n, ntail = nall - n;
    const double *dinv = nullptr;
    if (o->jacobi) { RC(ensure_dinv(op)); dinv = op->dinv_dev; }
    double *sc = red_out(c);
@@ -212,11 +248,12 @@ extern "C" int cdm_cg(cdm_op *op, const double *b, double *x, const cdm_krylov_o
    else
    {
       CDM_CUDA(c, cudaMemcpyAsync(d, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-      RC(cdm_apply_tail(op, d, r, true));
+      RC(cdm_apply_tail(op, d, r, true, false));
       RC(cdm_k_add(c, n, b, -1.0, r, r));
    }
-   if (dinv) { RC(cdm_k_pmult(c, n, dinv, r, d)); }
-   else { CDM_CUDA(c, cudaMemcpyAsync(d, r, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream)); }
+   if (gh) { RC(cdm_halo_P_space(sp, r)); }                 // r ghost-consistent from here on
+   if (dinv) { RC(cdm_k_pmult(c, nall, dinv, r, d)); }
+   else { CDM_CUDA(c, cudaMemcpyAsync(d, r, sizeof(double) * nall, cudaMemcpyDeviceToDevice, c->stream)); }
    double nom, den, betanom;
    RC(cdm_k_mdot_dev(c, n, 1, d, r, ld, sc)); RC(cdm_allreduce_sum(c, sc, 1)); RC(fetch(c, sc, 1, &nom));
    const double r0 = std::fmax(nom * o->rtol * o->rtol, o->atol * o->atol);
@@ -225,7 +262,7 @@ extern "C" int cdm_cg(cdm_op *op, const double *b, double *x, const cdm_krylov_o
    if (nom <= r0) { conv = 1; }
    else
    {
-      RC(cdm_apply_tail(op, d, z, true));
+      RC(cdm_apply_tail(op, d, z, true, gh));
       RC(cdm_k_mdot_dev(c, n, 1, z, d, ld, sc)); RC(cdm_allreduce_sum(c, sc, 1)); RC(fetch(c, sc, 1, &den));
       if (den > 0.0)
       {
@@ -233,9 +270,10 @@ extern "C" int cdm_cg(cdm_op *op, const double *b, double *x, const cdm_krylov_o
          {
             const double alpha = nom / den;
             RC(cdm_k_cg_update(c, n, alpha, d, z, x, r, sc));       // x += a d ; r -= a z ; sc = (r,r)
+            if (ntail > 0) { RC(cdm_k_axpy(c, ntail, -alpha, z + n, r + n)); }
             if (dinv)
             {
-               RC(cdm_k_pmult(c, n, dinv, r, zz));
+               RC(cdm_k_pmult(c, nall, dinv, r, zz));
                RC(cdm_k_mdot_dev(c, n, 1, r, zz, ld, sc));
             }
             RC(cdm_allreduce_sum(c, sc, 1));
@@ -244,8 +282,8 @@ extern "C" int cdm_cg(cdm_op *op, const double *b, double *x, const cdm_krylov_o
             if (betanom <= r0) { conv = 1; break; }
             if (it >= o->max_it) { break; }
             const double beta = betanom / nom;
-            RC(cdm_k_add(c, n, dinv ? zz : r, beta, d, d));          // d = z + beta d
-            RC(cdm_apply_tail(op, d, z, true));
+            RC(cdm_k_add(c, nall, dinv ? zz : r, beta, d, d));       // d = z + beta d
+            RC(cdm_apply_tail(op, d, z, true, gh));
             RC(cdm_k_mdot_dev(c, n, 1, d, z, ld, sc)); RC(cdm_allreduce_sum(c, sc, 1)); RC(fetch(c, sc, 1, &den));
             if (den <= 0.0) { break; }
             nom = betanom;
@@ -254,6 +292,7 @@ extern "C" int cdm_cg(cdm_op *op, const double *b, double *x, const cdm_krylov_o
    }
    CDM_CUDA(c, cudaEventRecord(c->ev1, c->stream));
    CDM_CUDA(c, cudaEventSynchronize(c->ev1));
+   RC(cdm_check_p2p(c));
    float ms = 0.f;
    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
    res->iters = it; res->converged = conv; res->final_norm = std::sqrt(std::fabs(betanom)); res->hist_len = hl;

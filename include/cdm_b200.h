@@ -118,6 +118,16 @@ int  cdm_space_halo_peers(const cdm_space *space, int *npeers);
 int  cdm_space_halo_peer(const cdm_space *space, int i, int *rank, int64_t *n_own, int64_t *n_ghost,
                          int32_t *own_idx, int32_t *ghost_idx);
 int  cdm_space_dof_global(const cdm_space *space, int64_t *keys);
+/* symmetric exchange plan of a partitioned space (the default multi-GPU protocol, one exchange per apply): every
+   rank of a dof's sharing group sends its partial sum to every other rank of the group; the contributions are
+   added in ascending rank order, so all sharers hold the bitwise identical sum and the L-vector stays consistent
+   on its ghost entries.  sym_peers: number of neighbour ranks, of distinct shared dofs and of CSR contributions.
+   sym_peer i: its rank, the local dofs shared with it (global-key order: the same order on both sides) and the
+   offset of its segment in the receive buffer.  sum_plan: dof[n_shared], off[n_shared+1], src[n_contrib] --
+   src >= 0: index into the receive buffer, src < 0: this rank's own value. */
+int  cdm_space_sym_peers(const cdm_space *space, int *npeers, int64_t *n_shared, int64_t *n_contrib);
+int  cdm_space_sym_peer(const cdm_space *space, int i, int *rank, int64_t *n, int64_t *offset, int32_t *idx);
+int  cdm_space_sym_sum_plan(const cdm_space *space, int32_t *dof, int32_t *off, int32_t *src);
 /* element order of the space: perm[e] = index in the mesh of the space's e-th element (identity
    unless the space is partitioned: then the n_boundary elements touching a shared dof come first,
    so that the halo exchange overlaps the interior elements).  Per-element inputs (gather map,
@@ -189,10 +199,17 @@ int  cdm_operator_csr_get(const cdm_op *op, int64_t *rowptr, int32_t *colind, do
    "kernel" (0 block kernel, 1-3 order-3 warp kernels, 4 group kernel, 5 sub-warp kernel; default by order),
    "tail" (1: caller vectors have the local size, see cdm_operator_local_size),
    "overlap" (multi-GPU: 0 serial halo exchange, 1 overlapped with interior elements up to 3 neighbours, 2 always),
-   "halo" (multi-GPU: 0 NCCL send/recv, 1 peer-memory stores + flags over NVLink; setting it to 1 is a
-   collective call: every rank must make it), "host_pipeline" (0/1, or a chunk count for cdm_operator_mult_host),
+   "halo" (multi-GPU shared-dof protocol: 2 (default) ONE symmetric peer-memory exchange per apply, the result is
+   consistent on the ghost entries too; 0 P and P^T over NCCL send/recv; 1 P and P^T over peer-memory stores;
+   setting it to 1 is a collective call, mode 2 is set up collectively by the first apply / solve),
+   "ghost_in" (with "tail": 1 = the caller guarantees that the ghost entries of x are consistent, e.g. x was produced
+   by a previous apply in halo mode 2 or by cdm_prolongate: the P exchange is skipped),
+   "allreduce" (1 (default) Krylov scalars all-reduced through peer memory, 0 ncclAllReduce), "host_pipeline" (0/1, or a chunk count for cdm_operator_mult_host),
    "grid_cap" (> 0: upper bound on the persistent grids, so that a small test mesh runs many elements per warp) */
 int  cdm_operator_set_option(cdm_op *op, const char *name, int value);
+/* current value of an option; "halo" and "allreduce" report the protocol actually in use (the peer-memory
+   protocols fall back to NCCL on every rank when their setup fails on any rank) */
+int  cdm_operator_get_option(const cdm_op *op, const char *name, int *value);
 /* ------------------- integrator-level (E-vector) and prolongation entry points */
 /* MFEM: BilinearFormIntegrator::AddMultPA(const Vector &x_E, Vector &y_E) -- what a ParBilinearForm under
    AssemblyLevel::PARTIAL dispatches to after its own ElementRestriction (a.Assemble(),

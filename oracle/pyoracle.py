@@ -368,3 +368,10 @@ class Op:
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    """OpenMP threads of the oracle (torchrun exports OMP_NUM_THREADS=1: callers that time the CPU
+    path set the count explicitly)"""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()

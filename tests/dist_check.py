@@ -47,7 +47,8 @@ def main():
     ap.add_argument("--mode", default="cpu", choices=["cpu", "gpu"])
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--mesh", type=int, nargs=3, default=[6, 5, 4])
-    ap.add_argument("--p2p", action="store_true", help="also check the peer-memory halo exchange (option halo=1)")
+    ap.add_argument("--p2p", action="store_true", help="also check the peer-memory P / P^T exchange (option halo=1)")
+    ap.add_argument("--halo", type=int, default=2, help="shared-dof protocol of the main checks: 2 symmetric peer-memory (default), 0 NCCL")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
@@ -97,6 +98,8 @@ def main():
     ok = True
     if gpu:
         op = cdm.ConvectionDiffusionOperator(sp, kappa=kap, vel=vel, mass=mass, ess_dofs=ess)
+        op.set_option("halo", args.halo)
+        print(f"[rank {rank}] shared-dof protocol requested: {args.halo}", flush=True)
         xd = torch.from_numpy(xg[mine[:nt]]).cuda()
         yd = torch.zeros(nt, dtype=torch.float64, device="cuda")
         torch.cuda.synchronize()
@@ -114,6 +117,38 @@ def main():
             print(f"[rank {rank}] apply kernel={kernel} scatter={scatter} overlap={overlap} rel err {err:.2e}", flush=True)
         op.set_option("kernel", 3 if p == 3 else (5 if p < 3 else 4))     # the defaults
         op.set_option("overlap", 1)
+        used = op.get_option("halo")
+        print(f"[rank {rank}] shared-dof protocol in use: {used}, peer-memory all-reduce: {op.get_option('allreduce')}", flush=True)
+        ok &= used == args.halo                                   # no silent fall-back on a box with NVLink peers
+        if used == 2:
+            # ghost consistency: local-size vectors ("tail"), the result must equal the oracle on EVERY local dof, and
+            # feeding y back as x without a P exchange ("ghost_in") must reproduce A (A x)
+            op.set_option("tail", 1)
+            xl, yl, zl = (torch.zeros(sp.ndof, dtype=torch.float64, device="cuda") for _ in range(3))
+            xl[:nt] = xd
+            torch.cuda.synchronize()
+            for scatter in (0, 1):
+                op.set_option("scatter", scatter)
+                op.Mult(xl, yl)                                   # P on x, then one symmetric exchange
+                ctx.sync()
+                err = np.linalg.norm(yl.cpu().numpy() - yg[mine]) / np.linalg.norm(yg)
+                ok &= err < 1e-12
+                op.set_option("ghost_in", 1)
+                for rep in range(4):                              # repeated: double-buffered receive areas, epochs
+                    op.Mult(yl, zl)
+                ctx.sync()
+                op.set_option("ghost_in", 0)
+                zz = P.pa_op(True).mult(yg)
+                err2 = np.linalg.norm(zl.cpu().numpy() - zz[mine]) / np.linalg.norm(zz)
+                ok &= err2 < 1e-12
+                print(f"[rank {rank}] symmetric exchange scatter={scatter}: whole local vector err {err:.2e}, chained apply without P {err2:.2e}", flush=True)
+            op.set_option("scatter", 1)
+            op.set_option("tail", 0)
+            # RecoverFEMSolution: u_L = P x_T
+            ul = torch.zeros(sp.ndof, dtype=torch.float64, device="cuda")
+            sp.prolongate(xd, ul)
+            ctx.sync()
+            ok &= np.array_equal(ul.cpu().numpy(), xg[mine])
         # Jacobi diagonal (P^T-summed) and distributed GMRES
         dd = torch.zeros(nt, dtype=torch.float64, device="cuda")
         op.AssembleDiagonal(dd)
@@ -133,6 +168,42 @@ def main():
         print(f"[rank {rank}] diag err {err:.2e} gmres iters {s.GetNumIterations()}/{info['iters']} hist err {herr:.2e} sol err {serr:.2e}", flush=True)
         nrm = ctx.norm2(xd)
         ok &= abs(nrm - np.linalg.norm(xg)) < 1e-12 * np.linalg.norm(xg)      # all-reduced dot over T-dofs
+        # same solve with ncclAllReduce for the Krylov scalars, and with a non-zero initial guess
+        op.set_option("allreduce", 0)
+        xs2 = torch.zeros(nt, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        s.Mult(bd, xs2)
+        ctx.sync()
+        ok &= s.GetNumIterations() == info["iters"] and np.linalg.norm((xs2 - xs).cpu().numpy()) <= 1e-9 * np.linalg.norm(xs_g)
+        op.set_option("allreduce", 1)
+        x0g = 0.5 * xs_g
+        xr_g, info0 = P.pa_op(True).gmres(bg, dinv=1 / dg, x0=x0g, variant=0, rtol=1e-10, atol=1e-12, max_it=500)
+        xs2.copy_(torch.from_numpy(x0g[mine[:nt]]).cuda())
+        torch.cuda.synchronize()
+        s.iterative_mode = True
+        s.Mult(bd, xs2)
+        ctx.sync()
+        s.iterative_mode = False
+        h0 = np.max(np.abs(s.history - info0["hist"][:len(s.history)]) / info0["hist"][0]) if len(s.history) == len(info0["hist"]) else 1.0
+        ok &= s.GetNumIterations() == info0["iters"] and h0 < 1e-10
+        print(f"[rank {rank}] gmres with non-zero initial guess: iters {s.GetNumIterations()}/{info0['iters']} hist err {h0:.2e}", flush=True)
+        # CG on the symmetric part (mfem::CGSolver, mesh_recession_handler.cpp:270-276)
+        Pk = orc.Problem(3, p, args.mesh, perturb=0.1, kappa=1.0, vel=None, mass=None)
+        xk_g, infok = Pk.pa_op(True).cg(bg, rtol=1e-12, atol=0.0, max_it=500)
+        opk = cdm.ConvectionDiffusionOperator(sp, kappa=1.0, ess_dofs=ess)
+        opk.set_option("halo", args.halo)
+        cg = cdm.CGSolver(500, 1e-12, 0.0, jacobi=False)
+        cg.SetOperator(opk)
+        xk = torch.zeros(nt, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        cg.Mult(bd, xk)
+        ctx.sync()
+        mk = min(len(cg.history), len(infok["hist"]))
+        hk = np.max(np.abs(cg.history[:mk] - infok["hist"][:mk]) / infok["hist"][0])
+        kerr = np.linalg.norm(xk.cpu().numpy() - xk_g[mine[:nt]]) / np.linalg.norm(xk_g)
+        ok &= cg.GetConverged() and abs(cg.GetNumIterations() - infok["iters"]) <= 1 and hk < 1e-10 and kerr < 1e-9
+        print(f"[rank {rank}] cg iters {cg.GetNumIterations()}/{infok['iters']} hist err {hk:.2e} sol err {kerr:.2e}", flush=True)
+        del opk
         # linear form (P^T-assembled) and L2 error (ghost values via P, all-reduced) on the partitioned space
         fn = lambda x: 1.0 + np.sin(2.3 * x[..., 0]) * np.cos(1.7 * x[..., 1]) + 0.5 * x[..., 2] ** 2
         lf_g = P.domain_lf(fn(P.rule_coords(p + 1)))
@@ -163,7 +234,7 @@ def main():
             herr = np.max(np.abs(s.history - info["hist"][:len(s.history)]) / info["hist"][0]) if len(s.history) == len(info["hist"]) else 1.0
             ok &= s.GetConverged() and s.GetNumIterations() == info["iters"] and herr < 1e-10
             print(f"[rank {rank}] peer-memory halo: gmres iters {s.GetNumIterations()}/{info['iters']} hist err {herr:.2e}", flush=True)
-            op.set_option("halo", 0)
+            op.set_option("halo", args.halo)
     else:
         # host emulation of cdm_halo_P / cdm_halo_PT with gloo, element work by the oracle
         lvx, lev, lbv, lba = lm.arrays()
@@ -217,6 +288,46 @@ def main():
         err = np.linalg.norm(yL[:nt] - yg[mine[:nt]]) / np.linalg.norm(yg)
         ok &= err < 1e-12
         print(f"[rank {rank}] host-emulated partitioned apply rel err {err:.2e} (ntrue {nt}, ghosts {sp.ndof - nt})", flush=True)
+        # the symmetric exchange (default GPU protocol): every sharer sends its partial sums to every other sharer and
+        # adds all contributions in rank order -> the WHOLE local vector (ghosts included) equals the oracle's result,
+        # bitwise identical on all sharers
+        speers, sdof, soff, ssrc = sp.sym_plan()
+        assert sorted(r for r, _, _ in speers) == [r for r, _, _ in speers] and rank not in [r for r, _, _ in speers]
+        assert np.array_equal(np.unique(sdof), np.flatnonzero(shared))          # exactly the shared dofs, each once
+        yS = np.zeros(sp.ndof)
+        L.orc_pa_apply(3, p, sp.ne, sp.ndof, g, o, i, orc._opt(Dd), orc._opt(Dc), orc._opt(Dm), z, yS)
+        total = sum(len(idx) for _, _, idx in speers)
+        recv = np.zeros(total)
+        reqs, bufs = [], []
+        for peer, off, idx in speers:
+            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(yS[idx])), peer))
+            t = torch.zeros(len(idx), dtype=torch.float64)
+            reqs.append(dist.irecv(t, peer))
+            bufs.append((off, t))
+        for r in reqs:
+            r.wait()
+        for off, t in bufs:
+            recv[off:off + len(t)] = t.numpy()
+        own = yS.copy()
+        for k in range(len(sdof)):
+            acc = 0.0
+            for j in range(soff[k], soff[k + 1]):
+                acc += own[sdof[k]] if ssrc[j] < 0 else recv[ssrc[j]]
+            yS[sdof[k]] = acc
+        yS[essm] = xL[essm]
+        err = np.linalg.norm(yS - yg[mine]) / np.linalg.norm(yg)
+        ok &= err < 1e-12
+        # bitwise agreement between sharers: compare my shared values with each peer's copy
+        reqs, bufs = [], []
+        for peer, off, idx in speers:
+            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(yS[idx])), peer))
+            t = torch.zeros(len(idx), dtype=torch.float64)
+            reqs.append(dist.irecv(t, peer))
+            bufs.append((idx, t))
+        for r in reqs:
+            r.wait()
+        ok &= all(np.array_equal(yS[idx], t.numpy()) for idx, t in bufs)
+        print(f"[rank {rank}] host-emulated symmetric exchange rel err {err:.2e} ({len(speers)} peers, {len(sdof)} shared dofs)", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda" if gpu else "cpu")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -17,10 +17,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(nproc, mode, order, n=(6, 5, 4)):
+def _run(nproc, mode, order, n=(6, 5, 4), extra=()):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "dist_check.py"), "--mode", mode, "--order", str(order), "--mesh", *map(str, n)]
+           os.path.join(ROOT, "tests", "dist_check.py"), "--mode", mode, "--order", str(order), "--mesh", *map(str, n), *extra]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
@@ -31,6 +31,7 @@ def test_partitioned_apply_gloo(nproc, order, mesh):
     """2x1x1, 2x2x1 and 2x2x2 boxes (the last one has face, edge and corner neighbours: 7 peers per rank)"""
     out = _run(nproc, "cpu", order, n=mesh)
     assert out.count("host-emulated partitioned apply") == nproc
+    assert out.count("host-emulated symmetric exchange") == nproc
 
 
 @pytest.mark.gpu
@@ -40,5 +41,7 @@ def test_partitioned_apply_and_gmres_nccl():
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run through gpurun --gpus 2)")
     nproc = 8 if n >= 8 else (4 if n >= 4 else 2)
-    out = _run(nproc, "gpu", 3, n=(8, 6, 6))
-    assert out.count("gmres iters") == nproc
+    out = _run(nproc, "gpu", 3, n=(8, 6, 6), extra=("--p2p",))          # default protocol: symmetric peer-memory exchange
+    assert out.count("cg iters") == nproc and out.count("chained apply without P") == 2 * nproc
+    out = _run(nproc, "gpu", 3, n=(8, 6, 6), extra=("--halo", "0"))     # P / P^T over NCCL
+    assert out.count("cg iters") == nproc
