@@ -215,6 +215,47 @@ def main():
         e_l = sp.l2_error(xd, fn(sp.rule_coords(p + 2)))
         ok &= lerr < 1e-12 and abs(e_l - e_g) < 1e-12 * e_g
         print(f"[rank {rank}] linear form err {lerr:.2e}  L2 error {e_l:.12e} vs {e_g:.12e}", flush=True)
+        # backward-Euler time steps (BASELINE config 3 semantics, linear_convection_diffusion_1D.cpp:537-572) on the
+        # partitioned mesh: mass apply, boundary values on the x faces, RHS elimination, GMRES -- against the oracle
+        # doing the same on the un-partitioned mesh
+        dt, pe = 1e-2, 10.0
+        Pm = orc.Problem(3, p, args.mesh, perturb=0.1, kappa=None, vel=None, mass=1.0, ess_attrs=(3, 5))
+        Pb = orc.Problem(3, p, args.mesh, perturb=0.1, kappa=dt / pe, vel=(1.0, 0.0, 0.0), alpha=dt, mass=1.0, ess_attrs=(3, 5))
+        mk = np.zeros(6, np.int32); mk[[2, 4]] = 1
+        ess2 = sp.essential_dofs(mk)
+        assert np.all(Pb.ess_mark[mine[ess2]] == 1) and Pb.ess_mark[mine].sum() == len(ess2)
+        mform = cdm.ConvectionDiffusionOperator(sp, mass=1.0)
+        bform = cdm.ConvectionDiffusionOperator(sp, kappa=dt / pe, vel=(1.0, 0.0, 0.0), alpha=dt, mass=1.0, ess_dofs=ess2)
+        for o in (mform, bform):
+            o.set_option("halo", args.halo)
+            o.set_option("tail", 1)
+        bs = cdm.GMRESSolver(cdm.GMRES_PETSC, 0, 500, 1e-10, 1e-12, jacobi=True)
+        bs.SetOperator(bform)
+        ref_b = Pb.pa_op(True)
+        db = np.where(Pb.ess_mark, 1.0, Pb.pa_diag())
+        c_g = np.zeros(P.ndof)
+        c_l, rhs_l, sol_l, g_l = (torch.zeros(sp.ndof, dtype=torch.float64, device="cuda") for _ in range(4))
+        essd2 = torch.from_numpy(ess2).cuda()
+        Xg = P.coords()
+        torch.cuda.synchronize()
+        for step in (1, 2, 3):
+            gb = np.where(Pb.ess_mark, np.cos(3.0 * Xg[:, 1] + step) * (1.0 - Xg[:, 0]), 0.0)      # time-dependent Dirichlet data
+            rhs_g = Pm.pa_apply(c_g)
+            ref_b.eliminate_rhs(gb, rhs_g)
+            c_new, ib = ref_b.gmres(rhs_g, dinv=1 / db, variant=0, rtol=1e-10, atol=1e-12, max_it=500)
+            mform.MultUnconstrained(c_l, rhs_l)
+            sp.project_dofs(essd2, gb[mine[ess2]], g_l)
+            bform.EliminateRHS(g_l, rhs_l)
+            bs.Mult(rhs_l, sol_l)
+            ctx.sync()
+            c_l.copy_(sol_l)
+            torch.cuda.synchronize()
+            c_g = c_new
+            hb = np.max(np.abs(bs.history - ib["hist"][:len(bs.history)]) / ib["hist"][0]) if len(bs.history) == len(ib["hist"]) else 1.0
+            eb = np.linalg.norm(sol_l[:nt].cpu().numpy() - c_new[mine[:nt]]) / np.linalg.norm(c_new)
+            ok &= bs.GetConverged() and bs.GetNumIterations() == ib["iters"] and hb < 1e-10 and eb < 1e-9
+            print(f"[rank {rank}] backward-Euler step {step}: gmres iters {bs.GetNumIterations()}/{ib['iters']} hist err {hb:.2e} sol err {eb:.2e}", flush=True)
+        del mform, bform
         if args.p2p:
             # the same apply / GMRES with the shared dofs exchanged through peer memory (NVLink stores + flags)
             op.set_option("halo", 1)

@@ -43,5 +43,6 @@ def test_partitioned_apply_and_gmres_nccl():
     nproc = 8 if n >= 8 else (4 if n >= 4 else 2)
     out = _run(nproc, "gpu", 3, n=(8, 6, 6), extra=("--p2p",))          # default protocol: symmetric peer-memory exchange
     assert out.count("cg iters") == nproc and out.count("chained apply without P") == 2 * nproc
+    assert out.count("backward-Euler step") == 3 * nproc
     out = _run(nproc, "gpu", 3, n=(8, 6, 6), extra=("--halo", "0"))     # P / P^T over NCCL
     assert out.count("cg iters") == nproc
