@@ -131,7 +131,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=66, help="elements per axis per GPU (66 -> 7 880 599 dofs, config 2)")
+    ap.add_argument("--n", "--elems", dest="n", type=int, default=66, help="elements per axis per GPU (66 -> 7 880 599 dofs, config 2)")
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--kernel", type=int, default=-1)
     ap.add_argument("--scatter", type=int, default=-1)

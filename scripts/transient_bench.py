@@ -38,7 +38,7 @@ def exact_concentration(x, t, pe):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=155)
+    ap.add_argument("--n", "--elems", dest="n", type=int, default=155)   # --elems: unambiguous under torch.distributed.run
     ap.add_argument("--order", type=int, default=2)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--pe", type=float, default=10.0)
