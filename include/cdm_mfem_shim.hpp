@@ -16,6 +16,7 @@
 #pragma once
 #include "cdm_b200.h"
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <functional>
 #include <map>
@@ -61,10 +62,11 @@ public:
    ~Vector() { Destroy(); }
    Vector(const Vector &) = delete;
    Vector &operator=(const Vector &) = delete;
-   void SetSize(const Device &dev, int64_t n)
+   void SetSize(const Device &dev, int64_t n) { SetSizeOn(dev.ctx(), n); }
+   void SetSizeOn(cdm_ctx *ctx, int64_t n)
    {
       Destroy();
-      ctx_ = dev.ctx(); n_ = n;
+      ctx_ = ctx; n_ = n;
       check(ctx_, cdm_vec_alloc(ctx_, n, &d_), "cdm_vec_alloc");
       check(ctx_, cdm_vec_set(ctx_, n, 0.0, d_), "cdm_vec_set");
    }
@@ -77,8 +79,11 @@ public:
    std::vector<double> HostCopy() const { std::vector<double> h(n_); GetToHost(h.data()); return h; }
    void Add(double a, const Vector &x) { check(ctx_, cdm_axpy(ctx_, n_, a, x.d_, d_), "cdm_axpy"); }   // *this += a x
    void Assign(const Vector &x) { *this = 0.0; Add(1.0, x); }                                          // *this = x (device copy)
+   void Scale(double a) { check(ctx_, cdm_add(ctx_, n_, d_, a - 1.0, d_, d_), "cdm_add"); }              // *this *= a  (x + (a-1) x)
+   void CopyFromDevice(const double *src) { *this = 0.0; check(ctx_, cdm_axpy(ctx_, n_, 1.0, src, d_), "cdm_axpy"); }
    double operator*(const Vector &y) const { double r; check(ctx_, cdm_dot(ctx_, n_, d_, y.d_, &r), "cdm_dot"); return r; }
    double Norml2() const { double r; check(ctx_, cdm_norm2(ctx_, n_, d_, &r), "cdm_norm2"); return r; }
+   cdm_ctx *ctx() const { return ctx_; }
 private:
    void Destroy() { if (d_) { cdm_vec_free(ctx_, d_); d_ = nullptr; } }
    cdm_ctx *ctx_ = nullptr;
@@ -247,9 +252,25 @@ public:
    { vel_c_ = velocity; vel_ = {CDM_COEFF_CONST, (int)velocity.size(), vel_c_.data()}; alpha_ = alpha; }
    void AddConvectionIntegratorQpt(const std::vector<double> &per_qpt, double alpha = 1.0)
    { vel_c_ = per_qpt; vel_ = {CDM_COEFF_QPT, fes_.Dimension(), vel_c_.data()}; alpha_ = alpha; }
-   // a.AddDomainIntegrator(new MassIntegrator(s))
-   void AddMassIntegrator(double s) { mass_c_ = {s}; mass_ = {CDM_COEFF_CONST, 1, mass_c_.data()}; }
-   void AddMassIntegrator(const std::vector<double> &per_qpt) { mass_c_ = per_qpt; mass_ = {CDM_COEFF_QPT, 1, mass_c_.data()}; }
+   // a.AddDomainIntegrator(new MassIntegrator(s)).  May be called several times: the reference's ALE form carries two
+   // mass integrators, Mass(J) and Mass(-div phi) (diffusion_mms_ale.cpp:1018-1021); mass integrators are additive in
+   // their coefficient, so the coefficients are summed point by point and ONE D_mass stream is stored and read.
+   void AddMassIntegrator(double s)
+   {
+      if (mass_.kind == CDM_COEFF_NONE) { mass_c_ = {s}; mass_ = {CDM_COEFF_CONST, 1, mass_c_.data()}; }
+      else { for (double &v : mass_c_) { v += s; } }
+   }
+   void AddMassIntegrator(const std::vector<double> &per_qpt)
+   {
+      if (mass_.kind == CDM_COEFF_NONE) { mass_c_ = per_qpt; }
+      else if (mass_.kind == CDM_COEFF_CONST) { const double c0 = mass_c_[0]; mass_c_ = per_qpt; for (double &v : mass_c_) { v += c0; } }
+      else
+      {
+         if (per_qpt.size() != mass_c_.size()) { throw std::runtime_error("AddMassIntegrator: per-point arrays of different length"); }
+         for (size_t i = 0; i < per_qpt.size(); i++) { mass_c_[i] += per_qpt[i]; }
+      }
+      mass_ = {CDM_COEFF_QPT, 1, mass_c_.data()};
+   }
    void SetEssentialTrueDofs(const std::vector<int32_t> &ess) { ess_ = ess; }
    // a.SetAssemblyLevel(AssemblyLevel::PARTIAL / LEGACY): PARTIAL (default) is the matrix-free operator;
    // LEGACY assembles the sparse matrix the application builds today and applies it as a CSR SpMV
@@ -277,6 +298,19 @@ public:
    void FormLinearSystem(const Vector &u, Vector &b) const
    { check(fes_.ctx(), cdm_eliminate_rhs(op_, u.Read(), b.ReadWrite()), "cdm_eliminate_rhs"); }
    void AssembleDiagonal(Vector &d) const { check(fes_.ctx(), cdm_operator_diag(op_, d.ReadWrite()), "cdm_operator_diag"); }
+   // a.RecoverFEMSolution(X, b, u): u_L = P X (linear_convection_diffusion_2D.cpp:377).  u has LocalSize() entries: the
+   // true dofs followed by the ghost dofs of this rank, whose values are fetched from their owners.
+   int64_t LocalSize() const { return cdm_space_local_size(fes_.handle()); }
+   void RecoverFEMSolution(const Vector &X, const Vector & /*b*/, Vector &u) const
+   {
+      if (u.Size() < LocalSize()) { throw std::runtime_error("RecoverFEMSolution: u must have LocalSize() entries"); }
+      check(fes_.ctx(), cdm_prolongate(fes_.handle(), X.Read(), u.ReadWrite()), "cdm_prolongate");
+   }
+   // BilinearFormIntegrator-level entry points (AssemblyLevel::PARTIAL): E-vectors [ne][nd] in, E-vectors out
+   void AddMultPA(const Vector &xE, Vector &yE) const
+   { check(fes_.ctx(), cdm_integrator_add_mult_pa(op_, xE.Read(), yE.ReadWrite()), "cdm_integrator_add_mult_pa"); }
+   void AssembleDiagonalPA(Vector &diagE) const
+   { check(fes_.ctx(), cdm_integrator_assemble_diagonal_pa(op_, diagE.ReadWrite()), "cdm_integrator_assemble_diagonal_pa"); }
    cdm_op *handle() const { return op_; }
    cdm_ctx *ctx() const { return fes_.ctx(); }
 private:
@@ -289,7 +323,10 @@ private:
    AssemblyLevel level_ = AssemblyLevel::PARTIAL;
 };
 
-// mfem::IterativeSolver surface
+// mfem::IterativeSolver surface.  SetOperator takes any cdm::Operator, like mfem::Solver::SetOperator(const Operator &):
+// a ConvectionDiffusionForm runs the fused device-resident Krylov drivers (cdm_gmres / cdm_cg: lazily normalised basis,
+// fused multi-dot / multi-axpy, ghost-consistent vectors); any other Operator runs the same algorithms through its
+// virtual Mult and the C-ABI vector kernels, with an optional preconditioner Operator (SetPreconditioner).
 class IterativeSolver
 {
 public:
@@ -298,8 +335,13 @@ public:
    void SetAbsTol(double v) { o_.atol = v; }
    void SetMaxIter(int v) { o_.max_it = v; }
    void SetPrintLevel(int) {}
-   void SetJacobi(bool on) { o_.jacobi = on ? 1 : 0; }          // -pc_type jacobi
-   void SetOperator(const ConvectionDiffusionForm &op) { op_ = &op; }
+   void SetJacobi(bool on) { o_.jacobi = on ? 1 : 0; }          // -pc_type jacobi (ConvectionDiffusionForm only)
+   void SetOperator(const Operator &op)
+   {
+      gen_ = &op;
+      op_ = dynamic_cast<const ConvectionDiffusionForm *>(&op);
+   }
+   void SetPreconditioner(const Operator &M) { prec_ = &M; }    // generic operators: z = M r through M.Mult
    bool iterative_mode = false;                                  // PetscLinearSolver default
    int GetNumIterations() const { return r_.iters; }
    bool GetConverged() const { return r_.converged != 0; }
@@ -316,9 +358,12 @@ protected:
       check(op_->ctx(), fn(op_->handle(), b.Read(), x.ReadWrite(), &o_, &r_, hist_.data()), what);
       hist_.resize(r_.hist_len);
    }
+   // z = M^{-1} r for a generic operator
+   void Precondition(const Vector &r, Vector &z) const { if (prec_) { prec_->Mult(r, z); } else { z.Assign(r); } }
    cdm_krylov_opts o_{CDM_GMRES_PETSC, 0, 500, 1e-10, 1e-12, 1, 1};
    cdm_krylov_result r_{0, 0, 0.0, 0, 0.0};
    const ConvectionDiffusionForm *op_ = nullptr;
+   const Operator *gen_ = nullptr, *prec_ = nullptr;
    std::vector<double> hist_;
 };
 
@@ -328,7 +373,106 @@ class GMRESSolver : public IterativeSolver
 public:
    explicit GMRESSolver(int variant = CDM_GMRES_PETSC) { o_.variant = variant; }
    void SetKDim(int m) { o_.restart = m; }
-   void Mult(const Vector &b, Vector &x) override { Run(cdm_gmres, b, x, "cdm_gmres"); }
+   void Mult(const Vector &b, Vector &x) override
+   {
+      if (op_ && !prec_) { Run(cdm_gmres, b, x, "cdm_gmres"); return; }
+      if (!gen_) { throw std::runtime_error("SetOperator has not been called"); }
+      Generic(b, x);
+   }
+private:
+   // left-preconditioned restarted GMRES through Operator::Mult: classical Gram-Schmidt with
+   // one fused multi-dot + multi-axpy per step for the PETSc variant, modified Gram-Schmidt for the mfem variant
+   void Generic(const Vector &b, Vector &x)
+   {
+      cdm_ctx *ctx = b.ctx();
+      const int64_t n = b.Size();
+      const int m = o_.restart > 0 ? o_.restart : (o_.variant == CDM_GMRES_PETSC ? 30 : 50);
+      double *V = nullptr;
+      check(ctx, cdm_vec_alloc(ctx, (int64_t)(m + 1) * n, &V), "cdm_vec_alloc");
+      struct Free { cdm_ctx *c; double *p; ~Free() { cdm_vec_free(c, p); } } guard{ctx, V};
+      Vector w, t, vj;
+      w.SetSizeOn(ctx, n); t.SetSizeOn(ctx, n); vj.SetSizeOn(ctx, n);
+      std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), s(m + 1), yv(m), hc(m + 2);
+      hist_.clear();
+      int it = 0, conv = 0;
+      double rnorm = 0.0, ttol = 0.0;
+      bool first = true;
+      if (!iterative_mode) { x = 0.0; }
+      auto col = [&](int j) { return V + (int64_t)j * n; };
+      while (true)
+      {
+         if (first && !iterative_mode) { Precondition(b, w); }
+         else { gen_->Mult(x, t); t.Scale(-1.0); t.Add(1.0, b); Precondition(t, w); }
+         double b2; check(ctx, cdm_dot(ctx, n, w.Read(), w.Read(), &b2), "cdm_dot");
+         const double beta = std::sqrt(b2);
+         rnorm = beta;
+         if (first)
+         {
+            double ref = beta;
+            if (iterative_mode && o_.variant == CDM_GMRES_PETSC) { Precondition(b, t); ref = t.Norml2(); }
+            ttol = std::max(o_.rtol * ref, o_.atol);
+            hist_.push_back(beta);
+            first = false;
+         }
+         if (rnorm <= ttol) { conv = 1; break; }
+         if (it >= o_.max_it) { break; }
+         check(ctx, cdm_vec_set(ctx, n, 0.0, col(0)), "cdm_vec_set");
+         check(ctx, cdm_axpy(ctx, n, 1.0 / beta, w.Read(), col(0)), "cdm_axpy");
+         std::fill(s.begin(), s.end(), 0.0);
+         s[0] = beta;
+         int j = 0;
+         while (j < m && it < o_.max_it)
+         {
+            vj.CopyFromDevice(col(j));
+            gen_->Mult(vj, t);
+            Precondition(t, w);
+            if (o_.variant == CDM_GMRES_PETSC)
+            {
+               check(ctx, cdm_mdot(ctx, n, j + 1, w.Read(), V, n, hc.data()), "cdm_mdot");
+               check(ctx, cdm_maxpy(ctx, n, j + 1, hc.data(), V, n, w.ReadWrite()), "cdm_maxpy");
+            }
+            else
+            {
+               for (int i = 0; i <= j; i++)
+               {
+                  check(ctx, cdm_dot(ctx, n, w.Read(), col(i), &hc[i]), "cdm_dot");
+                  check(ctx, cdm_axpy(ctx, n, -hc[i], col(i), w.ReadWrite()), "cdm_axpy");
+               }
+            }
+            const double hn = w.Norml2();
+            check(ctx, cdm_vec_set(ctx, n, 0.0, col(j + 1)), "cdm_vec_set");
+            if (hn > 0.0) { check(ctx, cdm_axpy(ctx, n, 1.0 / hn, w.Read(), col(j + 1)), "cdm_axpy"); }
+            hc[j + 1] = hn;
+            for (int i = 0; i < j; i++)
+            {
+               const double a = cs[i] * hc[i] + sn[i] * hc[i + 1];
+               hc[i + 1] = -sn[i] * hc[i] + cs[i] * hc[i + 1];
+               hc[i] = a;
+            }
+            const double den = std::hypot(hc[j], hc[j + 1]);
+            cs[j] = hc[j] / den; sn[j] = hc[j + 1] / den;
+            hc[j] = den; hc[j + 1] = 0.0;
+            s[j + 1] = -sn[j] * s[j];
+            s[j] = cs[j] * s[j];
+            for (int i = 0; i <= j; i++) { H[(size_t)j * (m + 1) + i] = hc[i]; }
+            j++; it++;
+            rnorm = std::fabs(s[j]);
+            hist_.push_back(rnorm);
+            if (rnorm <= ttol) { conv = 1; break; }
+            if (hn == 0.0) { break; }
+         }
+         for (int i = j - 1; i >= 0; i--)
+         {
+            double a = s[i];
+            for (int k = i + 1; k < j; k++) { a -= H[(size_t)k * (m + 1) + i] * yv[k]; }
+            yv[i] = a / H[(size_t)i * (m + 1) + i];
+         }
+         for (int i = 0; i < j; i++) { yv[i] = -yv[i]; }              // cdm_maxpy subtracts
+         check(ctx, cdm_maxpy(ctx, n, j, yv.data(), V, n, x.ReadWrite()), "cdm_maxpy");
+         if (conv || it >= o_.max_it) { break; }
+      }
+      r_.iters = it; r_.converged = conv; r_.final_norm = rnorm; r_.hist_len = (int)hist_.size(); r_.seconds = 0.0;
+   }
 };
 
 // mfem::CGSolver (rel 1e-12, abs 0, max 500 at mesh_recession_handler.cpp:271-273)
@@ -336,6 +480,56 @@ class CGSolver : public IterativeSolver
 {
 public:
    CGSolver() { o_.rtol = 1e-12; o_.atol = 0.0; o_.jacobi = 0; }
-   void Mult(const Vector &b, Vector &x) override { Run(cdm_cg, b, x, "cdm_cg"); }
+   void Mult(const Vector &b, Vector &x) override
+   {
+      if (op_ && !prec_) { Run(cdm_cg, b, x, "cdm_cg"); return; }
+      if (!gen_) { throw std::runtime_error("SetOperator has not been called"); }
+      Generic(b, x);
+   }
+private:
+   // mfem::CGSolver::Mult through Operator::Mult
+   void Generic(const Vector &b, Vector &x)
+   {
+      cdm_ctx *ctx = b.ctx();
+      const int64_t n = b.Size();
+      Vector r, d, z;
+      r.SetSizeOn(ctx, n); d.SetSizeOn(ctx, n); z.SetSizeOn(ctx, n);
+      hist_.clear();
+      int it = 0, conv = 0;
+      if (!iterative_mode) { x = 0.0; r.Assign(b); }
+      else { gen_->Mult(x, r); r.Scale(-1.0); r.Add(1.0, b); }
+      Precondition(r, d);
+      double nom = d * r, betanom = nom, den = 0.0;
+      const double r0 = std::max(nom * o_.rtol * o_.rtol, o_.atol * o_.atol);
+      hist_.push_back(nom);
+      if (nom <= r0) { conv = 1; }
+      else
+      {
+         gen_->Mult(d, z);
+         den = z * d;
+         if (den > 0.0)
+         {
+            for (it = 1;; it++)
+            {
+               const double alpha = nom / den;
+               x.Add(alpha, d);
+               r.Add(-alpha, z);
+               if (prec_) { prec_->Mult(r, z); betanom = r * z; }
+               else { betanom = r * r; }
+               hist_.push_back(betanom);
+               if (betanom <= r0) { conv = 1; break; }
+               if (it >= o_.max_it) { break; }
+               const double beta = betanom / nom;
+               d.Scale(beta);
+               d.Add(1.0, prec_ ? z : r);
+               gen_->Mult(d, z);
+               den = d * z;
+               if (den <= 0.0) { break; }
+               nom = betanom;
+            }
+         }
+      }
+      r_.iters = it; r_.converged = conv; r_.final_norm = std::sqrt(std::fabs(betanom)); r_.hist_len = (int)hist_.size(); r_.seconds = 0.0;
+   }
 };
 }  // namespace cdm

@@ -84,3 +84,16 @@ def test_transient_heat_driver_tracks_manufactured_solution(orc, dim, n, order):
         assert abs(final - want) <= 5e-6 * want, (final, want)       # printed with 7 digits; GMRES rtol 1e-10 vs direct solve
         finals.append(final)
     assert 0.45 < finals[1] / finals[0] < 0.55, finals
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,order", [(6, 3), (7, 2)])
+def test_generic_operator_solvers_mass_list_recover_and_integrator_level(n, order):
+    """examples/shim_generic_operator.cpp: Solver::SetOperator(const Operator &) + SetPreconditioner on a user-defined
+    Operator reproduce the fused drivers; two MassIntegrators on one form (diffusion_mms_ale.cpp:1018-1021);
+    RecoverFEMSolution (linear_convection_diffusion_2D.cpp:377); AddMultPA / AssembleDiagonalPA on E-vectors"""
+    _build()
+    exe = os.path.join(ROOT, "examples", "shim_generic_operator")
+    r = subprocess.run([exe, str(n), str(order)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all shim checks passed" in r.stdout
