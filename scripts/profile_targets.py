@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--only", default="", help="comma-separated target names")
+    ap.add_argument("--gmres-steps", type=int, default=4, help="GMRES steps inside the profiled range (0: skip)")
     args = ap.parse_args()
     import torch
     cdm = importlib.import_module("continuum-mechanics-mfem_b200")
@@ -71,10 +72,12 @@ def main():
             timed("diag_p3", lambda: op.AssembleDiagonal(d))
             b = torch.sin(0.5 + 0.11 * torch.arange(sp.ndof, dtype=torch.float64, device="cuda"))
             xs = torch.zeros_like(b)
-            s = cdm.GMRESSolver(cdm.GMRES_PETSC, 12, 12, 0.0, 0.0, jacobi=True)
-            s.SetOperator(op)
-            timed("gmres12_p3", lambda: s.Mult(b, xs), warm=1)
-            del s, b, xs, d
+            if args.gmres_steps > 0:
+                s = cdm.GMRESSolver(cdm.GMRES_PETSC, args.gmres_steps, args.gmres_steps, 0.0, 0.0, jacobi=True)
+                s.SetOperator(op)
+                timed(f"gmres{args.gmres_steps}_p3", lambda: s.Mult(b, xs), warm=1)
+                del s
+            del b, xs, d
         del op, sp, mesh, x, y
         torch.cuda.empty_cache()
     for p in (2, 3):
