@@ -74,6 +74,11 @@ SIGNATURES = {
     "cdm_comm_rank": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_ci)]),
     "cdm_mesh_cartesian": (_ci, [_vp, _ci, C.POINTER(_i64), C.POINTER(_cd), _cd, _pp]),
     "cdm_mesh_from_arrays": (_ci, [_vp, _ci, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _pp]),
+    "cdm_mesh_from_arrays_simplex": (_ci, [_vp, _ci, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _pp]),
+    "cdm_mesh_read_gmsh": (_ci, [_vp, C.c_char_p, _ci, _pp]),
+    "cdm_mesh_cartesian_sfc": (_ci, [_vp, _ci, C.POINTER(_i64), C.POINTER(_cd), _cd, _pp]),
+    "cdm_grid_sfc_ordering": (_ci, [_ci, C.POINTER(_i64), _vp]),
+    "cdm_mesh_geometry": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_ci), C.POINTER(_ci)]),
     "cdm_mesh_sizes": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "cdm_mesh_get": (_ci, [_vp, _vp, _vp, _vp, _vp]),
     "cdm_mesh_destroy": (_ci, [_vp]),
@@ -125,6 +130,18 @@ SIGNATURES = {
     "cdm_domain_lf": (_ci, [_vp, _ci, _vp, _cd, _ci, _vp]),
     "cdm_l2_error": (_ci, [_vp, _ci, _vp, _vp, C.POINTER(_cd)]),
     "cdm_vec_set_indexed": (_ci, [_vp, _i64, _vp, _vp, _vp]),
+    "cdm_config_load": (_ci, [C.c_char_p, _pp]),
+    "cdm_config_destroy": (_ci, [_vp]),
+    "cdm_config_has": (_ci, [_vp, C.c_char_p]),
+    "cdm_config_get_string": (_ci, [_vp, C.c_char_p, C.c_char_p, _ci]),
+    "cdm_config_get_double": (_ci, [_vp, C.c_char_p, C.POINTER(_cd)]),
+    "cdm_config_get_int": (_ci, [_vp, C.c_char_p, C.POINTER(_ci)]),
+    "cdm_config_get_bool": (_ci, [_vp, C.c_char_p, C.POINTER(_ci)]),
+    "cdm_config_get_doubles": (_ci, [_vp, C.c_char_p, _vp, _ci, C.POINTER(_ci)]),
+    "cdm_write_paraview": (_ci, [_vp, C.c_char_p, C.c_char_p, _ci, _cd, _ci, _vp, _vp]),
+    "cdm_petsc_options_load": (_ci, [C.c_char_p, C.POINTER(KrylovOpts), C.POINTER(_ci)]),
+    "cdm_operator_ilu_apply": (_ci, [_vp, _vp, _vp]),
+    "cdm_operator_ilu_levels": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_ci)]),
     "cdm_launch_count": (_i64, [_vp]),
     "cdm_vec_alloc": (_ci, [_vp, _i64, _pp]),
     "cdm_vec_free": (_ci, [_vp, _vp]),
@@ -251,13 +268,40 @@ class Mesh:
         self.dim, self.nv, self.ne, self.nbe = dim.value, nv.value, ne.value, nbe.value
 
     @classmethod
-    def cartesian(cls, ctx, dim, n, size=None, perturb=0.0):
+    def cartesian(cls, ctx, dim, n, size=None, perturb=0.0, sfc_ordering=False):
+        """Mesh::MakeCartesian2D/3D; sfc_ordering=True lists the elements along the Hilbert curve (MFEM's inline meshes)"""
         n = list(n) if not np.isscalar(n) else [n] * dim
         nn = (C.c_int64 * 3)(*((n + [0] * 3)[:3]))
         ss = (C.c_double * 3)(*((list(size) + [1.0] * 3)[:3] if size is not None else [1.0] * 3))
         h = C.c_void_p()
-        ctx.check(lib().cdm_mesh_cartesian(ctx.h, dim, nn, ss, float(perturb), C.byref(h)))
+        fn = lib().cdm_mesh_cartesian_sfc if sfc_ordering else lib().cdm_mesh_cartesian
+        ctx.check(fn(ctx.h, dim, nn, ss, float(perturb), C.byref(h)))
         return cls(ctx, h)
+
+    @classmethod
+    def read_gmsh(cls, ctx, path, refine=True):
+        """mfem::Mesh(path, 1, refine) for Gmsh 2.2 ASCII files (linear_convection_diffusion_2D.cpp:290)"""
+        h = C.c_void_p()
+        ctx.check(lib().cdm_mesh_read_gmsh(ctx.h, os.fspath(path).encode(), 1 if refine else 0, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_arrays_simplex(cls, ctx, vx, ev, bv, battr):
+        vx = np.ascontiguousarray(vx, np.float64)
+        ev = np.ascontiguousarray(ev, np.int32)
+        bv = np.ascontiguousarray(bv, np.int32)
+        battr = np.ascontiguousarray(battr, np.int32)
+        h = C.c_void_p()
+        ctx.check(lib().cdm_mesh_from_arrays_simplex(ctx.h, vx.shape[1], vx.shape[0], _ptr(vx), ev.shape[0], _ptr(ev),
+                                                     bv.shape[0], _ptr(bv), _ptr(battr), C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def geometry(self):
+        """(geom, vertices per element, vertices per boundary element); geom 0 tensor, 1 simplex"""
+        g, a, b = C.c_int(), C.c_int(), C.c_int()
+        lib().cdm_mesh_geometry(self.h, C.byref(g), C.byref(a), C.byref(b))
+        return g.value, a.value, b.value
 
     @classmethod
     def from_arrays(cls, ctx, vx, ev, bv, battr):
@@ -277,9 +321,10 @@ class Mesh:
         return Mesh(self.ctx, h)
 
     def arrays(self):
+        _, nve, nvb = self.geometry
         vx = np.zeros((self.nv, self.dim))
-        ev = np.zeros((self.ne, 2 ** self.dim), np.int32)
-        bv = np.zeros((self.nbe, 2 ** (self.dim - 1)), np.int32)
+        ev = np.zeros((self.ne, nve), np.int32)
+        bv = np.zeros((self.nbe, nvb), np.int32)
         battr = np.zeros(self.nbe, np.int32)
         lib().cdm_mesh_get(self.h, _ptr(vx), _ptr(ev), _ptr(bv), _ptr(battr))
         return vx, ev, bv, battr
@@ -309,6 +354,9 @@ class H1Space:
         self.dim, self.order, self.ne, self.ndof = dim.value, p.value, ne.value, ndof_.value
         self.d1d, self.q1d, self.ntrue = d1d.value, q1d.value, ntrue.value
         self.nd, self.nq = self.d1d ** self.dim, self.q1d ** self.dim
+        self.simplex = mesh.geometry[0] == 1
+        if self.simplex:                      # order-p triangle, collapsed Gauss-Legendre rule with q1d^2 points
+            self.nd = (self.order + 1) * (self.order + 2) // 2
 
     def maps(self):
         """ElementRestriction gather_map / offsets / indices (int32)."""
@@ -424,6 +472,15 @@ class H1Space:
         self.ctx.check(lib().cdm_l2_error(self.h, q1d, _ptr(u), _ptr(uex_q), C.byref(r)))
         return r.value
 
+    def write_paraview(self, prefix, collection, fields, cycle=0, time=0.0):
+        """ParaViewDataCollection::Save (linear_convection_diffusion_2D.cpp:421-433); fields: {name: host L-vector}"""
+        names = list(fields)
+        arrs = [np.ascontiguousarray(fields[k], np.float64) for k in names]
+        cn = (C.c_char_p * len(names))(*[k.encode() for k in names])
+        cp = (C.c_void_p * len(names))(*[a.ctypes.data for a in arrs])
+        self.ctx.check(lib().cdm_write_paraview(self.h, os.fspath(prefix).encode(), collection.encode(), int(cycle), float(time),
+                                                len(names), cn, cp))
+
     def project_dofs(self, idx, vals, u):
         """u[idx] = vals (ProjectBdrCoefficient with vals = g at the dof coordinates of idx)"""
         if isinstance(idx, np.ndarray):
@@ -535,6 +592,15 @@ class ConvectionDiffusionOperator:
         """BilinearFormIntegrator::AssembleDiagonalPA: dE += element-wise diagonal"""
         self.ctx.check(lib().cdm_integrator_assemble_diagonal_pa(self.h, _ptr(dE)))
 
+    def ilu_apply(self, r, z):
+        """z = (LU)^{-1} r, ILU(0) of the assembled constrained matrix (-pc_type bjacobi -sub_pc_type ilu on one rank)"""
+        self.ctx.check(lib().cdm_operator_ilu_apply(self.h, _ptr(r), _ptr(z)))
+
+    def ilu_levels(self):
+        a, b = C.c_int(), C.c_int()
+        self.ctx.check(lib().cdm_operator_ilu_levels(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def AssembleDiagonal(self, d):
         self.ctx.check(lib().cdm_operator_diag(self.h, _ptr(d)))
 
@@ -560,8 +626,10 @@ class _IterativeSolver:
     """mfem::IterativeSolver surface: SetRelTol/SetAbsTol/SetMaxIter/SetOperator/Mult/Get*."""
     _fn = None
 
-    def __init__(self, variant=GMRES_PETSC, restart=0, max_it=500, rtol=1e-10, atol=1e-12, jacobi=True):
-        self.opts = KrylovOpts(variant, restart, max_it, rtol, atol, 1, 1 if jacobi else 0)
+    def __init__(self, variant=GMRES_PETSC, restart=0, max_it=500, rtol=1e-10, atol=1e-12, jacobi=True, pc=None):
+        # pc: None -> jacobi flag; "none" | "jacobi" | "ilu" (-pc_type bjacobi -sub_pc_type ilu, Input/petsc_circle.opts:6-8)
+        pcv = {None: 1 if jacobi else 0, "none": 0, "jacobi": 1, "ilu": 2, "bjacobi": 2}[pc]
+        self.opts = KrylovOpts(variant, restart, max_it, rtol, atol, 1, pcv)
         self.res = KrylovResult()
         self.op = None
         self.iterative_mode = False
@@ -590,9 +658,60 @@ class _IterativeSolver:
 class GMRESSolver(_IterativeSolver):
     _fn = "cdm_gmres"
 
+    @classmethod
+    def from_petsc_options(cls, path):
+        """MFEMInitializePetsc(..., petsc_options_file, ...) + PetscLinearSolver (linear_convection_diffusion_2D.cpp:268-282,368)"""
+        s = cls()
+        kt = C.c_int()
+        rc = lib().cdm_petsc_options_load(os.fspath(path).encode(), C.byref(s.opts), C.byref(kt))
+        if rc != OK:
+            raise CdmError(rc, f"cannot load PETSc options from {path}")
+        s.ksp_type = "cg" if kt.value == 1 else "gmres"
+        return s
+
 
 class CGSolver(_IterativeSolver):
     _fn = "cdm_cg"
 
     def __init__(self, max_it=500, rtol=1e-12, atol=0.0, jacobi=False):
         super().__init__(GMRES_MFEM, 0, max_it, rtol, atol, jacobi)
+
+
+class Config:
+    """LoadParams (linear_convection_diffusion_2D.cpp:62-127): flat `key: value` YAML; get() keeps the caller's default
+    when the key is absent, like `if (n["key"]) p.key = n["key"].as<T>()`."""
+
+    def __init__(self, path):
+        self.h = C.c_void_p()
+        rc = lib().cdm_config_load(os.fspath(path).encode(), C.byref(self.h))
+        if rc != OK:
+            raise CdmError(rc, f"cannot load {path}" + (" (nested YAML is not supported)" if rc == EUNSUP else ""))
+        self.path = os.fspath(path)
+
+    def has(self, key):
+        return bool(lib().cdm_config_has(self.h, key.encode()))
+
+    def get(self, key, default=None, kind=str):
+        if not self.has(key):
+            return default
+        if kind is str:
+            buf = C.create_string_buffer(4096)
+            lib().cdm_config_get_string(self.h, key.encode(), buf, 4096)
+            return buf.value.decode()
+        if kind is list:
+            n = C.c_int()
+            if lib().cdm_config_get_doubles(self.h, key.encode(), None, 0, C.byref(n)) != OK:
+                raise CdmError(EINVAL, f"YAML key {key} is not a sequence")
+            v = np.zeros(n.value)
+            lib().cdm_config_get_doubles(self.h, key.encode(), _ptr(v), n.value, C.byref(n))
+            return list(v)
+        v = {float: C.c_double, int: C.c_int, bool: C.c_int}[kind]()
+        fn = {float: lib().cdm_config_get_double, int: lib().cdm_config_get_int, bool: lib().cdm_config_get_bool}[kind]
+        if fn(self.h, key.encode(), C.byref(v)) != OK:
+            raise CdmError(EINVAL, f"YAML key {key} has no {kind.__name__} value")
+        return kind(v.value)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().cdm_config_destroy(self.h)
+            self.h = None

@@ -115,7 +115,7 @@ int cdm_sync(cdm_ctx *c)
 static int space_finish(cdm_ctx *ctx, const cdm_mesh *mesh, cdm_space *sp)
 {
    // per-element vertex coordinates (order-1 mesh nodes)
-   const int nvpe = (sp->dim == 2) ? 4 : 8;
+   const int nvpe = (sp->geom == 1) ? sp->dim + 1 : ((sp->dim == 2) ? 4 : 8);
    sp->elem_x.resize((size_t)sp->ne * nvpe * sp->dim);
    for (int64_t e = 0; e < sp->ne; e++)
    {
@@ -132,6 +132,13 @@ static int space_finish(cdm_ctx *ctx, const cdm_mesh *mesh, cdm_space *sp)
       if ((rc = upload(ctx, sp->offsets, &sp->offsets_dev))) { return rc; }
       if ((rc = upload(ctx, sp->indices, &sp->indices_dev))) { return rc; }
       if ((rc = upload(ctx, sp->elem_x, &sp->elem_x_dev))) { return rc; }
+      if (sp->geom == 1)
+      {
+         if ((rc = upload(ctx, sp->sB, &sp->sB_dev))) { return rc; }
+         if ((rc = upload(ctx, sp->sG, &sp->sG_dev))) { return rc; }
+         if ((rc = upload(ctx, sp->sqw, &sp->sqw_dev))) { return rc; }
+         if ((rc = upload(ctx, sp->sqx, &sp->sqx_dev))) { return rc; }
+      }
       if (!sp->peers.empty())
       {
          // fused exchange plan: one pack and one unpack kernel per phase, whatever the peer count.
@@ -181,8 +188,21 @@ static cdm_space *space_new(cdm_ctx *ctx, const cdm_mesh *mesh, int order)
    cdm_space *sp = new (std::nothrow) cdm_space;
    if (!sp) { return nullptr; }
    sp->ctx = ctx; sp->dim = mesh->dim; sp->p = order; sp->d1d = order + 1;
+   sp->geom = mesh->geom;
    sp->q1d = cdm_host_q1d(mesh->dim, order);
    sp->nd = ipow(sp->d1d, sp->dim); sp->nq = ipow(sp->q1d, sp->dim);
+   if (sp->geom == 1)
+   {
+      // order-p triangle: (p+1)(p+2)/2 nodes; collapsed Gauss-Legendre rule with p+1 points per direction (exact to
+      // degree 2p: the constant-coefficient integrands of all three integrators on affine triangles)
+      sp->q1d = order + 1;
+      sp->nd = (order + 1) * (order + 2) / 2; sp->nq = sp->q1d * sp->q1d;
+      sp->snodes.resize(2 * sp->nd); sp->sqx.resize(2 * sp->nq); sp->sqw.resize(sp->nq);
+      sp->sB.resize((size_t)sp->nq * sp->nd); sp->sG.resize((size_t)2 * sp->nq * sp->nd);
+      cdm_host_tri_nodes(order, sp->snodes.data());
+      cdm_host_tri_rule(sp->q1d, sp->sqx.data(), sp->sqw.data());
+      cdm_host_tri_basis(order, sp->nq, sp->sqx.data(), sp->sB.data(), sp->sG.data());
+   }
    sp->ne = mesh->ne; sp->nv = mesh->nv; sp->nbe = mesh->nbe;
    sp->B.resize(sp->q1d * sp->d1d); sp->G.resize(sp->q1d * sp->d1d);
    sp->qw.resize(sp->q1d); sp->qx.resize(sp->q1d); sp->nodes.resize(sp->d1d);
@@ -336,6 +356,13 @@ int cdm_space_create_h1(cdm_ctx *ctx, const cdm_mesh *mesh, int order, cdm_space
    cdm_space *sp = space_new(ctx, mesh, order);
    if (!sp) { return cdm_fail(ctx, CDM_ENOMEM, "out of memory"); }
    sp->class_off.assign(5, 0);
+   if (mesh->geom == 1)
+   {
+      if (mesh->dim != 2) { delete sp; return cdm_fail(ctx, CDM_EUNSUP, "cdm_space_create_h1: simplex meshes are triangles only"); }
+      sp->ndof = cdm_host_h1_numbering_tri(*mesh, order, sp->gather, sp->bdr_dofs_off, sp->bdr_dofs_flat);
+      sp->class_off.clear();
+   }
+   else
    sp->ndof = cdm_host_h1_numbering(*mesh, order, sp->gather, sp->bdr_dofs_off, sp->bdr_dofs_flat, sp->class_off.data());
    if (sp->ndof < 0) { delete sp; return cdm_fail(ctx, CDM_EINVAL, "cdm_space_create_h1: boundary element not found in mesh"); }
    if (sp->ndof > 2147483000LL) { delete sp; return cdm_fail(ctx, CDM_EUNSUP, "cdm_space_create_h1: more than 2^31 dofs on one rank"); }
@@ -352,6 +379,7 @@ int cdm_space_create_from_table(cdm_ctx *ctx, const cdm_mesh *mesh, int order, i
 {
    if (!ctx || !mesh || !space || !elem_dof || ndof < 1) { return cdm_fail(ctx, CDM_EINVAL, "cdm_space_create_from_table: bad arguments"); }
    if (order < 1 || order > 6) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_space_create_from_table: order must be 1..6"); }
+   if (mesh->geom != 0) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_space_create_from_table: tensor-product meshes only"); }
    cdm_space *sp = space_new(ctx, mesh, order);
    if (!sp) { return cdm_fail(ctx, CDM_ENOMEM, "out of memory"); }
    sp->ndof = sp->ntrue = ndof;
@@ -427,10 +455,11 @@ int cdm_space_get_basis(const cdm_space *sp, double *B, double *G, double *qw, d
 // trilinear / bilinear map of reference point xi through element e
 static void map_point(const cdm_space *sp, int64_t e, const double *xi, double *X)
 {
-   const int dim = sp->dim, nvpe = (dim == 2) ? 4 : 8;
+   const int dim = sp->dim, nvpe = (sp->geom == 1) ? 3 : ((dim == 2) ? 4 : 8);
    const double x = xi[0], y = xi[1], z = (dim == 3) ? xi[2] : 0.0;
    double N[8];
-   if (dim == 2) { N[0] = (1 - x) * (1 - y); N[1] = x * (1 - y); N[2] = x * y; N[3] = (1 - x) * y; }
+   if (sp->geom == 1) { N[0] = 1.0 - x - y; N[1] = x; N[2] = y; }
+   else if (dim == 2) { N[0] = (1 - x) * (1 - y); N[1] = x * (1 - y); N[2] = x * y; N[3] = (1 - x) * y; }
    else
    {
       N[0] = (1 - x) * (1 - y) * (1 - z); N[1] = x * (1 - y) * (1 - z); N[2] = x * y * (1 - z); N[3] = (1 - x) * y * (1 - z);
@@ -451,7 +480,9 @@ int cdm_space_dof_coords(const cdm_space *sp, double *xyz)
    for (int64_t e = 0; e < sp->ne; e++)
       for (int l = 0; l < sp->nd; l++)
       {
-         const double xi[3] = {sp->nodes[l % d1d], sp->nodes[(l / d1d) % d1d], dim == 3 ? sp->nodes[l / (d1d * d1d)] : 0.0};
+         double xi[3] = {0.0, 0.0, 0.0};
+         if (sp->geom == 1) { xi[0] = sp->snodes[2 * l]; xi[1] = sp->snodes[2 * l + 1]; }
+         else { xi[0] = sp->nodes[l % d1d]; xi[1] = sp->nodes[(l / d1d) % d1d]; xi[2] = dim == 3 ? sp->nodes[l / (d1d * d1d)] : 0.0; }
          map_point(sp, e, xi, xyz + (size_t)sp->gather[(size_t)e * sp->nd + l] * dim);
       }
    return CDM_OK;
@@ -464,7 +495,9 @@ int cdm_space_qpt_coords(const cdm_space *sp, double *xyz)
    for (int64_t e = 0; e < sp->ne; e++)
       for (int q = 0; q < sp->nq; q++)
       {
-         const double xi[3] = {sp->qx[q % q1d], sp->qx[(q / q1d) % q1d], dim == 3 ? sp->qx[q / (q1d * q1d)] : 0.0};
+         double xi[3] = {0.0, 0.0, 0.0};
+         if (sp->geom == 1) { xi[0] = sp->sqx[2 * q]; xi[1] = sp->sqx[2 * q + 1]; }
+         else { xi[0] = sp->qx[q % q1d]; xi[1] = sp->qx[(q / q1d) % q1d]; xi[2] = dim == 3 ? sp->qx[q / (q1d * q1d)] : 0.0; }
          map_point(sp, e, xi, xyz + ((size_t)e * sp->nq + q) * dim);
       }
    return CDM_OK;
@@ -543,6 +576,7 @@ int cdm_space_destroy(cdm_space *sp)
    {
       cudaFree(sp->gather_dev); cudaFree(sp->offsets_dev); cudaFree(sp->indices_dev); cudaFree(sp->elem_x_dev);
       cudaFree(sp->work_dev); cudaFree(sp->elem_part_dev); cudaFree(sp->iota_dev);
+      cudaFree(sp->sB_dev); cudaFree(sp->sG_dev); cudaFree(sp->sqw_dev); cudaFree(sp->sqx_dev);
       cdm_halo_p2p_destroy(sp);
       cdm_halo_sym_destroy(sp);
       cudaFree(sp->sym.all_dev); cudaFree(sp->sym.sh_dof_dev); cudaFree(sp->sym.sh_off_dev); cudaFree(sp->sym.sh_src_dev);
@@ -585,6 +619,7 @@ int cdm_operator_create(cdm_space *sp, const cdm_coeff *kappa, const cdm_coeff *
    op->ncomp = (hk ? nsym : 0) + (hv ? sp->dim : 0) + (hm ? 1 : 0);
    op->slab = (op->ncomp * q2 + 1) & ~1;
    op->D_len = sp->ne * (int64_t)op->slab * (sp->dim == 3 ? sp->q1d : 1);
+   if (sp->geom == 1) { op->slab = (op->ncomp * sp->nq + 1) & ~1; op->D_len = sp->ne * (int64_t)op->slab; }
    int rc = CDM_OK;
    do
    {
@@ -610,7 +645,9 @@ int cdm_operator_create(cdm_space *sp, const cdm_coeff *kappa, const cdm_coeff *
          if ((rc = upload(ctx, op->ess_host, &op->ess_dev))) { break; }
          if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = CDM_ECUDA; break; }
       }
-      rc = cdm_k_setup_qdata(op, kappa, vel, conv_alpha, mass);
+      rc = (sp->geom == 1) ? cdm_k_setup_qdata_simplex(op, kappa, vel, conv_alpha, mass) : cdm_k_setup_qdata(op, kappa, vel, conv_alpha, mass);
+      // triangles have no sum-factorised apply: the operator IS the assembled sparse matrix (the reference's own path)
+      if (!rc && sp->geom == 1) { rc = cdm_operator_assemble_csr(op); if (!rc) { op->assembly = 1; } }
    } while (0);
    if (rc) { cdm_operator_destroy(op); return rc; }
    // default kernel per order (measured, profiles/): p=3 hand-specialised register-z kernel,
@@ -630,7 +667,8 @@ int cdm_operator_update(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel
    if (hk < 0 || hv < 0 || hm < 0 || (hk > 0) != op->has_diff || (hv > 0) != op->has_conv || (hm > 0) != op->has_mass)
       return cdm_fail(ctx, CDM_EINVAL, "cdm_operator_update: the set of integrators must not change");
    if (op->dinv_dev) { cudaFree(op->dinv_dev); op->dinv_dev = nullptr; }
-   const int rc = cdm_k_setup_qdata(op, kappa, vel, conv_alpha, mass);
+   const int rc = (op->sp->geom == 1) ? cdm_k_setup_qdata_simplex(op, kappa, vel, conv_alpha, mass)
+                                      : cdm_k_setup_qdata(op, kappa, vel, conv_alpha, mass);
    return rc ? rc : cdm_csr_refill_if_present(op);        // an assembled matrix follows the new coefficients
 }
 
@@ -661,6 +699,7 @@ int cdm_operator_set_option(cdm_op *op, const char *name, int value)
    {
       // 1: the reference's literal path -- apply = SpMV with the fully assembled CSR matrix (csr_path.cu)
       if (value != 0 && value != 1) { return CDM_EINVAL; }
+      if (value == 0 && op->sp->geom == 1) { return cdm_fail(op->sp->ctx, CDM_EUNSUP, "triangle spaces have no matrix-free apply (assembly must stay 1)"); }
       if (value == 1 && !op->csr) { const int rc = cdm_operator_assemble_csr(op); if (rc) { return rc; } }
       op->assembly = value;
       return CDM_OK;
@@ -1049,7 +1088,8 @@ int cdm_operator_diag(cdm_op *op, double *d_dev)
    const bool par = ctx->nranks > 1 && !sp->peers.empty();
    double *dst = d_dev;
    if (sp->ntrue != sp->ndof) { if ((rc = ensure_L(op))) { return rc; } dst = op->yL_dev; }
-   if ((rc = cdm_k_diag(op, dst))) { return rc; }
+   if (sp->geom == 1) { if ((rc = cdm_k_csr_diag(op, dst))) { return rc; } }
+   else if ((rc = cdm_k_diag(op, dst))) { return rc; }
    if (par && (rc = cdm_halo_PT(op, dst))) { return rc; }
    if (dst != d_dev) { CDM_CUDA(ctx, cudaMemcpyAsync(d_dev, dst, sizeof(double) * (size_t)sp->ntrue, cudaMemcpyDeviceToDevice, ctx->stream)); }
    if (op->n_ess > 0) { rc = cdm_k_set_idx(ctx, op->n_ess, op->ess_dev, 1.0, d_dev); }

@@ -49,6 +49,7 @@ struct cdm_ctx
 
 struct cdm_mesh
 {
+   int geom = 0;                    // 0: tensor elements (quads / hexes), 1: simplices (triangles)
    int dim = 0;
    int64_t nv = 0, ne = 0, nbe = 0;
    std::vector<double> vx;          // nv*dim, vertex-major
@@ -121,6 +122,11 @@ struct cdm_space
    std::vector<int32_t> gather, offsets, indices;     // ElementRestriction arrays
    std::vector<double> B, G, qw, nodes, qx;           // 1-D tables (q1d x d1d)
    std::vector<double> elem_x;                        // ne * nvpe * dim vertex coordinates
+   // simplex (triangle) spaces: dense reference tables of the operator's rule -- sB[q*nd + i] = phi_i(x_q),
+   // sG[(c*nq + q)*nd + i] = d phi_i / d xi_c (x_q), sqw[q], sqx[q*dim + c], snodes[i*dim + c]; nvpe = 3
+   int geom = 0;
+   std::vector<double> sB, sG, sqw, sqx, snodes;
+   double *sB_dev = nullptr, *sG_dev = nullptr, *sqw_dev = nullptr, *sqx_dev = nullptr;
    // entity tables kept for essential-dof marking
    std::vector<int32_t> bdr_vtx, bdr_attr;
    std::vector<int32_t> bdr_dofs_flat, bdr_dofs_off;  // per boundary element: its dofs
@@ -141,6 +147,18 @@ struct cdm_space
    std::vector<int64_t> elem_perm;
    std::vector<int64_t> class_off;                     // entity-class dof ranges (spaces numbered by this library)
    std::vector<int64_t> dof_global;                    // local dof -> global dof id (partitioned spaces)
+};
+
+// assembled matrix of an operator (csr_path.cu)
+struct cdm_csr
+{
+   int64_t n = 0, nnz = 0;
+   std::vector<int64_t> rowptr;
+   std::vector<int32_t> colind;
+   int64_t *rowptr_dev = nullptr;
+   int32_t *colind_dev = nullptr;
+   double *vals_dev = nullptr;
+   unsigned char *ess_mark_dev = nullptr;
 };
 
 struct cdm_op
@@ -168,6 +186,7 @@ struct cdm_op
    int halo_mode = 2;              // 0: P / P^T over NCCL send/recv, 1: P / P^T over peer memory, 2: one symmetric peer-memory exchange
    int assembly = 0;               // 0: partial assembly (matrix-free), 1: apply = SpMV with the assembled CSR matrix
    struct cdm_csr *csr = nullptr;  // csr_path.cu (built on demand)
+   struct cdm_ilu *ilu = nullptr;  // precond.cu: ILU(0) of the assembled matrix (built on demand)
    int kernel_variant = 0;
    int64_t grid_cap = 0;           // > 0: upper bound on the persistent grids (tests: forces many elements per warp)
    double *e_out = nullptr;        // != null: E-vector output of the element kernels goes here and is not transposed
@@ -211,6 +230,19 @@ int cdm_check_p2p(cdm_ctx *ctx);
            CDM_CUDA(ctx, cudaSetDevice((ctx)->device));                                  \
    } while (0)
 
+// ---- simplex elements (host_simplex.cpp, simplex.cu)
+// nodes of the order-p Lagrange triangle (MFEM H1_TriangleElement node set), nd = (p+1)(p+2)/2, xy[i*2 + c]
+void cdm_host_tri_nodes(int p, double *xy);
+// collapsed Gauss-Legendre rule with n points per direction on the reference triangle (exact to degree 2n-2): n*n points
+void cdm_host_tri_rule(int n, double *xy, double *w);
+// values and reference gradients of the nodal basis at arbitrary reference points: B[q*nd + i], G[(c*npts + q)*nd + i]
+void cdm_host_tri_basis(int p, int npts, const double *xy, double *B, double *G);
+int64_t cdm_host_h1_numbering_tri(const cdm_mesh &m, int p, std::vector<int32_t> &elem_dof,
+                                  std::vector<int32_t> &bdr_off, std::vector<int32_t> &bdr_flat);
+int cdm_k_setup_qdata_simplex(cdm_op *op, const cdm_coeff *kappa, const cdm_coeff *vel, double alpha, const cdm_coeff *mass);
+int cdm_simplex_rule_coords(const cdm_space *sp, int nq1d, double *xyz);           // host or device output
+int cdm_simplex_domain_lf(cdm_space *sp, int nq1d, const double *f_q, double scale, int accumulate, double *b_dev);
+int cdm_simplex_l2_error(cdm_space *sp, int nq1d, const double *u_dev, const double *uex_q, double *result_host);
 // ---- host-side builders (host_*.cpp)
 void cdm_host_gauss_legendre(int n, double *x, double *w);
 void cdm_host_gauss_lobatto(int n, double *x);
@@ -282,6 +314,12 @@ int cdm_allgather_bytes(cdm_ctx *c, const void *send_dev, void *recv_dev, size_t
 void cdm_csr_destroy(cdm_op *op);
 int cdm_csr_refill_if_present(cdm_op *op);          // new coefficient values into an existing pattern
 int cdm_k_csr_spmv(cdm_op *op, const double *x, double *y, bool constrained);
+int cdm_k_csr_diag(cdm_op *op, double *d);           // diagonal of the assembled matrix
+// ---- ILU(0) of the assembled matrix (precond.cu): -pc_type bjacobi -sub_pc_type ilu on one rank
+int cdm_ilu_setup(cdm_op *op);                      // symbolic (levels, host) + numeric factorisation (device)
+int cdm_ilu_refactor(cdm_op *op);                   // numeric factorisation only (new matrix values)
+int cdm_ilu_apply(cdm_op *op, const double *r, double *z);   // z = U^{-1} L^{-1} r; essential rows pass through
+void cdm_ilu_destroy(cdm_op *op);
 // ---- peer-memory halo exchange (halo_p2p.cu)
 int cdm_halo_p2p_setup(cdm_space *sp);              // collective over the ranks of the communicator
 void cdm_halo_p2p_destroy(cdm_space *sp);

@@ -7,29 +7,21 @@
 //   :368   PetscLinearSolver(A).Mult(B, X)   MatMult inside KSP
 // It exists so that the partially-assembled operator can be compared with the algorithm the application
 // actually runs, on the same GPU: operator option "assembly" = 1 switches cdm_operator_apply (and therefore
-// cdm_gmres / cdm_cg) to the CSR SpMV.  Single rank, quad / hex meshes; the matrix-free path stays the product.
+// cdm_gmres / cdm_cg) to the CSR SpMV.  Single rank; quad / hex meshes (where the matrix-free path stays the product)
+// and triangle meshes (where it is the only path, as in the reference).
 //
 // * pattern: on the host from the element restriction (row g = union of the dofs of the elements touching g,
 //   sorted) -- bit-exact with the oracle's pattern;
-// * values: one block per element; thread (i,j) accumulates a_ij = sum_q grad(phi_i).D grad(phi_j)
-//   + phi_i Dc.grad(phi_j) + Dm phi_i phi_j from the SAME quadrature data the matrix-free kernels stream
-//   (so both paths discretise identically), then adds it into its row by binary search (fp64 atomicAdd);
+// * values: one warp per matrix row; the element-matrix rows that map to it are computed entry by entry
+//   (a_ij = sum_q grad(phi_i).D grad(phi_j) + phi_i Dc.grad(phi_j) + Dm phi_i phi_j from the SAME quadrature data the
+//   matrix-free kernels stream, so both paths discretise identically) and added in the fixed order of the
+//   ElementRestriction transpose: no atomics, the matrix is bit-reproducible; quads, hexes and triangles;
 // * apply: warp per row, essential dofs handled like ConstrainedOperator (row -> identity, column skipped),
 //   which is the matrix FormLinearSystem produces with DIAG_ONE.
 #include "cdm_internal.hpp"
 #include "kernels_common.cuh"
 #include <algorithm>
 
-struct cdm_csr
-{
-   int64_t n = 0, nnz = 0;
-   std::vector<int64_t> rowptr;
-   std::vector<int32_t> colind;
-   int64_t *rowptr_dev = nullptr;
-   int32_t *colind_dev = nullptr;
-   double *vals_dev = nullptr;
-   unsigned char *ess_mark_dev = nullptr;
-};
 
 namespace
 {
@@ -47,60 +39,110 @@ __device__ __forceinline__ void basis_at(const BasisTables &t, int d1d, int q1d,
    if (DIM == 3) { g[2] = bx * by * t.G[qz * d1d + iz]; }
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(256)
-k_csr_assemble(BasisTables t, int d1d, int q1d, int64_t ne, const int32_t *__restrict__ gather,
-               const double *__restrict__ Dq, int slab, int has_diff, int has_conv, int has_mass,
-               const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind, double *__restrict__ vals)
+// One entry of an element matrix: a_ij = sum_q grad(phi_i) . D grad(phi_j) + phi_i Dc . grad(phi_j) + Dm phi_i phi_j.
+// MODE 2 / 3: tensor-product quads / hexes (1-D tables in the constant bank); MODE 1: triangles (dense tables B[q][i],
+// G[c][q][i] in global memory, quadrature data per element [component][nq]).
+template <int MODE>
+__device__ __forceinline__ double elem_entry(const BasisTables &t, int d1d, int q1d, int nd, int nq, const double *__restrict__ sB,
+                                             const double *__restrict__ sG, const double *__restrict__ Dq, int slab, int64_t e, int i, int j,
+                                             int has_diff, int has_conv, int has_mass)
 {
-   const int nd = (DIM == 3) ? d1d * d1d * d1d : d1d * d1d;
-   const int q2 = q1d * q1d, nq = (DIM == 3) ? q2 * q1d : q2;
+   constexpr int DIM = (MODE == 3) ? 3 : 2;
+   const int q2 = (MODE == 1) ? nq : q1d * q1d;
    const int oc = has_diff ? DIM * (DIM + 1) / 2 : 0, om = oc + (has_conv ? DIM : 0);
-   for (int64_t e = blockIdx.x; e < ne; e += gridDim.x)
+   double a = 0.0;
+   for (int q = 0; q < nq; q++)
    {
-      for (int ij = threadIdx.x; ij < nd * nd; ij += blockDim.x)
+      double pi, pj, gi[3], gj[3];
+      if (MODE == 1)
       {
-         const int i = ij / nd, j = ij - i * nd;
-         double a = 0.0;
-         for (int q = 0; q < nq; q++)
+         pi = sB[(size_t)q * nd + i]; pj = sB[(size_t)q * nd + j];
+         gi[0] = sG[(size_t)q * nd + i]; gi[1] = sG[((size_t)nq + q) * nd + i];
+         gj[0] = sG[(size_t)q * nd + j]; gj[1] = sG[((size_t)nq + q) * nd + j];
+      }
+      else
+      {
+         basis_at<DIM>(t, d1d, q1d, i, q, pi, gi);
+         basis_at<DIM>(t, d1d, q1d, j, q, pj, gj);
+      }
+      const double *dp = (MODE == 3) ? Dq + ((e * q1d + q / q2) * (int64_t)slab + q % q2) : Dq + (e * (int64_t)slab + q);
+      if (has_diff)
+      {
+         if (DIM == 3)
          {
-            double pi, pj, gi[3], gj[3];
-            basis_at<DIM>(t, d1d, q1d, i, q, pi, gi);
-            basis_at<DIM>(t, d1d, q1d, j, q, pj, gj);
-            const double *dp = (DIM == 3) ? Dq + ((e * q1d + q / q2) * (int64_t)slab + q % q2)
-                                          : Dq + (e * (int64_t)slab + q);
-            if (has_diff)
-            {
-               if (DIM == 3)
-               {
-                  const double d11 = dp[0], d21 = dp[q2], d31 = dp[2 * q2], d22 = dp[3 * q2], d32 = dp[4 * q2], d33 = dp[5 * q2];
-                  a += gi[0] * (d11 * gj[0] + d21 * gj[1] + d31 * gj[2]) + gi[1] * (d21 * gj[0] + d22 * gj[1] + d32 * gj[2])
-                       + gi[2] * (d31 * gj[0] + d32 * gj[1] + d33 * gj[2]);
-               }
-               else
-               {
-                  const double d11 = dp[0], d21 = dp[q2], d22 = dp[2 * q2];
-                  a += gi[0] * (d11 * gj[0] + d21 * gj[1]) + gi[1] * (d21 * gj[0] + d22 * gj[1]);
-               }
-            }
-            if (has_conv)
-            {
-               double s = dp[oc * q2] * gj[0] + dp[(oc + 1) * q2] * gj[1];
-               if (DIM == 3) { s += dp[(oc + 2) * q2] * gj[2]; }
-               a += pi * s;
-            }
-            if (has_mass) { a += dp[om * q2] * pi * pj; }
+            const double d11 = dp[0], d21 = dp[q2], d31 = dp[2 * q2], d22 = dp[3 * q2], d32 = dp[4 * q2], d33 = dp[5 * q2];
+            a += gi[0] * (d11 * gj[0] + d21 * gj[1] + d31 * gj[2]) + gi[1] * (d21 * gj[0] + d22 * gj[1] + d32 * gj[2])
+                 + gi[2] * (d31 * gj[0] + d32 * gj[1] + d33 * gj[2]);
          }
-         const int32_t row = gather[e * nd + i], col = gather[e * nd + j];
-         int64_t lo = rowptr[row], hi = rowptr[row + 1] - 1;
-         while (lo < hi)                                       // the pattern contains col by construction
+         else
          {
-            const int64_t mid = (lo + hi) >> 1;
-            if (colind[mid] < col) { lo = mid + 1; } else { hi = mid; }
+            const double d11 = dp[0], d21 = dp[q2], d22 = dp[2 * q2];
+            a += gi[0] * (d11 * gj[0] + d21 * gj[1]) + gi[1] * (d21 * gj[0] + d22 * gj[1]);
          }
-         atomicAdd(vals + lo, a);
+      }
+      if (has_conv)
+      {
+         double s = dp[oc * q2] * gj[0] + dp[(oc + 1) * q2] * gj[1];
+         if (DIM == 3) { s += dp[(oc + 2) * q2] * gj[2]; }
+         a += pi * s;
+      }
+      if (has_mass) { a += dp[om * q2] * pi * pj; }
+   }
+   return a;
+}
+
+// Deterministic fill, one warp per matrix row g: the (element, local row) pairs that map to g are visited in the fixed
+// order of the ElementRestriction transpose (offsets / indices); for each of them the lanes compute the nd entries of that
+// element-matrix row and add them into the CSR row (distinct columns within one element, a warp barrier between
+// elements): no atomics, the matrix is bit-reproducible.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_csr_fill_rows(BasisTables t, int d1d, int q1d, int nd, int nq, const double *__restrict__ sB, const double *__restrict__ sG,
+                int64_t nrows, const int32_t *__restrict__ offsets, const int32_t *__restrict__ indices, const int32_t *__restrict__ gather,
+                const double *__restrict__ Dq, int slab, int has_diff, int has_conv, int has_mass,
+                const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind, double *__restrict__ vals)
+{
+   const int lane = threadIdx.x & 31;
+   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+   for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < nrows; g += nwarps)
+   {
+      const int64_t r0 = rowptr[g], r1 = rowptr[g + 1];
+      for (int64_t k = r0 + lane; k < r1; k += 32) { vals[k] = 0.0; }
+      __syncwarp();
+      for (int32_t k = offsets[g]; k < offsets[g + 1]; k++)
+      {
+         const int32_t idx = indices[k];
+         const int64_t e = idx / nd;
+         const int i = idx - (int32_t)(e * nd);
+         for (int j = lane; j < nd; j += 32)
+         {
+            const double a = elem_entry<MODE>(t, d1d, q1d, nd, nq, sB, sG, Dq, slab, e, i, j, has_diff, has_conv, has_mass);
+            const int32_t col = gather[e * nd + j];
+            int64_t lo = r0, hi = r1 - 1;
+            while (lo < hi)                                    // the pattern contains col by construction
+            {
+               const int64_t mid = (lo + hi) >> 1;
+               if (colind[mid] < col) { lo = mid + 1; } else { hi = mid; }
+            }
+            vals[lo] += a;
+         }
+         __syncwarp();
       }
    }
+}
+
+__global__ void __launch_bounds__(256)
+k_csr_diag(int64_t n, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind, const double *__restrict__ vals, double *__restrict__ d)
+{
+   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (g >= n) { return; }
+   int64_t lo = rowptr[g], hi = rowptr[g + 1] - 1;
+   while (lo < hi)
+   {
+      const int64_t mid = (lo + hi) >> 1;
+      if (colind[mid] < g) { lo = mid + 1; } else { hi = mid; }
+   }
+   d[g] = vals[lo];
 }
 
 // y = A x (unconstrained) or the FormLinearSystem / ConstrainedOperator matrix: essential rows -> identity,
@@ -127,6 +169,7 @@ k_csr_spmv(int64_t n, const int64_t *__restrict__ rowptr, const int32_t *__restr
 void cdm_csr_destroy(cdm_op *op)
 {
    cdm_csr *m = op->csr;
+   cdm_ilu_destroy(op);
    if (!m) { return; }
    cudaFree(m->rowptr_dev); cudaFree(m->colind_dev); cudaFree(m->vals_dev); cudaFree(m->ess_mark_dev);
    delete m;
@@ -139,21 +182,30 @@ static int csr_fill(cdm_op *op)
    cdm_space *sp = op->sp;
    cdm_ctx *c = sp->ctx;
    cdm_csr *m = op->csr;
-   CDM_CUDA(c, cudaMemsetAsync(m->vals_dev, 0, sizeof(double) * (size_t)m->nnz, c->stream));
    BasisTables t;
    memset(&t, 0, sizeof(t));
-   for (int i = 0; i < sp->q1d * sp->d1d; i++) { t.B[i] = sp->B[i]; t.G[i] = sp->G[i]; }
-   const unsigned nb = (unsigned)std::min<int64_t>(sp->ne, (int64_t)c->sm_count * 16);
-   if (sp->dim == 2)
-   {
-      k_csr_assemble<2><<<nb, 256, 0, c->stream>>>(t, sp->d1d, sp->q1d, sp->ne, sp->gather_dev, op->D_dev, op->slab, op->has_diff,
-                                                   op->has_conv, op->has_mass, m->rowptr_dev, m->colind_dev, m->vals_dev);
-   }
-   else
-   {
-      k_csr_assemble<3><<<nb, 256, 0, c->stream>>>(t, sp->d1d, sp->q1d, sp->ne, sp->gather_dev, op->D_dev, op->slab, op->has_diff,
-                                                   op->has_conv, op->has_mass, m->rowptr_dev, m->colind_dev, m->vals_dev);
-   }
+   if (sp->geom == 0) { for (int i = 0; i < sp->q1d * sp->d1d; i++) { t.B[i] = sp->B[i]; t.G[i] = sp->G[i]; } }
+   const int64_t warps = std::min<int64_t>(m->n, (int64_t)c->sm_count * 64);
+   const unsigned nb = (unsigned)((warps * 32 + 255) / 256);
+#define FILL(MODE) k_csr_fill_rows<MODE><<<nb, 256, 0, c->stream>>>(t, sp->d1d, sp->q1d, sp->nd, sp->nq, sp->sB_dev, sp->sG_dev, m->n,     \
+      sp->offsets_dev, sp->indices_dev, sp->gather_dev, op->D_dev, op->slab, op->has_diff, op->has_conv, op->has_mass,                     \
+      m->rowptr_dev, m->colind_dev, m->vals_dev)
+   if (sp->geom == 1) { FILL(1); }
+   else if (sp->dim == 2) { FILL(2); }
+   else { FILL(3); }
+#undef FILL
+   c->launches++;
+   CDM_CUDA(c, cudaGetLastError());
+   if (op->ilu) { return cdm_ilu_refactor(op); }             // the preconditioner follows the new values
+   return CDM_OK;
+}
+
+int cdm_k_csr_diag(cdm_op *op, double *d)
+{
+   cdm_ctx *c = op->sp->ctx;
+   cdm_csr *m = op->csr;
+   if (!m) { return cdm_fail(c, CDM_EINVAL, "cdm_k_csr_diag: no assembled matrix"); }
+   k_csr_diag<<<(unsigned)((m->n + 255) / 256), 256, 0, c->stream>>>(m->n, m->rowptr_dev, m->colind_dev, m->vals_dev, d);
    c->launches++;
    CDM_CUDA(c, cudaGetLastError());
    return CDM_OK;

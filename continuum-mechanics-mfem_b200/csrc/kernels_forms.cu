@@ -345,6 +345,7 @@ int cdm_space_rule_coords(const cdm_space *sp, int q1d, double *xyz)
    if (!sp || !xyz) { return CDM_EINVAL; }
    cdm_ctx *c = sp->ctx;
    CDM_REQUIRE_GPU(c);
+   if (sp->geom == 1) { return cdm_simplex_rule_coords(sp, q1d == 0 ? sp->q1d : q1d, xyz); }
    if (q1d == 0) { q1d = sp->q1d; }
    RuleTables t;
    int rc = make_rule(sp, q1d, &t); if (rc) { return rc; }
@@ -372,6 +373,7 @@ int cdm_domain_lf(cdm_space *sp, int q1d, const double *f_q, double scale, int a
    cdm_ctx *c = sp->ctx;
    CDM_REQUIRE_GPU(c);
    if (q1d == 0) { q1d = sp->p + 1; }                      // DomainLFIntegrator default: order 2p
+   if (sp->geom == 1) { return cdm_simplex_domain_lf(sp, q1d, f_q, scale, accumulate, b_dev); }
    RuleTables t;
    int rc = make_rule(sp, q1d, &t); if (rc) { return rc; }
    const int dim = sp->dim, d1d = sp->d1d;
@@ -411,6 +413,7 @@ int cdm_l2_error(cdm_space *sp, int q1d, const double *u_dev, const double *uex_
    cdm_ctx *c = sp->ctx;
    CDM_REQUIRE_GPU(c);
    if (q1d == 0) { q1d = std::max(2, 2 * sp->p + 3) / 2 + 1; }   // the app's irs: order max(2, 2p+3)
+   if (sp->geom == 1) { return cdm_simplex_l2_error(sp, q1d, u_dev, uex_q, result_host); }
    RuleTables t;
    int rc = make_rule(sp, q1d, &t); if (rc) { return rc; }
    const int dim = sp->dim, d1d = sp->d1d, nd = sp->nd;

@@ -85,8 +85,21 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
    if (par && op->halo_mode == 2 && op->assembly == 0 && sp->sym.ready == 0) { RC(cdm_halo_sym_setup(sp)); }
    const bool gh = cdm_apply_keeps_ghosts(op);            // applies return ghost-consistent vectors
    const int64_t nall = gh ? sp->ndof : n, ntail = nall - n;
+   // preconditioner (-pc_type): 0 none, 1 jacobi, 2 block-Jacobi + ILU(0) on the assembled matrix (one block per rank;
+   // single rank only, like the assembled path itself)
    const double *dinv = nullptr;
-   if (o->jacobi) { RC(ensure_dinv(op)); dinv = op->dinv_dev; }
+   const bool ilu = o->jacobi == 2;
+   if (o->jacobi == 1) { RC(ensure_dinv(op)); dinv = op->dinv_dev; }
+   if (ilu)
+   {
+      if (par) { return cdm_fail(c, CDM_EUNSUP, "cdm_gmres: the ILU(0) preconditioner is single-rank"); }
+      if (!op->csr) { RC(cdm_operator_assemble_csr(op)); }
+      op->assembly = 1;                                   // ILU(0) belongs to the assembled matrix: apply = SpMV
+      RC(cdm_ilu_setup(op));
+   }
+   // z = M^{-1} r on the true dofs (initial residuals; the iteration itself fuses Jacobi into the multi-dot)
+   auto precond = [&](const double *r, double *z) -> int
+   { return ilu ? cdm_ilu_apply(op, r, z) : cdm_k_pmult_scaled(c, n, dinv, nullptr, r, z); };
    double *h_dev = red_out(c);                            // [m+1] dots of the current iteration
    double *nrm2 = red_out(c) + CDM_RED_MAXK;              // [m+2] squared norms of u_0 .. u_m
    double *y_dev = red_out(c) + 2 * CDM_RED_MAXK;
@@ -100,13 +113,13 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
    while (true)
    {
       // u_0 = M^{-1}(b - A x)
-      if (first && o->zero_guess) { RC(cdm_k_pmult_scaled(c, n, dinv, nullptr, b, V)); }
+      if (first && o->zero_guess) { RC(precond(b, V)); }
       else
       {
          CDM_CUDA(c, cudaMemcpyAsync(w, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
          RC(cdm_apply_tail(op, w, t, true, false));
          RC(cdm_k_add(c, n, b, -1.0, t, t));
-         RC(cdm_k_pmult_scaled(c, n, dinv, nullptr, t, V));
+         RC(precond(t, V));
       }
       if (gh) { RC(cdm_halo_P_space(sp, V)); }             // once per cycle: make u_0 ghost-consistent
       RC(cdm_k_mdot_dev(c, n, 1, V, V, ld, nrm2));
@@ -122,7 +135,7 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
          double ref = beta;
          if (!o->zero_guess && o->variant == CDM_GMRES_PETSC)
          {
-            RC(cdm_k_pmult_scaled(c, n, dinv, nullptr, b, w));
+            RC(precond(b, w));
             RC(cdm_k_mdot_dev(c, n, 1, w, w, ld, h_dev));
             RC(cdm_allreduce_sum(c, h_dev, 1));
             double nb2; RC(fetch(c, h_dev, 1, &nb2));
@@ -143,10 +156,12 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
          double *uj = V + (int64_t)j * ld, *un = V + (int64_t)(j + 1) * ld;
          if (!applied) { RC(cdm_apply_tail(op, uj, t, true, gh)); }
          applied = false;
+         const double *pre = t;                            // M^{-1} A u_j when the preconditioner is not the fused Jacobi
+         if (ilu) { RC(cdm_ilu_apply(op, t, w)); pre = w; }
          if (o->variant == CDM_GMRES_PETSC)
          {
             // classical Gram-Schmidt: all j+1 dots against the same vector, one all-reduce
-            RC(cdm_k_mdot_lazy_dev(c, n, j + 1, t, dinv, nrm2 + j, un, V, ld, nrm2, h_dev));
+            RC(cdm_k_mdot_lazy_dev(c, n, j + 1, pre, dinv, nrm2 + j, un, V, ld, nrm2, h_dev));
             if (ntail > 0) { RC(cdm_k_pmult_scaled(c, ntail, dinv ? dinv + n : nullptr, nrm2 + j, t + n, un + n)); }
             RC(cdm_allreduce_sum(c, h_dev, j + 1));
             RC(cdm_k_maxpy_lazy_dev(c, n, j + 1, h_dev, nrm2, V, ld, un, nrm2 + (j + 1)));
@@ -155,7 +170,7 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
          else
          {
             // modified Gram-Schmidt (mfem::GMRESSolver), scalars stay on the device
-            RC(cdm_k_pmult_scaled(c, nall, dinv, nrm2 + j, t, un));
+            RC(cdm_k_pmult_scaled(c, nall, dinv, nrm2 + j, pre, un));
             for (int i = 0; i <= j; i++)
             {
                RC(cdm_k_mdot_dev(c, n, 1, un, V + (int64_t)i * ld, ld, h_dev + i));
@@ -236,6 +251,7 @@ extern "C" int cdm_cg(cdm_op *op, const double *b, double *x, const cdm_krylov_o
    const bool gh = cdm_apply_keeps_ghosts(op);
    const int64_t nall = gh ? sp->ndof : n, ntail = nall - n;
    const double *dinv = nullptr;
+   if (o->jacobi == 2) { return cdm_fail(c, CDM_EUNSUP, "cdm_cg: only none / Jacobi preconditioning (ILU(0) is wired into cdm_gmres)"); }
    if (o->jacobi) { RC(ensure_dinv(op)); dinv = op->dinv_dev; }
    double *sc = red_out(c);
    int it = 0, conv = 0, hl = 0;

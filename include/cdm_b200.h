@@ -72,6 +72,23 @@ int  cdm_mesh_from_arrays(cdm_ctx *ctx, int dim, int64_t nv, const double *verti
                           int64_t ne, const int32_t *elem_vtx,
                           int64_t nbe, const int32_t *bdr_vtx, const int32_t *bdr_attr,
                           cdm_mesh **mesh);
+/* triangle meshes (the meshes the reference ships: Mesh/unit_square.msh, unit_circle.msh): 3 vertices per element,
+   2 per boundary segment, counter-clockwise.  Spaces on them are order-p Lagrange triangles; the operator is applied as
+   the assembled sparse matrix (there is no tensor structure to sum-factorise). */
+int  cdm_mesh_from_arrays_simplex(cdm_ctx *ctx, int dim, int64_t nv, const double *vertices,
+                                  int64_t ne, const int32_t *elem_vtx,
+                                  int64_t nbe, const int32_t *bdr_vtx, const int32_t *bdr_attr, cdm_mesh **mesh);
+/* Mesh(mesh_file, 1, 1) for Gmsh 2.2 ASCII files (linear_convection_diffusion_2D.cpp:290, Input/input_2d.yaml:1):
+   triangles, quadrilaterals or hexahedra as elements, lines / quadrilaterals as boundary elements, physical tags as
+   attributes; vertices in file order (unused ones dropped), elements in file order.  mark_for_refinement = the
+   `refine` constructor argument: triangles are rotated so that their longest edge comes first. */
+int  cdm_mesh_read_gmsh(cdm_ctx *ctx, const char *path, int mark_for_refinement, cdm_mesh **mesh);
+/* Mesh::MakeCartesian2D/3D with sfc_ordering = true (MFEM's default for inline-quad / inline-hex meshes): elements
+   listed along the generalised Hilbert curve; cdm_grid_sfc_ordering returns the curve itself, coords[k*dim + c]. */
+int  cdm_mesh_cartesian_sfc(cdm_ctx *ctx, int dim, const int64_t n[3], const double size[3], double perturb, cdm_mesh **mesh);
+int  cdm_grid_sfc_ordering(int dim, const int64_t n[3], int64_t *coords);
+/* geom: 0 tensor-product elements, 1 simplices */
+int  cdm_mesh_geometry(const cdm_mesh *mesh, int *geom, int *verts_per_elem, int *verts_per_bdr);
 int  cdm_mesh_sizes(const cdm_mesh *mesh, int *dim, int64_t *nv, int64_t *ne, int64_t *nbe);
 int  cdm_mesh_get(const cdm_mesh *mesh, double *vertices, int32_t *elem_vtx,
                   int32_t *bdr_vtx, int32_t *bdr_attr);       /* any pointer may be NULL */
@@ -268,6 +285,28 @@ int  cdm_l2_error(cdm_space *space, int q1d, const double *u_dev, const double *
 int  cdm_vec_set_indexed(cdm_ctx *ctx, int64_t n, const int32_t *idx, const double *vals,
                          double *u_dev);
 
+/* -------------------------------------------- driver input and output files */
+/* LoadParams (linear_convection_diffusion_2D.cpp:62-127): the flat `key: value` YAML the drivers read (scalars,
+   quoted strings, [a, b] flow sequences, # comments).  Getters return CDM_EINVAL for a missing / malformed key, so the
+   caller keeps its default exactly like `if (n["key"]) p.key = n["key"].as<T>()`. */
+typedef struct cdm_config cdm_config;
+int  cdm_config_load(const char *path, cdm_config **cfg);
+int  cdm_config_destroy(cdm_config *cfg);
+int  cdm_config_has(const cdm_config *cfg, const char *key);
+int  cdm_config_get_string(const cdm_config *cfg, const char *key, char *buf, int buflen);
+int  cdm_config_get_double(const cdm_config *cfg, const char *key, double *value);
+int  cdm_config_get_int(const cdm_config *cfg, const char *key, int *value);
+int  cdm_config_get_bool(const cdm_config *cfg, const char *key, int *value);
+int  cdm_config_get_doubles(const cdm_config *cfg, const char *key, double *values, int maxn, int *n);
+/* MFEMInitializePetsc(&argc, &argv, petsc_options_file, NULL) (:268-282) for the options the drivers use
+   (Input/petsc.opts:2-6, Input/petsc_circle.opts:2-8): -ksp_type gmres|cg, -ksp_rtol, -ksp_atol, -ksp_max_it,
+   -ksp_gmres_restart, -pc_type none|jacobi|ilu|bjacobi (+ -sub_pc_type ilu).  Starts from PETSc's defaults.
+   ksp_type: 0 gmres, 1 cg; the preconditioner lands in opts->jacobi (0 none, 1 Jacobi, 2 block-Jacobi + ILU(0)). */
+/* ParaViewDataCollection ... Save() (:421-433): <prefix>/<collection>/<collection>.pvd + Cycle%06d/{data.pvtu,
+   proc%06d.vtu}; every element refined into order^dim linear cells on its node lattice; fields are host L-vectors. */
+int  cdm_write_paraview(const cdm_space *space, const char *prefix_path, const char *collection, int cycle, double time,
+                        int nfields, const char *const *names, const double *const *fields_host);
+
 /* number of kernel launches issued by this context so far */
 int64_t cdm_launch_count(const cdm_ctx *ctx);
 
@@ -305,7 +344,8 @@ typedef struct
    int    max_it;      /* -ksp_max_it 500 */
    double rtol, atol;  /* -ksp_rtol 1e-10 -ksp_atol 1e-12 ; CG: rel 1e-12 abs 0 */
    int    zero_guess;  /* 1: iterative_mode=false (PetscLinearSolver default) */
-   int    jacobi;      /* 1: -pc_type jacobi (diag from cdm_operator_diag) */
+   int    jacobi;      /* -pc_type: 0 none, 1 jacobi (diag from cdm_operator_diag), 2 bjacobi + ilu: ILU(0) of the
+                          assembled matrix, one block per rank (Input/petsc_circle.opts:6-8; cdm_gmres, single rank) */
 } cdm_krylov_opts;
 typedef struct
 {
@@ -322,6 +362,11 @@ int  cdm_gmres(cdm_op *op, const double *b_dev, double *x_dev, const cdm_krylov_
 /* mfem::CGSolver::Mult (mesh_recession_handler.cpp:270-276); hist = (r,z) per iteration */
 int  cdm_cg(cdm_op *op, const double *b_dev, double *x_dev, const cdm_krylov_opts *opts,
             cdm_krylov_result *result, double *hist_host);
+int  cdm_petsc_options_load(const char *path, cdm_krylov_opts *opts, int *ksp_type);
+/* PCApply of -pc_type ilu / bjacobi + ilu: z = (LU)^{-1} r with the ILU(0) factors of the matrix the solver sees
+   (assembles the matrix and factorises on first use); cdm_operator_ilu_levels: dependency levels of the two sweeps */
+int  cdm_operator_ilu_apply(cdm_op *op, const double *r_dev, double *z_dev);
+int  cdm_operator_ilu_levels(cdm_op *op, int *forward, int *backward);
 
 #ifdef __cplusplus
 }

@@ -139,6 +139,15 @@ typedef struct {
 void orc_gmres(const orc_op *A, const double *dinv, const double *b, double *x,
                const orc_krylov_opts *o, orc_krylov_result *r, double *hist);
 /* mfem::CGSolver restatement; hist = (r,z) values */
+/* ILU(0) (natural ordering, PETSc PCILU defaults) and GMRES left-preconditioned with it: -pc_type bjacobi
+   -sub_pc_type ilu on one rank (Input/petsc_circle.opts:6-8) */
+typedef struct orc_ilu orc_ilu;
+orc_ilu *orc_ilu0_factor(int64_t n, const int64_t *rowptr, const int32_t *colind, const double *vals);
+void orc_ilu0_solve(const orc_ilu *f, const double *r, double *z);
+void orc_ilu0_get(const orc_ilu *f, double *lu);
+void orc_ilu0_free(orc_ilu *f);
+void orc_gmres_ilu(const orc_op *A, const orc_ilu *ilu, const double *b, double *x,
+                   const orc_krylov_opts *o, orc_krylov_result *res, double *hist);
 void orc_cg(const orc_op *A, const double *dinv, const double *b, double *x,
             const orc_krylov_opts *o, orc_krylov_result *r, double *hist);
 

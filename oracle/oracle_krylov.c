@@ -85,8 +85,61 @@ static double dot(int64_t n, const double *a, const double *b)
    return s;
 }
 
+/* ---- ILU(0), natural ordering, sequential IKJ: the reference's -pc_type bjacobi -sub_pc_type ilu on one rank
+   (Input/petsc_circle.opts:6-8; PETSc PCILU defaults: 0 levels of fill).  [PETSc-upstream: not vendored] */
+struct orc_ilu { int64_t n; const int64_t *rowptr; const int32_t *colind; double *lu; int64_t *diag; };
+
+orc_ilu *orc_ilu0_factor(int64_t n, const int64_t *rowptr, const int32_t *colind, const double *vals)
+{
+   orc_ilu *f = calloc(1, sizeof(*f));
+   f->n = n; f->rowptr = rowptr; f->colind = colind;
+   f->lu = malloc(sizeof(double) * (size_t)rowptr[n]);
+   f->diag = malloc(sizeof(int64_t) * (size_t)n);
+   memcpy(f->lu, vals, sizeof(double) * (size_t)rowptr[n]);
+   for (int64_t i = 0; i < n; i++)
+      for (int64_t p = rowptr[i]; p < rowptr[i + 1]; p++) if (colind[p] == i) { f->diag[i] = p; }
+   for (int64_t i = 0; i < n; i++)
+   {
+      for (int64_t p = rowptr[i]; p < f->diag[i]; p++)
+      {
+         const int32_t k = colind[p];
+         const double lik = f->lu[p] / f->lu[f->diag[k]];
+         f->lu[p] = lik;
+         int64_t s = f->diag[k] + 1;                       /* merge the tails of rows i and k (both sorted) */
+         for (int64_t q = p + 1; q < rowptr[i + 1]; q++)
+         {
+            while (s < rowptr[k + 1] && colind[s] < colind[q]) { s++; }
+            if (s < rowptr[k + 1] && colind[s] == colind[q]) { f->lu[q] -= lik * f->lu[s]; }
+         }
+      }
+   }
+   return f;
+}
+
+void orc_ilu0_solve(const orc_ilu *f, const double *r, double *z)
+{
+   for (int64_t i = 0; i < f->n; i++)
+   {
+      double s = r[i];
+      for (int64_t p = f->rowptr[i]; p < f->diag[i]; p++) { s -= f->lu[p] * z[f->colind[p]]; }
+      z[i] = s;
+   }
+   for (int64_t i = f->n - 1; i >= 0; i--)
+   {
+      double s = z[i];
+      for (int64_t p = f->diag[i] + 1; p < f->rowptr[i + 1]; p++) { s -= f->lu[p] * z[f->colind[p]]; }
+      z[i] = s / f->lu[f->diag[i]];
+   }
+}
+
+void orc_ilu0_get(const orc_ilu *f, double *lu) { memcpy(lu, f->lu, sizeof(double) * (size_t)f->rowptr[f->n]); }
+void orc_ilu0_free(orc_ilu *f) { if (f) { free(f->lu); free(f->diag); free(f); } }
+
+static const orc_ilu *g_ilu = NULL;      /* preconditioner of the solve in progress (orc_gmres_ilu) */
+
 static void pc(int64_t n, const double *dinv, const double *r, double *z)
 {
+   if (g_ilu) { orc_ilu0_solve(g_ilu, r, z); return; }
    if (!dinv) { memcpy(z, r, sizeof(double) * n); return; }
    #pragma omp parallel for schedule(static)
    for (int64_t i = 0; i < n; i++) { z[i] = dinv[i] * r[i]; }
@@ -199,6 +252,15 @@ void orc_gmres(const orc_op *A, const double *dinv, const double *b, double *x,
    }
    res->iters = it; res->converged = conv; res->final_norm = rnorm; res->hist_len = hl;
    free(V); free(w); free(t); free(H); free(cs); free(sn); free(s); free(yv); free(hc);
+}
+
+/* the same GMRES with z = (LU)^{-1} r as the left preconditioner */
+void orc_gmres_ilu(const orc_op *A, const orc_ilu *ilu, const double *b, double *x,
+                   const orc_krylov_opts *o, orc_krylov_result *res, double *hist)
+{
+   g_ilu = ilu;
+   orc_gmres(A, NULL, b, x, o, res, hist);
+   g_ilu = NULL;
 }
 
 /* mfem::CGSolver::Mult (linalg/solvers.cpp), SURVEY.md C.6 */

@@ -83,6 +83,12 @@ def lib():
     L.orc_op_eliminate_rhs.argtypes = [vp, f64p, f64p]
     L.orc_gmres.argtypes = [vp, vp, f64p, f64p, C.POINTER(KOpts), C.POINTER(KRes), f64p]
     L.orc_cg.argtypes = [vp, vp, f64p, f64p, C.POINTER(KOpts), C.POINTER(KRes), f64p]
+    L.orc_ilu0_factor.argtypes = [i64, i64p, i32p, f64p]
+    L.orc_ilu0_factor.restype = vp
+    L.orc_ilu0_solve.argtypes = [vp, f64p, f64p]
+    L.orc_ilu0_get.argtypes = [vp, f64p]
+    L.orc_ilu0_free.argtypes = [vp]
+    L.orc_gmres_ilu.argtypes = [vp, vp, f64p, f64p, C.POINTER(KOpts), C.POINTER(KRes), f64p]
     L.orc_rule_coords.argtypes = [ci, ci, i64, i32p, f64p, f64p]
     L.orc_domain_lf.argtypes = [ci, ci, ci, i64, i32p, f64p, i32p, f64p, cd, f64p]
     L.orc_l2_error.argtypes = [ci, ci, ci, i64, i32p, f64p, i32p, vp, vp]
@@ -328,9 +334,43 @@ class CSR:
     def op(self):
         return Op(lib().orc_op_csr(self.n, self.rowptr, self.colind, self.vals), self.n, keep=self)
 
+    def ilu0(self):
+        """ILU(0) factors of this matrix (natural ordering): -pc_type bjacobi -sub_pc_type ilu on one rank"""
+        return ILU0(self)
+
+    def gmres_ilu(self, b, ilu, restart=0, max_it=2000, rtol=1e-10, atol=1e-12):
+        o = KOpts(0, restart, max_it, rtol, atol, 1)
+        r = KRes()
+        x = np.zeros(self.n)
+        hist = np.zeros(max_it + 2)
+        A = self.op()
+        lib().orc_gmres_ilu(A.h, ilu.h, np.ascontiguousarray(b, np.float64), x, C.byref(o), C.byref(r), hist)
+        return x, dict(iters=r.iters, converged=bool(r.converged), final_norm=r.final_norm, hist=hist[:r.hist_len].copy())
+
     def to_scipy(self):
         import scipy.sparse as sp
         return sp.csr_matrix((self.vals, self.colind, self.rowptr), shape=(self.n, self.n))
+
+
+class ILU0:
+    def __init__(self, A):
+        self.A = A
+        self.h = lib().orc_ilu0_factor(A.n, A.rowptr, A.colind, A.vals)
+
+    def solve(self, r):
+        z = np.zeros(self.A.n)
+        lib().orc_ilu0_solve(self.h, np.ascontiguousarray(r, np.float64), z)
+        return z
+
+    def factors(self):
+        lu = np.zeros(len(self.A.vals))
+        lib().orc_ilu0_get(self.h, lu)
+        return lu
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_ilu0_free(self.h)
+            self.h = None
 
 
 class Op:

@@ -1,0 +1,186 @@
+"""Data formats either side of the path and the host side of the triangle path (rank 3): Gmsh 2.2
+reader, Hilbert-curve element order, YAML / PETSc-options loaders, ParaView writer, triangle H1 numbering against an
+independent numpy restatement (oracle/tri_oracle.py), the oracle's ILU(0) against its defining property.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import cdm_b200 as cdm
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REF = "/root/reference/myapps/convection_diffusion"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return cdm.Context(host_only=True)
+
+
+def test_gmsh_fixture_meshes(ctx):
+    m = cdm.Mesh.read_gmsh(ctx, os.path.join(GOLD, "square_tri.msh"))
+    vx, ev, bv, ba = m.arrays()
+    assert m.dim == 2 and m.geometry == (1, 3, 2) and m.nv == 100 and m.nbe == 36 and sorted(set(ba.tolist())) == [1, 2, 3, 4]
+    a, b, c = vx[ev[:, 0]], vx[ev[:, 1]], vx[ev[:, 2]]
+    area = 0.5 * ((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0]))
+    assert area.min() > 0 and abs(area.sum() - 1.0) < 1e-14                        # counter-clockwise, covers the square
+    ln = lambda p, q: np.hypot(*(p - q).T)
+    assert np.all(ln(a, b) >= ln(b, c)) and np.all(ln(a, b) >= ln(c, a))           # refine=1: longest edge first
+    m0 = cdm.Mesh.read_gmsh(ctx, os.path.join(GOLD, "square_tri.msh"), refine=False)
+    assert np.array_equal(np.sort(m0.arrays()[1], axis=1), np.sort(ev, axis=1))    # same triangles, rotated only
+    # boundary attributes sit on the sides the physical names say (Mesh/unit_square.geo:18-21)
+    for attr, (axis, val) in {1: (1, 0.0), 2: (0, 1.0), 3: (1, 1.0), 4: (0, 0.0)}.items():
+        assert np.allclose(vx[bv[ba == attr]][:, :, axis], val)
+    d = cdm.Mesh.read_gmsh(ctx, os.path.join(GOLD, "disk_tri.msh"))
+    assert np.allclose(np.hypot(*d.arrays()[0][d.arrays()[2]].reshape(-1, 2).T), 1.0)
+    with pytest.raises(cdm.CdmError):
+        cdm.Mesh.read_gmsh(ctx, os.path.join(GOLD, "oracle_small.json"))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree is only present in the build container")
+def test_reference_meshes_and_inputs_load_unmodified(ctx):
+    """every mesh and every flat input file the reference ships"""
+    want = {"unit_square": (1, 510, 938, 80), "unit_circle": (1, 1593, 3056, 128), "square_0p01": (1, 515, 948, 80),
+            "ablation_strip": (0, 2880, 2629, 500), "ablation_strip_tri_uniform": (1, 917, 1676, 156)}
+    for name, (geom, nv, ne, nbe) in want.items():
+        m = cdm.Mesh.read_gmsh(ctx, f"{REF}/Mesh/{name}.msh")
+        assert (m.geometry[0], m.nv, m.ne, m.nbe) == (geom, nv, ne, nbe)
+    sp = cdm.H1Space(cdm.Mesh.read_gmsh(ctx, f"{REF}/Mesh/unit_square.msh"), 3)     # Input/input_2d.yaml: order 3
+    assert sp.ndof == 4342 and len(sp.essential_dofs(np.ones(4, np.int32))) == 240
+    cfg = cdm.Config(f"{REF}/Input/input_2d.yaml")
+    assert cfg.get("mesh_file") == "Mesh/unit_square.msh" and cfg.get("order", 1, int) == 3 and cfg.get("kappa", 0.0, float) == 0.1
+    assert cfg.get("cy", 0.0, float) == -2.0 and cfg.get("save_paraview", False, bool) is True and cfg.get("absent", "dflt") == "dflt"
+    assert cdm.Config(f"{REF}/Input/input.yaml").get("peclet", None, list) == [1.0, 10.0, 100.0]
+    o = cdm.GMRESSolver.from_petsc_options(f"{REF}/Input/petsc.opts").opts
+    assert (o.rtol, o.atol, o.max_it, o.restart, o.jacobi) == (1e-10, 1e-12, 500, 30, 1)
+    o = cdm.GMRESSolver.from_petsc_options(f"{REF}/Input/petsc_circle.opts").opts
+    assert (o.rtol, o.atol, o.max_it, o.jacobi) == (1e-10, 1e-12, 2000, 2)
+
+
+def test_yaml_and_petsc_options_loaders(tmp_path):
+    y = tmp_path / "in.yaml"
+    y.write_text("# comment\nmesh_file: Mesh/a b.msh   # trailing\norder: 3\nkappa: 1.0e-1\ncy: -2.0\nname: \"q # not a comment\"\n"
+                 "peclet: [1.0, 10.0, 100.0]\nsave_paraview: false\n---\n")
+    c = cdm.Config(y)
+    assert c.get("mesh_file") == "Mesh/a b.msh" and c.get("order", 0, int) == 3 and c.get("kappa", 0.0, float) == 0.1
+    assert c.get("name") == "q # not a comment" and c.get("peclet", None, list) == [1.0, 10.0, 100.0]
+    assert c.get("save_paraview", True, bool) is False and not c.has("nokey")
+    with pytest.raises(cdm.CdmError):
+        c.get("mesh_file", 0, int)
+    (tmp_path / "nested.yaml").write_text("a:\n  b: 1\n")
+    with pytest.raises(cdm.CdmError):
+        cdm.Config(tmp_path / "nested.yaml")
+    p = tmp_path / "petsc.opts"
+    p.write_text("# opts\n-ksp_type gmres\n-ksp_rtol 1.0e-10 -ksp_atol 1.0e-12\n-ksp_max_it 2000\n-pc_type bjacobi\n-sub_ksp_type preonly\n"
+                 "-sub_pc_type ilu\n-ksp_monitor\n-ksp_gmres_restart 50\n")
+    s = cdm.GMRESSolver.from_petsc_options(p)
+    assert s.ksp_type == "gmres" and (s.opts.rtol, s.opts.atol, s.opts.max_it, s.opts.restart, s.opts.jacobi) == (1e-10, 1e-12, 2000, 50, 2)
+    p.write_text("-ksp_type cg\n-pc_type none\n")
+    s = cdm.GMRESSolver.from_petsc_options(p)
+    assert s.ksp_type == "cg" and s.opts.jacobi == 0 and s.opts.rtol == 1e-5            # KSP default rtol
+    p.write_text("-pc_type gamg\n")
+    with pytest.raises(cdm.CdmError):
+        cdm.GMRESSolver.from_petsc_options(p)
+
+
+@pytest.mark.parametrize("n", [[4, 4], [5, 3], [7, 7], [16, 9], [2, 2, 2], [8, 8, 8], [3, 4, 5], [6, 5, 7]])
+def test_hilbert_curve_ordering(ctx, n):
+    """NCMesh::GridSfcOrdering: a permutation of the cells whose consecutive cells are neighbours (a few diagonal steps
+    appear on odd-sized 3-D grids, as in the generalised Hilbert curve itself); the mesh lists its elements along it"""
+    import ctypes as C
+    dim = len(n)
+    co = np.zeros((int(np.prod(n)), dim), np.int64)
+    assert cdm.lib().cdm_grid_sfc_ordering(dim, (C.c_int64 * 3)(*(n + [1] * (3 - dim))), co.ctypes.data_as(C.c_void_p)) == 0
+    lin = co[:, 0] + n[0] * (co[:, 1] + (n[1] * co[:, 2] if dim == 3 else 0))
+    assert np.array_equal(np.sort(lin), np.arange(len(lin))) and np.all(co[0] == 0)
+    step = np.abs(np.diff(co, axis=0))
+    assert step.max() == 1 and (step.sum(1) > 1).sum() <= (0 if dim == 2 else len(lin) // 20)
+    m, ms = cdm.Mesh.cartesian(ctx, dim, n, perturb=0.1), cdm.Mesh.cartesian(ctx, dim, n, perturb=0.1, sfc_ordering=True)
+    (vx, ev, bv, ba), (vxs, evs, bvs, bas) = m.arrays(), ms.arrays()
+    assert np.array_equal(vx, vxs) and np.array_equal(bv, bvs) and np.array_equal(evs, ev[lin])
+    sp, sps = cdm.H1Space(m, 2), cdm.H1Space(ms, 2)
+    assert sp.ndof == sps.ndof                                                           # same space, renumbered
+
+
+def test_paraview_writer(ctx, tmp_path):
+    import xml.etree.ElementTree as ET
+    for mesh, p in ((cdm.Mesh.read_gmsh(ctx, os.path.join(GOLD, "square_tri.msh")), 3), (cdm.Mesh.cartesian(ctx, 2, [3, 2]), 2),
+                    (cdm.Mesh.cartesian(ctx, 3, [2, 2, 1]), 3)):
+        sp = cdm.H1Space(mesh, p)
+        X = sp.dof_coords()
+        sp.write_paraview(tmp_path, "coll", {"u": X[:, 0] + 2 * X[:, 1], "u_exact": X[:, 0]}, cycle=3, time=0.25)
+        assert os.path.exists(tmp_path / "coll" / "coll.pvd") and os.path.exists(tmp_path / "coll" / "Cycle000003" / "data.pvtu")
+        piece = ET.parse(tmp_path / "coll" / "Cycle000003" / "proc000000.vtu").getroot().find("UnstructuredGrid/Piece")
+        sub = p ** mesh.dim
+        assert int(piece.get("NumberOfPoints")) == sp.ne * sp.nd and int(piece.get("NumberOfCells")) == sp.ne * sub
+        pts = np.array(piece.find("Points/DataArray").text.split(), float).reshape(-1, 3)
+        conn = np.array(piece.find("Cells/DataArray[@Name='connectivity']").text.split(), int)
+        vals = np.array(piece.find("PointData/DataArray[@Name='u']").text.split(), float)
+        assert np.allclose(vals, pts[:, 0] + 2 * pts[:, 1]) and conn.min() == 0 and conn.max() == sp.ne * sp.nd - 1
+        if mesh.dim == 2:                                                                # sub-cells tile the domain
+            vpc = 3 if sp.simplex else 4
+            c = pts[conn.reshape(-1, vpc)]
+            x, y = c[:, :, 0], c[:, :, 1]
+            area = 0.5 * np.abs(np.sum(x * np.roll(y, -1, 1) - np.roll(x, -1, 1) * y, axis=1))
+            assert abs(area.sum() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("mesh", ["square_tri", "disk_tri"])
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_triangle_numbering_matches_independent_restatement(ctx, mesh, p):
+    """element-to-dof map (native order = the E-vector order of simplices), essential dofs and dof coordinates of the C++
+    host code against the numpy restatement; bit-exact for the integer arrays"""
+    from oracle import tri_oracle as T
+    m = cdm.Mesh.read_gmsh(ctx, os.path.join(GOLD, mesh + ".msh"))
+    vx, ev, bv, ba = m.arrays()
+    sp = cdm.H1Space(m, p)
+    P = T.TriProblem(p, vx, ev, bv, ba)
+    g, o, i = sp.maps()
+    assert sp.ndof == P.ndof and sp.nd == P.nd and np.array_equal(g, P.elem_dof)
+    assert np.array_equal(sp.essential_dofs(np.ones(int(ba.max()), np.int32)), P.ess)
+    assert np.abs(sp.dof_coords() - P.coords()).max() < 1e-15
+    if int(ba.max()) == 4:
+        mk = np.array([0, 1, 0, 1], np.int32)
+        Px = T.TriProblem(p, vx, ev, bv, ba, ess_attrs=(2, 4))
+        assert np.array_equal(sp.essential_dofs(mk), Px.ess)
+
+
+def test_triangle_oracle_known_answers():
+    """the numpy triangle oracle itself: K 1 = 0, C 1 = 0, 1^T M 1 = area, symmetry, exactness of the nodal interpolation"""
+    from oracle import tri_oracle as T
+    ctx = cdm.Context(host_only=True)
+    vx, ev, bv, ba = cdm.Mesh.read_gmsh(ctx, os.path.join(GOLD, "square_tri.msh")).arrays()
+    for p in (1, 2, 3, 4):
+        one = np.ones(T.TriProblem(p, vx, ev, bv, ba).ndof)
+        K = T.TriProblem(p, vx, ev, bv, ba, kappa=1.0, vel=None, mass=None).csr().to_scipy()
+        Cm = T.TriProblem(p, vx, ev, bv, ba, kappa=None, vel=(1.0, -2.0), mass=None).csr().to_scipy()
+        M = T.TriProblem(p, vx, ev, bv, ba, kappa=None, vel=None, mass=1.0).csr().to_scipy()
+        assert abs(K @ one).max() < 1e-12 and abs(Cm @ one).max() < 1e-12 and abs(one @ (M @ one) - 1.0) < 1e-13
+        assert abs(K - K.T).max() < 1e-12 and abs(M - M.T).max() < 1e-14
+        B = T.eval_basis(p, T.tri_nodes(p))
+        assert np.abs(B - np.eye(len(B))).max() < 1e-12
+        P = T.TriProblem(p, vx, ev, bv, ba)
+        X = P.coords()
+        u = (1 + X[:, 0]) ** p - X[:, 1] ** p                                             # in P_p: interpolated exactly
+        xq = P.rule_coords(p + 2)
+        assert P.l2_error(u, (1 + xq[..., 0]) ** p - xq[..., 1] ** p, p + 2) < 1e-13
+
+
+def test_oracle_ilu0_defining_property(orc):
+    import scipy.sparse as sps
+    P = orc.Problem(2, 2, 6, perturb=0.1, vel=(1.0, -2.0))
+    A = P.csr()
+    b = np.random.default_rng(0).uniform(-1, 1, P.ndof)
+    A.eliminate(P.ess_mark, np.zeros(P.ndof), b)
+    f = A.ilu0()
+    F = sps.csr_matrix((f.factors(), A.colind, A.rowptr), shape=(A.n, A.n))
+    L, U = sps.tril(F, -1) + sps.eye(A.n), sps.triu(F, 0)
+    S = A.to_scipy()
+    mask = S.copy(); mask.data[:] = 1.0
+    assert abs((L @ U - S).multiply(mask)).max() < 1e-14                                   # (LU)_ij = a_ij on the pattern of A
+    z = f.solve(b)
+    assert np.linalg.norm(L @ (U @ z) - b) < 1e-13 * np.linalg.norm(b)
+    x, info = A.gmres_ilu(b, f)
+    _, info_j = A.op().gmres(b, dinv=1 / A.diag())
+    assert info["converged"] and info["iters"] < info_j["iters"]
+    assert np.linalg.norm(A.spmv(x) - b) < 1e-8 * np.linalg.norm(b)
