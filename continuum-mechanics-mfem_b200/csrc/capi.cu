@@ -653,7 +653,7 @@ int cdm_operator_create(cdm_space *sp, const cdm_coeff *kappa, const cdm_coeff *
    // default kernel per order (measured, profiles/): p=3 hand-specialised register-z kernel,
    // p>=4 the generic group kernel, p<=2 and 2D the block kernel
    // 3D defaults: sub-warp kernel (5) for orders 1-2, warp kernel (3) for order 3, group kernel (4) above
-   op->kernel_variant = (sp->dim != 3) ? 0 : (sp->p <= 2 ? 5 : (sp->p == 3 ? 3 : 4));
+   op->kernel_variant = (sp->dim != 3) ? (sp->p <= 4 ? 6 : 0) : (sp->p <= 2 ? 5 : (sp->p == 3 ? 3 : 4));
    *out = op;
    return CDM_OK;
 }
@@ -719,6 +719,7 @@ int cdm_operator_set_option(cdm_op *op, const char *name, int value)
    if (!std::strcmp(name, "grid_cap")) { if (value < 0) { return CDM_EINVAL; } op->grid_cap = value; return CDM_OK; }
    if (!std::strcmp(name, "host_pipeline")) { op->host_pipeline = value; return CDM_OK; }
    if (!std::strcmp(name, "overlap")) { if (value < 0 || value > 2) { return CDM_EINVAL; } op->overlap = value; return CDM_OK; }
+   if (!std::strcmp(name, "ilu_sweep")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->ilu_sweep = value; return CDM_OK; }
    return cdm_fail(op->sp->ctx, CDM_EINVAL, std::string("unknown option ") + name);
 }
 
@@ -729,6 +730,7 @@ int cdm_operator_get_option(const cdm_op *op, const char *name, int *value)
    if (!std::strcmp(name, "kernel")) { *value = op->kernel_variant; return CDM_OK; }
    if (!std::strcmp(name, "assembly")) { *value = op->assembly; return CDM_OK; }
    if (!std::strcmp(name, "overlap")) { *value = op->overlap; return CDM_OK; }
+   if (!std::strcmp(name, "ilu_sweep")) { *value = op->ilu_sweep; return CDM_OK; }
    if (!std::strcmp(name, "tail")) { *value = op->tail ? 1 : 0; return CDM_OK; }
    if (!std::strcmp(name, "ghost_in")) { *value = op->ghost_in ? 1 : 0; return CDM_OK; }
    // the protocol actually in use: 2 falls back to 0 when the peer-memory setup failed on any rank

@@ -187,6 +187,7 @@ struct cdm_op
    int assembly = 0;               // 0: partial assembly (matrix-free), 1: apply = SpMV with the assembled CSR matrix
    struct cdm_csr *csr = nullptr;  // csr_path.cu (built on demand)
    struct cdm_ilu *ilu = nullptr;  // precond.cu: ILU(0) of the assembled matrix (built on demand)
+   int ilu_sweep = 1;              // 1: single-launch triangular sweeps (dependency flags), 0: one launch per level
    int kernel_variant = 0;
    int64_t grid_cap = 0;           // > 0: upper bound on the persistent grids (tests: forces many elements per warp)
    double *e_out = nullptr;        // != null: E-vector output of the element kernels goes here and is not transposed
@@ -320,6 +321,7 @@ int cdm_ilu_setup(cdm_op *op);                      // symbolic (levels, host) +
 int cdm_ilu_refactor(cdm_op *op);                   // numeric factorisation only (new matrix values)
 int cdm_ilu_apply(cdm_op *op, const double *r, double *z);   // z = U^{-1} L^{-1} r; essential rows pass through
 void cdm_ilu_destroy(cdm_op *op);
+int cdm_ilu_check(cdm_op *op);                      // blocking: CDM_ECUDA if a single-launch sweep gave up waiting for a row
 // ---- peer-memory halo exchange (halo_p2p.cu)
 int cdm_halo_p2p_setup(cdm_space *sp);              // collective over the ranks of the communicator
 void cdm_halo_p2p_destroy(cdm_space *sp);

@@ -628,6 +628,7 @@ static int ensure_yE(cdm_op *op)
 int cdm_k_apply_p3(cdm_op *op, const int32_t *gmap, const double *xL, double *yL);   // kernels_apply_p3.cu
 int cdm_k_apply_group(cdm_op *op, const int32_t *gmap, const double *xL, double *yL);   // kernels_apply_warp.cu
 int cdm_k_apply_sub(cdm_op *op, const int32_t *gmap, const double *xL, double *yL);     // kernels_apply_sub.cu
+int cdm_k_apply_2d_thread(cdm_op *op, const int32_t *gmap, const double *xL, double *yL);   // kernels_apply_2d.cu
 
 #define LAUNCH3D(P, NBZ)                                                                              \
    case P: {                                                                                          \
@@ -663,7 +664,12 @@ int cdm_k_apply(cdm_op *op, const double *xL, double *yL, bool constrained)
    if (op->assembly == 1 && op->csr) { return cdm_k_csr_spmv(op, xL, yL, constrained); }   // the reference's literal path
    const int32_t *gmap = op->gmap_override ? op->gmap_override
                                            : ((constrained && op->gather_c_dev) ? op->gather_c_dev : sp->gather_dev);
-   if (sp->dim == 3 && op->kernel_variant == 4)
+   if (sp->dim == 2 && op->kernel_variant == 6)
+   {
+      const int rc = cdm_k_apply_2d_thread(op, gmap, xL, yL);
+      if (rc != 1) { return rc; }          // 1: order / integrator set not instantiated -> generic kernel
+   }
+   else if (sp->dim == 3 && op->kernel_variant == 4)
    {
       const int rc = cdm_k_apply_group(op, gmap, xL, yL);
       if (rc != 1) { return rc; }

@@ -226,6 +226,7 @@ extern "C" int cdm_gmres(cdm_op *op, const double *b, double *x, const cdm_krylo
    CDM_CUDA(c, cudaEventRecord(c->ev1, c->stream));
    CDM_CUDA(c, cudaEventSynchronize(c->ev1));
    RC(cdm_check_p2p(c));
+   if (ilu) { RC(cdm_ilu_check(op)); }
    float ms = 0.f;
    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
    res->iters = it; res->converged = conv; res->final_norm = rnorm; res->hist_len = hl;

@@ -10,9 +10,16 @@
 //              symbolic phases): row i depends on the rows k < i of its pattern (factorisation, forward solve) and on
 //              the rows j > i (backward solve);
 //   numeric  : one launch per level, one warp per row, IKJ elimination restricted to the pattern;
-//   apply    : z = U^{-1} L^{-1} r, one launch per level and sweep, one warp per row (shuffle reduction).
-// Level-scheduled sweeps are launch-bound on small matrices (hundreds of levels x ~4 us); that is the price of an
-// exact ILU(0) -- results match the sequential algorithm to round-off, which is what the parity tests check.
+//   apply    : z = U^{-1} L^{-1} r, one warp per row (lane-strided products, shuffle reduction).  Two schedules with
+//              identical arithmetic:
+//              * operator option "ilu_sweep" = 1 (default): ONE launch per sweep.  Rows are issued in level order, a warp
+//                waits on a per-row epoch flag (ld.acquire.gpu) for each entry it needs and publishes its own row with
+//                st.release.gpu -- the dependency chain then costs one L2 round trip per level instead of a kernel
+//                launch (3 850 levels at BASELINE config 2).  Forward progress: a row only waits for rows earlier in the
+//                issue order, and thread blocks are dispatched in index order; the spin is bounded and raises an error
+//                word instead of hanging the device.
+//              * "ilu_sweep" = 0: one launch per level and sweep (no inter-block assumptions; the fallback).
+// Either way the result matches the sequential algorithm to round-off, which is what the parity tests check.
 #include "cdm_internal.hpp"
 #include "kernels_common.cuh"
 #include <algorithm>
@@ -25,6 +32,8 @@ struct cdm_ilu
    int32_t *fwd_rows_dev = nullptr, *bwd_rows_dev = nullptr;    // rows grouped by level
    std::vector<int64_t> fwd_off, bwd_off;                        // level offsets into the two lists
    double *tmp_dev = nullptr;
+   unsigned int *ready_dev = nullptr;    // per-row epoch of the single-launch sweeps; [n] is the error word
+   unsigned int epoch = 0;
 };
 
 namespace
@@ -119,13 +128,66 @@ k_ilu_backward_level(int nrows, const int32_t *__restrict__ rows, const int64_t 
    s = warp_sum(s);
    if (lane == 0) { z[i] = (z[i] - s) / lu[d]; }
 }
+// ---- single-launch sweeps: row rows[w] of warp w waits for the rows it depends on through epoch flags
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
+{
+   unsigned int v;
+   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
+{ asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+constexpr unsigned int ILU_SPIN_LIMIT = 1u << 24;        // ~ seconds; a healthy sweep waits micro-seconds
+
+// value of row c once it has been published in this sweep (0 and the error word set if it never is)
+__device__ __forceinline__ double wait_row(const double *v, unsigned int *ready, int64_t n, int32_t c, unsigned int epoch)
+{
+   unsigned int spins = 0;
+   while (ld_acquire_u32(ready + c) != epoch)
+   {
+      if (++spins > ILU_SPIN_LIMIT) { atomicExch(ready + n, 1u); return 0.0; }
+      __nanosleep(20);
+   }
+   return __ldcg(v + c);
+}
+
+__global__ void __launch_bounds__(256)
+k_ilu_forward_flags(int64_t n, const int32_t *__restrict__ rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                    const int64_t *__restrict__ diag, const double *__restrict__ lu, const double *__restrict__ r, double *y,
+                    unsigned int *ready, unsigned int epoch)
+{
+   const int lane = threadIdx.x & 31;
+   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   if (w >= n) { return; }
+   const int32_t i = rows[w];
+   double s = 0.0;
+   for (int64_t p = rowptr[i] + lane; p < diag[i]; p += 32) { s += lu[p] * wait_row(y, ready, n, colind[p], epoch); }
+   s = warp_sum(s);
+   if (lane == 0) { y[i] = r[i] - s; __threadfence(); st_release_u32(ready + i, epoch); }
+}
+
+__global__ void __launch_bounds__(256)
+k_ilu_backward_flags(int64_t n, const int32_t *__restrict__ rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                     const int64_t *__restrict__ diag, const double *__restrict__ lu, double *z, unsigned int *ready, unsigned int epoch)
+{
+   const int lane = threadIdx.x & 31;
+   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   if (w >= n) { return; }
+   const int32_t i = rows[w];
+   const int64_t d = diag[i];
+   double s = 0.0;
+   for (int64_t p = d + 1 + lane; p < rowptr[i + 1]; p += 32) { s += lu[p] * wait_row(z, ready, n, colind[p], epoch); }
+   s = warp_sum(s);
+   if (lane == 0) { z[i] = (__ldcg(z + i) - s) / lu[d]; __threadfence(); st_release_u32(ready + i, epoch); }
+}
 }  // namespace
 
 void cdm_ilu_destroy(cdm_op *op)
 {
    cdm_ilu *f = op->ilu;
    if (!f) { return; }
-   cudaFree(f->lu_dev); cudaFree(f->diag_dev); cudaFree(f->fwd_rows_dev); cudaFree(f->bwd_rows_dev); cudaFree(f->tmp_dev);
+   cudaFree(f->lu_dev); cudaFree(f->diag_dev); cudaFree(f->fwd_rows_dev); cudaFree(f->bwd_rows_dev); cudaFree(f->tmp_dev); cudaFree(f->ready_dev);
    delete f;
    op->ilu = nullptr;
 }
@@ -190,10 +252,11 @@ int cdm_ilu_setup(cdm_op *op)
    auto fail = [&](int rc) { cdm_ilu_destroy(op); return rc; };
    if (cudaMalloc(&f->lu_dev, sizeof(double) * (size_t)m->nnz) != cudaSuccess || cudaMalloc(&f->diag_dev, sizeof(int64_t) * (size_t)n) != cudaSuccess ||
        cudaMalloc(&f->fwd_rows_dev, sizeof(int32_t) * (size_t)n) != cudaSuccess || cudaMalloc(&f->bwd_rows_dev, sizeof(int32_t) * (size_t)n) != cudaSuccess ||
-       cudaMalloc(&f->tmp_dev, sizeof(double) * (size_t)n) != cudaSuccess)
+       cudaMalloc(&f->tmp_dev, sizeof(double) * (size_t)n) != cudaSuccess || cudaMalloc(&f->ready_dev, sizeof(unsigned int) * (size_t)(n + 1)) != cudaSuccess)
    { cudaGetLastError(); return fail(cdm_fail(c, CDM_ENOMEM, "cdm_ilu_setup: out of device memory")); }
    cudaMemcpyAsync(f->fwd_rows_dev, fr.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
    cudaMemcpyAsync(f->bwd_rows_dev, br.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+   cudaMemsetAsync(f->ready_dev, 0, sizeof(unsigned int) * (size_t)(n + 1), c->stream);
    int rc = cdm_ilu_refactor(op);
    if (cudaStreamSynchronize(c->stream) != cudaSuccess && !rc) { rc = cdm_fail(c, CDM_ECUDA, "cdm_ilu_setup: device failure"); }
    return rc ? fail(rc) : CDM_OK;
@@ -205,6 +268,16 @@ int cdm_ilu_apply(cdm_op *op, const double *r, double *z)
    cdm_csr *m = op->csr;
    cdm_ilu *f = op->ilu;
    if (!m || !f) { return cdm_fail(c, CDM_EINVAL, "cdm_ilu_apply: no factorisation"); }
+   if (op->ilu_sweep == 1)
+   {
+      if (f->epoch > 0xfffffff0u) { CDM_CUDA(c, cudaMemsetAsync(f->ready_dev, 0, sizeof(unsigned int) * (size_t)f->n, c->stream)); f->epoch = 0; }
+      const unsigned nb = (unsigned)((f->n * 32 + 255) / 256);
+      k_ilu_forward_flags<<<nb, 256, 0, c->stream>>>(f->n, f->fwd_rows_dev, m->rowptr_dev, m->colind_dev, f->diag_dev, f->lu_dev, r, z, f->ready_dev, ++f->epoch);
+      k_ilu_backward_flags<<<nb, 256, 0, c->stream>>>(f->n, f->bwd_rows_dev, m->rowptr_dev, m->colind_dev, f->diag_dev, f->lu_dev, z, f->ready_dev, ++f->epoch);
+      c->launches += 2;
+      CDM_CUDA(c, cudaGetLastError());
+      return CDM_OK;
+   }
    for (size_t l = 0; l + 1 < f->fwd_off.size(); l++)
    {
       const int nr = (int)(f->fwd_off[l + 1] - f->fwd_off[l]);
@@ -219,6 +292,18 @@ int cdm_ilu_apply(cdm_op *op, const double *r, double *z)
    }
    c->launches += (int64_t)(f->fwd_off.size() + f->bwd_off.size()) - 2;
    CDM_CUDA(c, cudaGetLastError());
+   return CDM_OK;
+}
+
+int cdm_ilu_check(cdm_op *op)
+{
+   cdm_ctx *c = op->sp->ctx;
+   cdm_ilu *f = op->ilu;
+   if (!f || op->ilu_sweep != 1) { return CDM_OK; }
+   unsigned int err = 0;
+   CDM_CUDA(c, cudaMemcpyAsync(&err, f->ready_dev + f->n, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
+   CDM_CUDA(c, cudaStreamSynchronize(c->stream));
+   if (err) { return cdm_fail(c, CDM_ECUDA, "ILU(0) sweep: a row never became available (set operator option ilu_sweep = 0)"); }
    return CDM_OK;
 }
 

@@ -358,3 +358,49 @@ def test_two_contexts_one_process(torch, orc):
                 c.sync()
                 assert rel(yd.cpu().numpy(), y_ref) < APPLY_TOL
             del op, sp, mesh
+
+
+# ------------------------------------------------------------ (e) 2D: the thread-per-element kernel (option 6)
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+@pytest.mark.parametrize("which", ["full", "mass", "diff+mass", "diff"])
+def test_2d_thread_kernel_long_loops(torch, ctx, orc, p, which):
+    """kernel option 6 (default in 2D): a warp owns 32 elements per round; persistent grid capped to 2 blocks so every
+    warp re-arms its staging buffers several times and the last chunk is ragged (31 x 33 = 1023 elements); integrator
+    subsets, shuffled vertex numbering, both scatter modes, against the oracle and against the block kernel"""
+    kw = dict(full=dict(), mass=dict(kappa=None, vel=None, mass=1.3), diff=dict(kappa=0.3, vel=None, mass=None))
+    kw["diff+mass"] = dict(kappa=0.3, vel=None, mass=2.0)
+    P, mesh, sp = make(ctx, orc, 2, p, [31, 33], perturb=0.12, shuffle_seed=p, **kw[which])
+    D = Dev(torch, ctx)
+    x = np.random.default_rng(23).uniform(-1, 1, P.ndof)
+    y_ref, yc_ref = P.pa_apply(x), P.pa_op(True).mult(x)
+    xd, yd = D.up(x), D.zeros(P.ndof)
+    op = make_op(P, sp)
+    assert op.get_option("kernel") == 6
+    for cap in (0, 2):
+        op.set_option("grid_cap", cap)
+        for scatter in (0, 1):
+            op.set_option("scatter", scatter)
+            op.MultUnconstrained(xd, yd)
+            assert rel(D.down(yd), y_ref) < APPLY_TOL, (cap, scatter)
+            op.Mult(xd, yd)
+            assert rel(D.down(yd), yc_ref) < APPLY_TOL, (cap, scatter)
+    op.set_option("kernel", 0)
+    op.Mult(xd, yd)
+    assert rel(D.down(yd), yc_ref) < APPLY_TOL
+
+
+@pytest.mark.parametrize("p,n", [(2, 700), (3, 466)])
+def test_2d_at_size_matches_oracle(torch, ctx, orc, p, n):
+    """~2 M dofs in 2D (BASELINE config 1's element type at bench size): more chunks than resident warps, default kernel"""
+    P, mesh, sp = make(ctx, orc, 2, p, n, perturb=0.1)
+    D = Dev(torch, ctx)
+    x = np.random.default_rng(5).uniform(-1, 1, P.ndof)
+    xz = np.where(P.ess_mark, 0.0, x)
+    yc_ref = np.where(P.ess_mark, x, P.pa_apply_fast(xz))
+    op = make_op(P, sp)
+    xd, yd = D.up(x), D.zeros(P.ndof)
+    for scatter in (0, 1):
+        op.set_option("scatter", scatter)
+        op.Mult(xd, yd)
+        assert rel(D.down(yd), yc_ref) < APPLY_TOL

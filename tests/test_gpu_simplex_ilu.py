@@ -97,6 +97,13 @@ def test_ilu0_factors_sweeps_and_gmres_history(torch, ctx, orc, case):
     zd = d.zeros(P.ndof)
     op.ilu_apply(d.up(r), zd)
     assert rel(d.down(zd), f.solve(r)) <= 1e-12
+    # the single-launch sweeps (default) and the one-launch-per-level sweeps do the same arithmetic: bit-identical
+    assert op.get_option("ilu_sweep") == 1
+    op.set_option("ilu_sweep", 0)
+    z0 = d.zeros(P.ndof)
+    op.ilu_apply(d.up(r), z0)
+    assert np.array_equal(d.down(z0), d.down(zd))
+    op.set_option("ilu_sweep", 1)
     lf, lb = op.ilu_levels()
     assert 1 < lf < P.ndof and 1 < lb < P.ndof
     # GMRES(30), left-preconditioned, zero initial guess
