@@ -20,13 +20,14 @@ namespace
 {
 using namespace cdmk;
 
-template <int P, int NW, int NBUF, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
-__global__ void __launch_bounds__(NW * 32)
+template <int P, int NW, int NBUF, int MINB, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
+__global__ void __launch_bounds__(NW * 32, MINB)
 k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restrict__ gmap, const double *__restrict__ x,
                  const double *__restrict__ Dg, const int slab, const int sstride, double *__restrict__ y)
 {
    constexpr int D = P + 1, Q = P + 1, ND = D * D, Q2 = Q * Q;
    constexpr int OC = DIFF ? 3 : 0, OM = OC + (CONV ? 2 : 0);
+   constexpr bool PF = P <= 3;              // gather one chunk ahead (order 4 has no registers to spare for it)
    extern __shared__ __align__(128) unsigned char smraw[];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    double *wbuf = reinterpret_cast<double *>(smraw) + (size_t)wib * NBUF * 32 * sstride;
@@ -49,6 +50,16 @@ k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restri
       if (e < ne) { bulk_g2s_stream(wbuf + (size_t)(b * 32 + lane) * sstride, Dg + e * (int64_t)slab, slab_bytes, &bars[b]); }
    };
    if (gw < nchunks) { issue(gw, 0); }
+   // gather pipeline: the dofs of the next chunk are fetched while the current one is being processed
+   int32_t g[ND], gn[ND];
+   double u[ND];
+   {
+      const int64_t e = gw * 32 + lane;
+      #pragma unroll
+      for (int i = 0; i < ND; i++) { gn[i] = (PF && gw < nchunks && e < ne) ? __ldg(gmap + e * ND + i) : -1; }
+      #pragma unroll
+      for (int i = 0; i < ND; i++) { u[i] = (PF && gn[i] >= 0) ? __ldg(x + gn[i]) : 0.0; }
+   }
    int it = 0;
    for (int64_t chunk = gw; chunk < nchunks; chunk += nwarps, it++)
    {
@@ -57,13 +68,18 @@ k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restri
       if (NBUF == 2 && next < nchunks) { issue(next, b ^ 1); }     // the other buffer was consumed one iteration ago
       const int64_t e = chunk * 32 + lane;
       const bool valid = e < ne;
-      // ---- gather
-      int32_t g[ND];
-      double u[ND];
-      #pragma unroll
-      for (int i = 0; i < ND; i++) { g[i] = valid ? __ldg(gmap + e * ND + i) : -1; }
-      #pragma unroll
-      for (int i = 0; i < ND; i++) { u[i] = (g[i] >= 0) ? __ldg(x + g[i]) : 0.0; }
+      if (PF)
+      {
+         #pragma unroll
+         for (int i = 0; i < ND; i++) { g[i] = gn[i]; }
+      }
+      else
+      {
+         #pragma unroll
+         for (int i = 0; i < ND; i++) { g[i] = valid ? __ldg(gmap + e * ND + i) : -1; }
+         #pragma unroll
+         for (int i = 0; i < ND; i++) { u[i] = (g[i] >= 0) ? __ldg(x + g[i]) : 0.0; }
+      }
       // ---- x contraction: bu[dy][qx] = sum_dx B[qx][dx] u[dy][dx], gu with G
       double bu[D][Q], gu[D][Q];
       #pragma unroll
@@ -81,6 +97,16 @@ k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restri
             }
             bu[dy][qx] = s0; gu[dy][qx] = s1;
          }
+      }
+      // ---- u is dead: fetch the dofs of the next chunk (used one iteration from now)
+      if (PF)
+      {
+         const int64_t en = next * 32 + lane;
+         const bool nv = next < nchunks && en < ne;
+         #pragma unroll
+         for (int i = 0; i < ND; i++) { gn[i] = nv ? __ldg(gmap + en * ND + i) : -1; }
+         #pragma unroll
+         for (int i = 0; i < ND; i++) { u[i] = (gn[i] >= 0) ? __ldg(x + gn[i]) : 0.0; }
       }
       // ---- quadrature data of this chunk
       mbar_wait(&bars[b], (uint32_t)((NBUF == 2 ? (it >> 1) : it) & 1));
@@ -150,13 +176,13 @@ k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restri
 // rows of the staging buffer: >= slab doubles, = 2 (mod 4) so 128-bit shared loads of a quarter warp are conflict-free
 int staging_stride(int slab) { int s = slab; while ((s & 3) != 2) { s++; } return s; }
 
-template <int P, int NW, int NBUF, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
+template <int P, int NW, int NBUF, int MINB, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
 int launch_2d(cdm_op *op, const BasisTables &tb, const int32_t *gmap, const double *xL, double *out)
 {
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
    constexpr int ND = (P + 1) * (P + 1);
-   auto kern = k_apply2d_thread<P, NW, NBUF, DIFF, CONV, MASS, ATOMIC>;
+   auto kern = k_apply2d_thread<P, NW, NBUF, MINB, DIFF, CONV, MASS, ATOMIC>;
    const int sstride = staging_stride(op->slab);
    const size_t smem = (size_t)NW * NBUF * 32 * sstride * sizeof(double) + (size_t)NW * NBUF * sizeof(uint64_t);
    int blocks_per_sm = 0;
@@ -177,11 +203,11 @@ int launch_2d(cdm_op *op, const BasisTables &tb, const int32_t *gmap, const doub
    return CDM_OK;
 }
 
-template <int P, int NW, int NBUF>
+template <int P, int NW, int NBUF, int MINB>
 int dispatch_2d(cdm_op *op, const BasisTables &tb, const int32_t *gmap, const double *xL, double *out, bool atomic)
 {
-#define T2D_ONE(DF, CV, MS) (atomic ? launch_2d<P, NW, NBUF, DF, CV, MS, true>(op, tb, gmap, xL, out) \
-                                    : launch_2d<P, NW, NBUF, DF, CV, MS, false>(op, tb, gmap, xL, out))
+#define T2D_ONE(DF, CV, MS) (atomic ? launch_2d<P, NW, NBUF, MINB, DF, CV, MS, true>(op, tb, gmap, xL, out) \
+                                    : launch_2d<P, NW, NBUF, MINB, DF, CV, MS, false>(op, tb, gmap, xL, out))
    if (op->has_diff && op->has_conv && op->has_mass) { return T2D_ONE(true, true, true); }
    if (op->has_diff && !op->has_conv && op->has_mass) { return T2D_ONE(true, false, true); }
    if (!op->has_diff && !op->has_conv && op->has_mass) { return T2D_ONE(false, false, true); }
@@ -191,13 +217,28 @@ int dispatch_2d(cdm_op *op, const BasisTables &tb, const int32_t *gmap, const do
 }
 }  // namespace
 
+// per order: warps per block (NW), staging buffers per warp (NB), resident blocks the register budget is sized for (MB).
+// Measured at 8 M dofs (profiles/r02_sweep2d_variants.md): p=2 (4,2,2) 90.6 % / (4,1,3) 87.7 % / (4,1,4) 81.1 %;
+// p=3 (4,2,1) 70.2 % / (4,1,2) 74.5 % / (8,1,1) 75.1 %; p=4 (4,1,1) 49.8 % / (2,1,2) 50.4 % / (2,2,1) 30.2 %.
+#ifndef CDM_2D_P1_NW
+#define CDM_2D_P1_NW 4
+#define CDM_2D_P1_NB 2
+#define CDM_2D_P1_MB 4
+#endif
+#ifndef CDM_2D_P2_NW
+#define CDM_2D_P2_NW 4
+#define CDM_2D_P2_NB 2
+#define CDM_2D_P2_MB 2
+#endif
 #ifndef CDM_2D_P3_NW
 #define CDM_2D_P3_NW 4
-#define CDM_2D_P3_NBUF 2
+#define CDM_2D_P3_NB 1
+#define CDM_2D_P3_MB 2
 #endif
 #ifndef CDM_2D_P4_NW
 #define CDM_2D_P4_NW 4
-#define CDM_2D_P4_NBUF 1
+#define CDM_2D_P4_NB 1
+#define CDM_2D_P4_MB 1
 #endif
 
 // returns 1 when this operator is not covered (caller falls back to the generic kernel)
@@ -222,10 +263,10 @@ int cdm_k_apply_2d_thread(cdm_op *op, const int32_t *gmap, const double *xL, dou
    int rc = 1;
    switch (sp->p)
    {
-      case 1: rc = dispatch_2d<1, 4, 2>(op, tb, gmap, xL, out, atomic); break;
-      case 2: rc = dispatch_2d<2, 4, 2>(op, tb, gmap, xL, out, atomic); break;
-      case 3: rc = dispatch_2d<3, CDM_2D_P3_NW, CDM_2D_P3_NBUF>(op, tb, gmap, xL, out, atomic); break;
-      case 4: rc = dispatch_2d<4, CDM_2D_P4_NW, CDM_2D_P4_NBUF>(op, tb, gmap, xL, out, atomic); break;
+      case 1: rc = dispatch_2d<1, CDM_2D_P1_NW, CDM_2D_P1_NB, CDM_2D_P1_MB>(op, tb, gmap, xL, out, atomic); break;
+      case 2: rc = dispatch_2d<2, CDM_2D_P2_NW, CDM_2D_P2_NB, CDM_2D_P2_MB>(op, tb, gmap, xL, out, atomic); break;
+      case 3: rc = dispatch_2d<3, CDM_2D_P3_NW, CDM_2D_P3_NB, CDM_2D_P3_MB>(op, tb, gmap, xL, out, atomic); break;
+      case 4: rc = dispatch_2d<4, CDM_2D_P4_NW, CDM_2D_P4_NB, CDM_2D_P4_MB>(op, tb, gmap, xL, out, atomic); break;
    }
    if (rc) { return rc; }
    if (!atomic && !op->e_out) { return cdm_k_restrict_transpose(sp, op->yE_dev, yL); }

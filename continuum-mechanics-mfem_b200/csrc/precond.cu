@@ -13,9 +13,9 @@
 //   apply    : z = U^{-1} L^{-1} r, one warp per row (lane-strided products, shuffle reduction).  Two schedules with
 //              identical arithmetic:
 //              * operator option "ilu_sweep" = 1 (default): ONE launch per sweep.  Rows are issued in level order, a warp
-//                waits on a per-row epoch flag (ld.acquire.gpu) for each entry it needs and publishes its own row with
-//                st.release.gpu -- the dependency chain then costs one L2 round trip per level instead of a kernel
-//                launch (3 850 levels at BASELINE config 2).  Forward progress: a row only waits for rows earlier in the
+//                polls the result word of each row it needs (pre-filled with a NaN pattern no computation produces; value and
+//                flag are one 8-byte word, so no fences) -- the dependency chain then costs one L2 round trip per level
+//                instead of a kernel launch (3 850 levels at BASELINE config 2).  Forward progress: a row only waits for rows earlier in the
 //                issue order, and thread blocks are dispatched in index order; the spin is bounded and raises an error
 //                word instead of hanging the device.
 //              * "ilu_sweep" = 0: one launch per level and sweep (no inter-block assumptions; the fallback).
@@ -32,8 +32,7 @@ struct cdm_ilu
    int32_t *fwd_rows_dev = nullptr, *bwd_rows_dev = nullptr;    // rows grouped by level
    std::vector<int64_t> fwd_off, bwd_off;                        // level offsets into the two lists
    double *tmp_dev = nullptr;
-   unsigned int *ready_dev = nullptr;    // per-row epoch of the single-launch sweeps; [n] is the error word
-   unsigned int epoch = 0;
+   unsigned int *err_dev = nullptr;      // error word of the single-launch sweeps (a row never became available)
 };
 
 namespace
@@ -128,48 +127,61 @@ k_ilu_backward_level(int nrows, const int32_t *__restrict__ rows, const int64_t 
    s = warp_sum(s);
    if (lane == 0) { z[i] = (z[i] - s) / lu[d]; }
 }
-// ---- single-launch sweeps: row rows[w] of warp w waits for the rows it depends on through epoch flags
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
-{
-   unsigned int v;
-   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-   return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
-{ asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-
+// ---- single-launch sweeps: the warp of row rows[w] waits for the rows it depends on.  Value and "ready" flag are the
+// same 8-byte word: the result vector is pre-filled with a NaN pattern no computation produces, a consumer polls the
+// word until it changes (one L2 round trip per dependency level, no fences: an aligned 8-byte store is single-copy
+// atomic).  The forward sweep writes y into `tmp` and arms z for the backward sweep; the backward sweep consumes
+// tmp[i] and re-arms it for the next application.
+constexpr unsigned long long ILU_PENDING = 0xFFF8C0DEC0DEC0DEull;
 constexpr unsigned int ILU_SPIN_LIMIT = 1u << 24;        // ~ seconds; a healthy sweep waits micro-seconds
 
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const double *p)
+{
+   unsigned long long v;
+   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+   return v;
+}
+
 // value of row c once it has been published in this sweep (0 and the error word set if it never is)
-__device__ __forceinline__ double wait_row(const double *v, unsigned int *ready, int64_t n, int32_t c, unsigned int epoch)
+__device__ __forceinline__ double wait_row(const double *v, unsigned int *err, int32_t c)
 {
    unsigned int spins = 0;
-   while (ld_acquire_u32(ready + c) != epoch)
+   unsigned long long w;
+   while ((w = ld_volatile_u64(v + c)) == ILU_PENDING)
    {
-      if (++spins > ILU_SPIN_LIMIT) { atomicExch(ready + n, 1u); return 0.0; }
-      __nanosleep(20);
+      if (++spins > ILU_SPIN_LIMIT) { atomicExch(err, 1u); return 0.0; }
    }
-   return __ldcg(v + c);
+   return __longlong_as_double((long long)w);
+}
+
+__global__ void __launch_bounds__(256) k_ilu_arm(int64_t n, double *v)
+{
+   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { reinterpret_cast<unsigned long long *>(v)[i] = ILU_PENDING; }
 }
 
 __global__ void __launch_bounds__(256)
 k_ilu_forward_flags(int64_t n, const int32_t *__restrict__ rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
-                    const int64_t *__restrict__ diag, const double *__restrict__ lu, const double *__restrict__ r, double *y,
-                    unsigned int *ready, unsigned int epoch)
+                    const int64_t *__restrict__ diag, const double *__restrict__ lu, const double *__restrict__ r, double *y, double *z,
+                    unsigned int *err)
 {
    const int lane = threadIdx.x & 31;
    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
    if (w >= n) { return; }
    const int32_t i = rows[w];
    double s = 0.0;
-   for (int64_t p = rowptr[i] + lane; p < diag[i]; p += 32) { s += lu[p] * wait_row(y, ready, n, colind[p], epoch); }
+   for (int64_t p = rowptr[i] + lane; p < diag[i]; p += 32) { s += lu[p] * wait_row(y, err, colind[p]); }
    s = warp_sum(s);
-   if (lane == 0) { y[i] = r[i] - s; __threadfence(); st_release_u32(ready + i, epoch); }
+   if (lane == 0)
+   {
+      y[i] = r[i] - s;
+      reinterpret_cast<unsigned long long *>(z)[i] = ILU_PENDING;       // arm the backward sweep (a later launch)
+   }
 }
 
 __global__ void __launch_bounds__(256)
 k_ilu_backward_flags(int64_t n, const int32_t *__restrict__ rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
-                     const int64_t *__restrict__ diag, const double *__restrict__ lu, double *z, unsigned int *ready, unsigned int epoch)
+                     const int64_t *__restrict__ diag, const double *__restrict__ lu, double *y, double *z, unsigned int *err)
 {
    const int lane = threadIdx.x & 31;
    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -177,9 +189,13 @@ k_ilu_backward_flags(int64_t n, const int32_t *__restrict__ rows, const int64_t 
    const int32_t i = rows[w];
    const int64_t d = diag[i];
    double s = 0.0;
-   for (int64_t p = d + 1 + lane; p < rowptr[i + 1]; p += 32) { s += lu[p] * wait_row(z, ready, n, colind[p], epoch); }
+   for (int64_t p = d + 1 + lane; p < rowptr[i + 1]; p += 32) { s += lu[p] * wait_row(z, err, colind[p]); }
    s = warp_sum(s);
-   if (lane == 0) { z[i] = (__ldcg(z + i) - s) / lu[d]; __threadfence(); st_release_u32(ready + i, epoch); }
+   if (lane == 0)
+   {
+      z[i] = (y[i] - s) / lu[d];
+      reinterpret_cast<unsigned long long *>(y)[i] = ILU_PENDING;       // re-arm the forward sweep of the next application
+   }
 }
 }  // namespace
 
@@ -187,7 +203,7 @@ void cdm_ilu_destroy(cdm_op *op)
 {
    cdm_ilu *f = op->ilu;
    if (!f) { return; }
-   cudaFree(f->lu_dev); cudaFree(f->diag_dev); cudaFree(f->fwd_rows_dev); cudaFree(f->bwd_rows_dev); cudaFree(f->tmp_dev); cudaFree(f->ready_dev);
+   cudaFree(f->lu_dev); cudaFree(f->diag_dev); cudaFree(f->fwd_rows_dev); cudaFree(f->bwd_rows_dev); cudaFree(f->tmp_dev); cudaFree(f->err_dev);
    delete f;
    op->ilu = nullptr;
 }
@@ -252,11 +268,12 @@ int cdm_ilu_setup(cdm_op *op)
    auto fail = [&](int rc) { cdm_ilu_destroy(op); return rc; };
    if (cudaMalloc(&f->lu_dev, sizeof(double) * (size_t)m->nnz) != cudaSuccess || cudaMalloc(&f->diag_dev, sizeof(int64_t) * (size_t)n) != cudaSuccess ||
        cudaMalloc(&f->fwd_rows_dev, sizeof(int32_t) * (size_t)n) != cudaSuccess || cudaMalloc(&f->bwd_rows_dev, sizeof(int32_t) * (size_t)n) != cudaSuccess ||
-       cudaMalloc(&f->tmp_dev, sizeof(double) * (size_t)n) != cudaSuccess || cudaMalloc(&f->ready_dev, sizeof(unsigned int) * (size_t)(n + 1)) != cudaSuccess)
+       cudaMalloc(&f->tmp_dev, sizeof(double) * (size_t)n) != cudaSuccess || cudaMalloc(&f->err_dev, sizeof(unsigned int)) != cudaSuccess)
    { cudaGetLastError(); return fail(cdm_fail(c, CDM_ENOMEM, "cdm_ilu_setup: out of device memory")); }
    cudaMemcpyAsync(f->fwd_rows_dev, fr.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
    cudaMemcpyAsync(f->bwd_rows_dev, br.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
-   cudaMemsetAsync(f->ready_dev, 0, sizeof(unsigned int) * (size_t)(n + 1), c->stream);
+   cudaMemsetAsync(f->err_dev, 0, sizeof(unsigned int), c->stream);
+   k_ilu_arm<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, f->tmp_dev);
    int rc = cdm_ilu_refactor(op);
    if (cudaStreamSynchronize(c->stream) != cudaSuccess && !rc) { rc = cdm_fail(c, CDM_ECUDA, "cdm_ilu_setup: device failure"); }
    return rc ? fail(rc) : CDM_OK;
@@ -270,10 +287,9 @@ int cdm_ilu_apply(cdm_op *op, const double *r, double *z)
    if (!m || !f) { return cdm_fail(c, CDM_EINVAL, "cdm_ilu_apply: no factorisation"); }
    if (op->ilu_sweep == 1)
    {
-      if (f->epoch > 0xfffffff0u) { CDM_CUDA(c, cudaMemsetAsync(f->ready_dev, 0, sizeof(unsigned int) * (size_t)f->n, c->stream)); f->epoch = 0; }
       const unsigned nb = (unsigned)((f->n * 32 + 255) / 256);
-      k_ilu_forward_flags<<<nb, 256, 0, c->stream>>>(f->n, f->fwd_rows_dev, m->rowptr_dev, m->colind_dev, f->diag_dev, f->lu_dev, r, z, f->ready_dev, ++f->epoch);
-      k_ilu_backward_flags<<<nb, 256, 0, c->stream>>>(f->n, f->bwd_rows_dev, m->rowptr_dev, m->colind_dev, f->diag_dev, f->lu_dev, z, f->ready_dev, ++f->epoch);
+      k_ilu_forward_flags<<<nb, 256, 0, c->stream>>>(f->n, f->fwd_rows_dev, m->rowptr_dev, m->colind_dev, f->diag_dev, f->lu_dev, r, f->tmp_dev, z, f->err_dev);
+      k_ilu_backward_flags<<<nb, 256, 0, c->stream>>>(f->n, f->bwd_rows_dev, m->rowptr_dev, m->colind_dev, f->diag_dev, f->lu_dev, f->tmp_dev, z, f->err_dev);
       c->launches += 2;
       CDM_CUDA(c, cudaGetLastError());
       return CDM_OK;
@@ -301,8 +317,14 @@ int cdm_ilu_check(cdm_op *op)
    cdm_ilu *f = op->ilu;
    if (!f || op->ilu_sweep != 1) { return CDM_OK; }
    unsigned int err = 0;
-   CDM_CUDA(c, cudaMemcpyAsync(&err, f->ready_dev + f->n, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
+   CDM_CUDA(c, cudaMemcpyAsync(&err, f->err_dev, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
    CDM_CUDA(c, cudaStreamSynchronize(c->stream));
+   if (err)
+   {
+      // leave the sweeps usable: clear the word and re-arm the forward buffer
+      cudaMemsetAsync(f->err_dev, 0, sizeof(unsigned int), c->stream);
+      k_ilu_arm<<<(unsigned)((f->n + 255) / 256), 256, 0, c->stream>>>(f->n, f->tmp_dev);
+   }
    if (err) { return cdm_fail(c, CDM_ECUDA, "ILU(0) sweep: a row never became available (set operator option ilu_sweep = 0)"); }
    return CDM_OK;
 }
