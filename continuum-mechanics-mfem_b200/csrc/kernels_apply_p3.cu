@@ -611,10 +611,17 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
          #pragma unroll
          for (int dx = 0; dx < D; dx++)
          {
+#ifdef CDM_P3_SPLIT_B3
+            double a = 0.0, ag = 0.0;
+            #pragma unroll
+            for (int q = 0; q < Q; q++) { a += tb.B[q * D + dx] * a2[q]; if (DIFF) { ag += tb.G[q * D + dx] * a1[q]; } }
+            yv[dx] = a + ag;
+#else
             double a = 0.0;
             #pragma unroll
             for (int q = 0; q < Q; q++) { a += tb.B[q * D + dx] * a2[q]; if (DIFF) { a += tb.G[q * D + dx] * a1[q]; } }
             yv[dx] = a;
+#endif
          }
          if (ATOMIC)
          {

@@ -326,14 +326,20 @@ k_apply3d_sub(const SubTables tb, const int64_t ne, const int32_t *__restrict__ 
          const int dy = sl % D, dz = sl / D;
          #pragma unroll
          for (int q = 0; q < Q; q++) { a2[q] = sP1[q + PA * dy + PB * dz]; if (DIFF) { a1[q] = sP0[q + PA * dy + PB * dz]; } }
+         double yv[D];                                       // results first, scatter after: the asm red.add is a compiler barrier
          #pragma unroll
          for (int dx = 0; dx < D; dx++)
          {
             double a = 0.0;
             #pragma unroll
             for (int q = 0; q < Q; q++) { a += tb.B[q * D + dx] * a2[q]; if (DIFF) { a += tb.G[q * D + dx] * a1[q]; } }
-            if (ATOMIC) { s_red_add_f64_if(y, g[dx], a); }
-            else if (act) { y[e * ND + D * sl + dx] = a; }
+            yv[dx] = a;
+         }
+         #pragma unroll
+         for (int dx = 0; dx < D; dx++)
+         {
+            if (ATOMIC) { s_red_add_f64_if(y, g[dx], yv[dx]); }
+            else if (act) { y[e * ND + D * sl + dx] = yv[dx]; }
          }
       }
       __syncwarp();                                          // P buffers are rewritten by the next element's F1

@@ -55,11 +55,14 @@ template <int P> struct GroupCfg
    static constexpr int D = P + 1, Q = P + 2, T = Q * Q, ND = D * D * D;
    static constexpr int EPW = (T <= 10) ? 3 : (T <= 16 ? 2 : 1);   // groups per warp
    static constexpr int WPG = (T <= 32) ? 1 : 2;                   // warps per group
-   static constexpr int GPB = (P <= 3) ? 4 * EPW : (P == 4 ? 2 : 1);   // groups per block
+   #ifndef CDM_G4_GPB
+#define CDM_G4_GPB 2
+#endif
+   static constexpr int GPB = (P <= 3) ? 4 * EPW : (P == 4 ? CDM_G4_GPB : 1);   // groups per block (two-warp groups: the block IS the group)
    static constexpr int THREADS = (WPG == 1) ? 32 * (GPB / EPW) : 64 * GPB;
 // resident blocks per SM the register budget is sized for.  p=5: 5 blocks fit the shared memory, but the
 // 204-register cap of MINB = 5 made ptxas spill 200 B inside the element loop (53 % of the roofline);
-// MINB = 4 -> 160 registers, no spills, 73 %.  p=4: MINB 3 / 4 / 5 -> 46 % / 76 % / 56 %.
+// MINB = 4 -> 160 registers, no spills, 73 %.  p=4 (two groups per block): MINB 3 / 4 / 5 -> 46 % / 76 % / 56 %; one group per block x 8 blocks: 52 %.
 #ifndef CDM_G5_MINB
 #define CDM_G5_MINB 4
 #endif
@@ -111,6 +114,10 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    auto gsync = [&]()
    {
       if (C::WPG == 1) { __syncwarp(); }
+#ifndef CDM_G_REGBAR
+      else if (C::GPB == 1) { __syncthreads(); }             // the block is the group: barrier 0, immediate operand (a register
+                                                             // barrier id showed up as 4-12 % branch_resolving stalls)
+#endif
       else { asm volatile("bar.sync %0, 64;" ::"r"(gsafe + 1) : "memory"); }
    };
 
@@ -321,12 +328,27 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
          double a1[Q], a2[Q];
          #pragma unroll
          for (int q = 0; q < Q; q++) { a2[q] = sP1[q + PST * t1]; if (DIFF) { a1[q] = sP0[q + PST * t1]; } }
+         // all D results first (2 D independent accumulation chains), then the scatter: a red.add inside the dx loop is
+         // a compiler barrier (asm volatile, "memory") and serialised the chains -- 15 % of the stall samples at p = 5, 6
+         constexpr bool SPLIT = P >= 5;                     // p = 4 runs at its 128-register cap: one accumulator per dx
+         double yb[D], yg[SPLIT ? D : 1];
          #pragma unroll
          for (int dx = 0; dx < D; dx++)
          {
-            double a = 0.0;
+            double sb = 0.0, sg = 0.0;
             #pragma unroll
-            for (int q = 0; q < Q; q++) { a += tb.B[q * D + dx] * a2[q]; if (DIFF) { a += tb.G[q * D + dx] * a1[q]; } }
+            for (int q = 0; q < Q; q++)
+            {
+               sb += tb.B[q * D + dx] * a2[q];
+               if (DIFF) { if (SPLIT) { sg += tb.G[q * D + dx] * a1[q]; } else { sb += tb.G[q * D + dx] * a1[q]; } }
+            }
+            yb[dx] = sb;
+            if (SPLIT) { yg[dx] = sg; }
+         }
+         #pragma unroll
+         for (int dx = 0; dx < D; dx++)
+         {
+            const double a = SPLIT ? yb[dx] + yg[dx] : yb[dx];
             if (ATOMIC) { if (g[dx] >= 0) { g_red_add(y + g[dx], a); } }
             else { y[e * ND + D * t1 + dx] = a; }
          }
