@@ -29,42 +29,15 @@ struct WarpTables
    double Dq[CDM_MAX_Q1D * CDM_MAX_Q1D];   // collocation derivative, Dq[i*Q + k] = l_k'(x_i) on the Gauss points
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-   asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (TMA engine)
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-   // D is read exactly once per apply: mark its lines evict-first in L2 so that the stream does not push
-   // out the x / y vectors, which are re-read (gather) and re-written (red.add) by neighbouring elements
-   uint64_t pol;
-   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void red_add_f64(double *addr, double v)
-{
-   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
-}
+// mbarrier / bulk-async copy / red.add helpers: kernels_common.cuh (namespace cdmk); the D stream is evict-first in L2:
+// it is read exactly once per apply and must not push out the x / y vectors, which are re-read (gather) and re-written
+// (red.add) by neighbouring elements
+using cdmk::smem_u32;
+using cdmk::mbar_init;
+using cdmk::mbar_expect_tx;
+using cdmk::mbar_wait;
+using cdmk::red_add_f64;
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { cdmk::bulk_g2s_stream(dst, src, bytes, bar); }
 // y[g] += v unless g < 0 (essential dof).  A predicated red (-DCDM_P3_PREDICATED_RED) measured the same as
 // the branch within run-to-run noise on config 2, so the branch stays.
 __device__ __forceinline__ void red_add_f64_if(double *y, int g, double v)
@@ -72,8 +45,7 @@ __device__ __forceinline__ void red_add_f64_if(double *y, int g, double v)
 #ifndef CDM_P3_PREDICATED_RED
    if (g >= 0) { red_add_f64(y + g, v); }
 #else
-   asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %2, 0;\n@p red.global.add.f64 [%0], %1;\n}\n"
-                ::"l"(y + g), "d"(v), "r"(g) : "memory");
+   cdmk::red_add_f64_pred(y, g, v);
 #endif
 }
 

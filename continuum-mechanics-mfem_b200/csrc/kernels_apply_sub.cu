@@ -34,41 +34,14 @@ template <int D, int Q> struct SubCfg;
 template <> struct SubCfg<2, 3> { static constexpr int EPW = 3, PA = 3, PB = 6, RB = 9, EMOD = 10; static constexpr bool WHOLE = true; };
 template <> struct SubCfg<3, 4> { static constexpr int EPW = 2, PA = 5, PB = 20, RB = 20, EMOD = 0; static constexpr bool WHOLE = false; };
 
-__device__ __forceinline__ uint32_t s_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void s_mbar_init(uint64_t *bar, uint32_t count)
-{
-   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void s_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void s_mbar_wait(uint64_t *bar, uint32_t parity)
-{
-   asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(s_smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D bulk async copy global -> shared (TMA engine), L2 evict-first: D is read exactly once per apply
-__device__ __forceinline__ void s_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-   uint64_t pol;
-   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                ::"r"(s_smem_u32(dst)), "l"(src), "r"(bytes), "r"(s_smem_u32(bar)), "l"(pol) : "memory");
-}
+// mbarrier / bulk-async copy (L2 evict-first: D is read exactly once per apply) / predicated red.add helpers:
+// kernels_common.cuh (namespace cdmk)
+__device__ __forceinline__ void s_mbar_init(uint64_t *bar, uint32_t count) { cdmk::mbar_init(bar, count); }
+__device__ __forceinline__ void s_mbar_expect_tx(uint64_t *bar, uint32_t bytes) { cdmk::mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void s_mbar_wait(uint64_t *bar, uint32_t parity) { cdmk::mbar_wait(bar, parity); }
+__device__ __forceinline__ void s_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { cdmk::bulk_g2s_stream(dst, src, bytes, bar); }
 // y[g] += v unless g < 0 (essential dof / element owned by nobody): predicated, no branch
-__device__ __forceinline__ void s_red_add_f64_if(double *y, int g, double v)
-{
-   asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %2, 0;\n@p red.global.add.f64 [%0], %1;\n}\n"
-                ::"l"(y + g), "d"(v), "r"(g) : "memory");
-}
+__device__ __forceinline__ void s_red_add_f64_if(double *y, int g, double v) { cdmk::red_add_f64_pred(y, g, v); }
 
 template <int D, int Q>
 __host__ __device__ constexpr int sub_elem_doubles(int slab)

@@ -22,33 +22,12 @@ struct GroupTables
    double G[CDM_MAX_Q1D * CDM_MAX_D1D];
 };
 
-__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void g_mbar_init(uint64_t *bar, uint32_t count)
-{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory"); }
-__device__ __forceinline__ void g_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void g_mbar_wait(uint64_t *bar, uint32_t parity)
-{
-   asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "GWAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra GDONE_%=;\n"
-      "bra GWAIT_%=;\n"
-      "GDONE_%=:\n"
-      "}\n" ::"r"(s_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void g_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-   // evict-first: the D stream must not push the x / y vectors out of L2 (see kernels_apply_p3.cu)
-   uint64_t pol;
-   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void g_red_add(double *addr, double v)
-{ asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory"); }
+// mbarrier / bulk-async copy / red.add helpers: kernels_common.cuh (namespace cdmk)
+__device__ __forceinline__ void g_mbar_init(uint64_t *bar, uint32_t count) { cdmk::mbar_init(bar, count); }
+__device__ __forceinline__ void g_mbar_expect_tx(uint64_t *bar, uint32_t bytes) { cdmk::mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void g_mbar_wait(uint64_t *bar, uint32_t parity) { cdmk::mbar_wait(bar, parity); }
+__device__ __forceinline__ void g_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { cdmk::bulk_g2s_stream(dst, src, bytes, bar); }
+__device__ __forceinline__ void g_red_add(double *addr, double v) { cdmk::red_add_f64(addr, v); }
 
 template <int P> struct GroupCfg
 {

@@ -76,4 +76,10 @@ __device__ __forceinline__ void bulk_g2s_stream(void *dst, const void *src, uint
 }
 __device__ __forceinline__ void red_add_f64(double *addr, double v)
 { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory"); }
+// y[g] += v unless g < 0 (essential dof), as one predicated instruction
+__device__ __forceinline__ void red_add_f64_pred(double *y, int g, double v)
+{
+   asm volatile("{\n.reg .pred p;\nsetp.ge.s32 p, %2, 0;\n@p red.global.add.f64 [%0], %1;\n}\n"
+                ::"l"(y + g), "d"(v), "r"(g) : "memory");
+}
 }  // namespace cdmk
