@@ -717,7 +717,8 @@ int cdm_operator_set_option(cdm_op *op, const char *name, int value)
    if (!std::strcmp(name, "ghost_in")) { op->ghost_in = value != 0; return CDM_OK; }
    if (!std::strcmp(name, "allreduce")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->sp->ctx->allreduce_mode = value; return CDM_OK; }
    if (!std::strcmp(name, "grid_cap")) { if (value < 0) { return CDM_EINVAL; } op->grid_cap = value; return CDM_OK; }
-   if (!std::strcmp(name, "host_pipeline")) { op->host_pipeline = value; return CDM_OK; }
+   if (!std::strcmp(name, "host_pipeline")) { op->host_pipeline = value; destroy_host_pipe(op); return CDM_OK; }
+   if (!std::strcmp(name, "host_pipeline_shape")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->host_pipeline_shape = value; destroy_host_pipe(op); return CDM_OK; }
    if (!std::strcmp(name, "overlap")) { if (value < 0 || value > 2) { return CDM_EINVAL; } op->overlap = value; return CDM_OK; }
    if (!std::strcmp(name, "ilu_sweep")) { if (value != 0 && value != 1) { return CDM_EINVAL; } op->ilu_sweep = value; return CDM_OK; }
    return cdm_fail(op->sp->ctx, CDM_EINVAL, std::string("unknown option ") + name);
@@ -928,12 +929,25 @@ static int build_host_pipe(cdm_op *op)
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
    cdm_op::host_pipe &hp = op->pipe;
-   // option "host_pipeline" > 1 selects the chunk count; default 6 (measured on config 2: K = 2 / 4 / 6 / 8 /
-   // 12 / 24 -> 2.27 / 2.06 / 2.05 / 2.06 / 2.27 / 2.53 ms per step, un-pipelined 2.83 ms)
-   const int Kwant = op->host_pipeline > 1 ? std::min(op->host_pipeline, 64) : 6;
+   // option "host_pipeline" > 1 selects the chunk count.  Round 1: 6 equal chunks, four copies (one per entity class) per
+   // chunk and direction: 2.05 ms per step at config 2 (un-pipelined 2.83 ms).  The device timeline (CDM_PIPE_DEBUG)
+   // showed both links busy end to end at 37 GB/s each -- a single large copy pair reaches 47 GB/s each -- plus 0.37 ms
+   // before the first download and 0.22 ms after the last kernel.  So (option "host_pipeline_shape" = 1, default):
+   // * tapered chunks (the first and the last are half as long): the head and the tail of the pipeline shrink;
+   // * fewer, larger copies: vertices (4 % of the dofs) go up in one piece before the first chunk and come down in one
+   //   piece after the last, edges (22 %) move every second chunk; faces and interiors every chunk.
+   const int Kwant = op->host_pipeline > 1 ? std::min(op->host_pipeline, 64) : (op->host_pipeline_shape ? 8 : 6);
    const int K = (int)std::min<int64_t>(Kwant, std::max<int64_t>(1, sp->ne / 4096));
+   const bool shaped = op->host_pipeline_shape != 0 && K >= 3;
    hp.eb.resize(K + 1);
-   for (int c = 0; c <= K; c++) { hp.eb[c] = sp->ne * c / K; }
+   {
+      std::vector<double> w(K, 2.0);
+      if (shaped) { w[0] = w[K - 1] = 1.0; }
+      double tot = 0.0, acc = 0.0;
+      for (double v : w) { tot += v; }
+      hp.eb[0] = 0;
+      for (int c = 0; c < K; c++) { acc += w[c]; hp.eb[c + 1] = (c + 1 == K) ? sp->ne : (int64_t)((double)sp->ne * acc / tot); }
+   }
    std::vector<int32_t> fc(sp->ndof, K), lc(sp->ndof, -1);
    for (int c = 0; c < K; c++)
       for (int64_t i = hp.eb[c] * sp->nd; i < hp.eb[c + 1] * sp->nd; i++)
@@ -953,14 +967,21 @@ static int build_host_pipe(cdm_op *op)
          if (fc[g] < K) { umax[fc[g]] = std::max(umax[fc[g]], g + 1); }
          if (lc[g] >= 0) { dmin[lc[g]] = std::min(dmin[lc[g]], g); }
       }
-      hp.ub[k] = lo;
-      for (int c = 0; c < K; c++) { hp.ub[(size_t)(c + 1) * 4 + k] = std::max(hp.ub[(size_t)c * 4 + k], umax[c]); }
-      hp.ub[(size_t)K * 4 + k] = hi;
-      // after chunk c everything below min{g : lc[g] > c} is final
-      std::vector<int64_t> suffix(K + 1, hi);
+      // needed[c+1]: everything chunks 0..c read ; final[c+1]: everything below min{g : lc[g] > c} is final after chunk c
+      std::vector<int64_t> needed(K + 1, lo), fin(K + 1, lo), suffix(K + 1, hi);
+      for (int c = 0; c < K; c++) { needed[c + 1] = std::max(needed[c], umax[c]); }
+      needed[K] = hi;
       for (int c = K - 1; c >= 0; c--) { suffix[c] = std::min(suffix[c + 1], dmin[c]); }
-      hp.db[k] = lo;
-      for (int c = 0; c < K; c++) { hp.db[(size_t)(c + 1) * 4 + k] = std::max(hp.db[(size_t)c * 4 + k], (c + 1 < K) ? suffix[c + 1] : hi); }
+      for (int c = 0; c < K; c++) { fin[c + 1] = std::max(fin[c], (c + 1 < K) ? suffix[c + 1] : hi); }
+      // copies of class k happen every m-th chunk: uploads run ahead, downloads lag behind
+      const int m = !shaped ? 1 : (k == 0 ? K : (k == 1 ? 2 : 1));
+      hp.ub[k] = lo; hp.db[k] = lo;
+      for (int c = 0; c < K; c++)
+      {
+         const bool up_now = (c % m) == 0, down_now = ((c + 1) % m) == 0 || c == K - 1;
+         hp.ub[(size_t)(c + 1) * 4 + k] = up_now ? needed[std::min(K, (c / m + 1) * m)] : hp.ub[(size_t)c * 4 + k];
+         hp.db[(size_t)(c + 1) * 4 + k] = down_now ? fin[c + 1] : hp.db[(size_t)c * 4 + k];
+      }
    }
    CDM_CUDA(ctx, cudaStreamCreateWithFlags(&hp.su, cudaStreamNonBlocking));
    CDM_CUDA(ctx, cudaStreamCreateWithFlags(&hp.sd, cudaStreamNonBlocking));
@@ -1005,10 +1026,19 @@ static int mult_host_pipelined(cdm_op *op, const double *x_host, double *y_host,
    const int K = hp.K;
    cudaStream_t C = ctx->stream;
    static const bool debug = getenv("CDM_PIPE_DEBUG") != nullptr;
+   // CDM_PIPE_DEBUG: device timeline of the three streams (timing events, created on first use and kept)
+   static std::vector<cudaEvent_t> dbg;                  // [0] start, then per chunk: upload done, kernel done, download done
+   if (debug && dbg.size() != (size_t)(3 * K + 1))
+   {
+      for (cudaEvent_t e : dbg) { cudaEventDestroy(e); }
+      dbg.assign((size_t)(3 * K + 1), nullptr);
+      for (cudaEvent_t &e : dbg) { cudaEventCreate(&e); }
+   }
    const auto t0 = std::chrono::steady_clock::now();
    // work already queued on the compute stream may still read xL / yL (cdm_eliminate_rhs returns without a sync):
    // the upload and download streams start after it
    CDM_CUDA(ctx, cudaEventRecord(ctx->ev0, C));
+   if (debug) { cudaEventRecord(dbg[0], C); }
    CDM_CUDA(ctx, cudaStreamWaitEvent(hp.su, ctx->ev0, 0));
    CDM_CUDA(ctx, cudaStreamWaitEvent(hp.sd, ctx->ev0, 0));
    CDM_CUDA(ctx, cudaMemsetAsync(op->yL_dev, 0, sizeof(double) * (size_t)sp->ndof, C));
@@ -1021,6 +1051,7 @@ static int mult_host_pipelined(cdm_op *op, const double *x_host, double *y_host,
          if (b > a) { cudaMemcpyAsync(op->xL_dev + a, x_host + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, hp.su); }
       }
       cudaEventRecord(hp.ev_up[c], hp.su);
+      if (debug) { cudaEventRecord(dbg[1 + 3 * c], hp.su); }
    }
    const auto t1 = std::chrono::steady_clock::now();
    op->range_on = true;
@@ -1037,12 +1068,14 @@ static int mult_host_pipelined(cdm_op *op, const double *x_host, double *y_host,
          op->range_on = true;
       }
       cudaEventRecord(hp.ev_k[c], C);
+      if (debug) { cudaEventRecord(dbg[2 + 3 * c], C); }
       cudaStreamWaitEvent(hp.sd, hp.ev_k[c], 0);
       for (int k = 0; k < 4; k++)
       {
          const int64_t a = hp.db[(size_t)c * 4 + k], b = hp.db[(size_t)(c + 1) * 4 + k];
          if (b > a) { cudaMemcpyAsync(y_host + a, op->yL_dev + a, sizeof(double) * (size_t)(b - a), cudaMemcpyDeviceToHost, hp.sd); }
       }
+      if (debug) { cudaEventRecord(dbg[3 + 3 * c], hp.sd); }
    }
    op->range_on = false;
    const auto t2 = std::chrono::steady_clock::now();
@@ -1057,6 +1090,14 @@ static int mult_host_pipelined(cdm_op *op, const double *x_host, double *y_host,
       { return std::chrono::duration<double, std::milli>(b - a).count(); };
       fprintf(stderr, "[cdm pipe] enqueue uploads %.3f ms, enqueue kernels+downloads %.3f ms, wait %.3f ms, ess fix %.3f ms\n",
               ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
+      fprintf(stderr, "[cdm pipe] timeline (ms after start; chunk: upload done / kernel done / download done):");
+      for (int c = 0; c < K; c++)
+      {
+         float a = 0.f, b = 0.f, d = 0.f;
+         cudaEventElapsedTime(&a, dbg[0], dbg[1 + 3 * c]); cudaEventElapsedTime(&b, dbg[0], dbg[2 + 3 * c]); cudaEventElapsedTime(&d, dbg[0], dbg[3 + 3 * c]);
+         fprintf(stderr, "  %d: %.3f / %.3f / %.3f", c, a, b, d);
+      }
+      fprintf(stderr, "\n");
    }
    return CDM_OK;
 }

@@ -203,6 +203,7 @@ struct cdm_op
       int32_t *ess_by_chunk_dev = nullptr;
    } pipe;
    int host_pipeline = 1;
+   int host_pipeline_shape = 1;    // 1: tapered chunks + merged copies of the small entity classes, 0: round-1 schedule
    // krylov workspace (lazy)
    double *kry_dev = nullptr; int64_t kry_len = 0;
    std::vector<double> coef_scratch;

@@ -213,7 +213,10 @@ int  cdm_operator_assemble_csr(cdm_op *op);
 int  cdm_operator_csr_sizes(const cdm_op *op, int64_t *nrows, int64_t *nnz);
 int  cdm_operator_csr_get(const cdm_op *op, int64_t *rowptr, int32_t *colind, double *vals);
 /* tuning knobs (benchmarks): "assembly" (0 partial assembly, default; 1 full assembly + SpMV, see above), "scatter" (0 E-vector + deterministic gather transpose, 1 fp64 red.add, default),
-   "kernel" (0 block kernel, 1-3 order-3 warp kernels, 4 group kernel, 5 sub-warp kernel; default by order),
+   "kernel" (0 block kernel, 1-3 order-3 warp kernels, 4 group kernel, 5 sub-warp kernel, 6 2D thread-per-element kernel;
+   default by dimension and order),
+   "ilu_sweep" (ILU(0) apply: 1 (default) one launch per triangular sweep, rows wait for their dependencies on the
+   device; 0 one launch per dependency level),
    "tail" (1: caller vectors have the local size, see cdm_operator_local_size),
    "overlap" (multi-GPU: 0 serial halo exchange, 1 overlapped with interior elements up to 3 neighbours, 2 always),
    "halo" (multi-GPU shared-dof protocol: 2 (default) ONE symmetric peer-memory exchange per apply, the result is

@@ -37,16 +37,23 @@ def t(fn, reps=10):
 print("H2D 63MB ms", t(lambda: xd.copy_(xh, non_blocking=True)))
 print("D2H 63MB ms", t(lambda: yh.copy_(yd, non_blocking=True)))
 x, y = xh.numpy(), yh.numpy()
-for K in (2, 4, 6, 12, 16, 24):          # chunk-count sweep: one operator per K (the plan is built once per operator)
-    opk = cdm.ConvectionDiffusionOperator(sp, kappa=0.1, vel=(1.0, -2.0, 0.5), mass=1.0, ess_dofs=ess)
-    opk.set_option("host_pipeline", K)
-    print("mult_host K=%d ms" % K, t(lambda: opk.mult_host(x, y)))
-    del opk
 ref = None
-for mode in (0, 1):
-    op.set_option("host_pipeline", mode)
-    print("mult_host pipeline=%d ms" % mode, t(lambda: op.mult_host(x, y)))
-    if ref is None:
-        ref = y.copy()
-    else:
-        print("pipelined vs plain rel diff", np.linalg.norm(y - ref) / np.linalg.norm(ref))
+op.set_option("host_pipeline", 0)
+print("mult_host un-pipelined ms", t(lambda: op.mult_host(x, y)))
+ref = y.copy()
+for shape in (0, 1):                       # 0: round-1 schedule (equal chunks, 4 copies per chunk and direction), 1: tapered + merged
+    for K in (4, 6, 8, 10, 12, 16):
+        opk = cdm.ConvectionDiffusionOperator(sp, kappa=0.1, vel=(1.0, -2.0, 0.5), mass=1.0, ess_dofs=ess)
+        opk.set_option("host_pipeline_shape", shape)
+        opk.set_option("host_pipeline", K)
+        ms = t(lambda: opk.mult_host(x, y))
+        print("mult_host shape=%d K=%d ms %.4f  rel diff vs un-pipelined %.2e" % (shape, K, ms, np.linalg.norm(y - ref) / np.linalg.norm(ref)))
+        del opk
+for cap in (0, 444, 296, 148, 74):            # does the HBM-saturating element kernel starve the copy engines?
+    opk = cdm.ConvectionDiffusionOperator(sp, kappa=0.1, vel=(1.0, -2.0, 0.5), mass=1.0, ess_dofs=ess)
+    opk.set_option("host_pipeline", 6)
+    opk.set_option("grid_cap", cap)
+    print("mult_host shape=1 K=6 grid_cap=%d ms %.4f" % (cap, t(lambda: opk.mult_host(x, y))))
+    del opk
+op.set_option("host_pipeline", 1)
+print("mult_host default ms", t(lambda: op.mult_host(x, y)), "rel diff", np.linalg.norm(y - ref) / np.linalg.norm(ref))

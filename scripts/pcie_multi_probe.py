@@ -66,6 +66,21 @@ def d2h():
     sd.synchronize()
 
 
+SPLIT = [torch.cuda.Stream() for _ in range(4)]
+
+
+def h2d_split(k):
+    """the same upload cut into k pieces on k streams (k copy engines reading host memory at once)"""
+    def fn():
+        for i in range(k):
+            a, b = N * i // k, N * (i + 1) // k
+            with torch.cuda.stream(SPLIT[i]):
+                xd[a:b].copy_(xh[a:b], non_blocking=True)
+        for i in range(k):
+            SPLIT[i].synchronize()
+    return fn
+
+
 def both():
     with torch.cuda.stream(su):
         xd.copy_(xh, non_blocking=True)
@@ -79,7 +94,8 @@ rows = []
 while k <= world:
     act = rank < k
     r = {"active_ranks": k}
-    for name, fn, vol in (("h2d", h2d, nbytes), ("d2h", d2h, nbytes), ("both", both, 2 * nbytes)):
+    for name, fn, vol in (("h2d", h2d, nbytes), ("d2h", d2h, nbytes), ("both", both, 2 * nbytes), ("h2d_again", h2d, nbytes),
+                          ("h2d_2streams", h2d_split(2), nbytes), ("h2d_4streams", h2d_split(4), nbytes)):
         t = timed(fn, act)
         r[name + "_ms"] = round(t * 1e3, 4)
         r[name + "_GBs_per_rank"] = round(vol / t / 1e9, 2)
