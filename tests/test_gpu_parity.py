@@ -148,6 +148,14 @@ def test_pipelined_host_apply(torch, ctx, p, n):
         y_plain = op.mult_host(x, constrained=constrained)
         op.set_option("host_pipeline", 1)
         assert rel(y_pipe, y_dev) < 1e-13 and rel(y_plain, y_dev) < 1e-13 and rel(yp.numpy(), y_dev) < 1e-13
+        # both schedules (0: equal chunks, one copy per entity class and chunk; 1: tapered chunks, merged small classes)
+        # and odd chunk counts
+        for shape, K in ((0, 1), (0, 5), (1, 3), (1, 7)):
+            op.set_option("host_pipeline_shape", shape)
+            op.set_option("host_pipeline", K)
+            assert rel(op.mult_host(x, constrained=constrained), y_dev) < 1e-13, (shape, K)
+        op.set_option("host_pipeline_shape", 1)
+        op.set_option("host_pipeline", 1)
         if constrained:
             assert np.array_equal(y_pipe[ess], x[ess]) and np.array_equal(yp.numpy()[ess], x[ess])
 
