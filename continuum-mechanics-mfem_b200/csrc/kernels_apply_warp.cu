@@ -42,6 +42,9 @@ template <int P> struct GroupCfg
 // resident blocks per SM the register budget is sized for.  p=5: 5 blocks fit the shared memory, but the
 // 204-register cap of MINB = 5 made ptxas spill 200 B inside the element loop (53 % of the roofline);
 // MINB = 4 -> 160 registers, no spills, 73 %.  p=4 (two groups per block): MINB 3 / 4 / 5 -> 46 % / 76 % / 56 %; one group per block x 8 blocks: 52 %.
+#ifndef CDM_G_BALANCED
+#define CDM_G_BALANCED 1
+#endif
 #ifndef CDM_G5_MINB
 #define CDM_G5_MINB 4
 #endif
@@ -59,6 +62,107 @@ template <int P> struct GroupCfg
    static constexpr int PS = (PST * D * D + 1) & ~1;
 };
 
+// ---- the four exchange stages as functions of a compile-time output range [LO, HI): a two-warp group can then give
+// each of its warps one half of the outputs of a stage (warp-uniform branch, coefficients stay in the constant bank)
+template <int P, bool GRAD, int QLO, int QHI>
+__device__ __forceinline__ void grp_f1(const GroupTables &tb, const double *px, double *sP0, double *sP1, int t1)
+{
+   constexpr int D = P + 1, PST = GroupCfg<P>::PST;
+   #pragma unroll
+   for (int q = QLO; q < QHI; q++)
+   {
+      double tB = 0.0, tG = 0.0;
+      #pragma unroll
+      for (int d = 0; d < D; d++) { tB += tb.B[q * D + d] * px[d]; if (GRAD) { tG += tb.G[q * D + d] * px[d]; } }
+      sP0[q + PST * t1] = tB;
+      if (GRAD) { sP1[q + PST * t1] = tG; }
+   }
+}
+template <int P, bool GRAD, int QLO, int QHI>
+__device__ __forceinline__ void grp_f2(const GroupTables &tb, const double *sP0, const double *sP1, double *sR0, double *sR1, double *sR2,
+                                       int qx2, int dz2)
+{
+   constexpr int D = P + 1, Q = P + 2, PST = GroupCfg<P>::PST, RSTR = GroupCfg<P>::RSTR;
+   double tB[D], tG[D];
+   #pragma unroll
+   for (int dy = 0; dy < D; dy++)
+   {
+      tB[dy] = sP0[qx2 + PST * (dy + D * dz2)];
+      if (GRAD) { tG[dy] = sP1[qx2 + PST * (dy + D * dz2)]; }
+   }
+   #pragma unroll
+   for (int q = QLO; q < QHI; q++)
+   {
+      double vbb = 0.0, vgb = 0.0, vbg = 0.0;
+      #pragma unroll
+      for (int dy = 0; dy < D; dy++)
+      {
+         vbb += tb.B[q * D + dy] * tB[dy];
+         if (GRAD) { vgb += tb.B[q * D + dy] * tG[dy]; vbg += tb.G[q * D + dy] * tB[dy]; }
+      }
+      sR0[qx2 + Q * q + RSTR * dz2] = vbb;
+      if (GRAD) { sR1[qx2 + Q * q + RSTR * dz2] = vgb; sR2[qx2 + Q * q + RSTR * dz2] = vbg; }
+   }
+}
+template <int P, bool DIFF, int DLO, int DHI>
+__device__ __forceinline__ void grp_b2(const GroupTables &tb, const double *sR0, const double *sR1, const double *sR2, double *sP0, double *sP1,
+                                       int qx2, int dz2)
+{
+   constexpr int D = P + 1, Q = P + 2, PST = GroupCfg<P>::PST, RSTR = GroupCfg<P>::RSTR;
+   double wx[Q], wy[Q], wb[Q];
+   #pragma unroll
+   for (int q = 0; q < Q; q++)
+   {
+      wb[q] = sR2[qx2 + Q * q + RSTR * dz2];
+      if (DIFF) { wx[q] = sR0[qx2 + Q * q + RSTR * dz2]; wy[q] = sR1[qx2 + Q * q + RSTR * dz2]; }
+   }
+   #pragma unroll
+   for (int dy = DLO; dy < DHI; dy++)
+   {
+      double a1 = 0.0, a2 = 0.0;
+      #pragma unroll
+      for (int q = 0; q < Q; q++)
+      {
+         a2 += tb.B[q * D + dy] * wb[q];
+         if (DIFF) { a1 += tb.B[q * D + dy] * wx[q]; a2 += tb.G[q * D + dy] * wy[q]; }
+      }
+      sP1[qx2 + PST * (dy + D * dz2)] = a2;
+      if (DIFF) { sP0[qx2 + PST * (dy + D * dz2)] = a1; }
+   }
+}
+template <int P, bool DIFF, bool ATOMIC, int DLO, int DHI>
+__device__ __forceinline__ void grp_b3(const GroupTables &tb, const double *sP0, const double *sP1, int t1, const int32_t *g, double *y, int64_t e)
+{
+   constexpr int D = P + 1, Q = P + 2, PST = GroupCfg<P>::PST, ND = D * D * D;
+   double a1[Q], a2[Q];
+   #pragma unroll
+   for (int q = 0; q < Q; q++) { a2[q] = sP1[q + PST * t1]; if (DIFF) { a1[q] = sP0[q + PST * t1]; } }
+   // all results first (independent accumulation chains), then the scatter: a red.add inside the dx loop is a
+   // compiler barrier (asm volatile, "memory") and serialised the chains -- 15 % of the stall samples at p = 5, 6
+   constexpr bool SPLIT = P >= 5;                           // p = 4 runs at its 128-register cap: one accumulator per dx
+   double yb[D], yg[SPLIT ? D : 1];
+   #pragma unroll
+   for (int dx = DLO; dx < DHI; dx++)
+   {
+      double sb = 0.0, sg = 0.0;
+      #pragma unroll
+      for (int q = 0; q < Q; q++)
+      {
+         sb += tb.B[q * D + dx] * a2[q];
+         if (DIFF) { if (SPLIT) { sg += tb.G[q * D + dx] * a1[q]; } else { sb += tb.G[q * D + dx] * a1[q]; } }
+      }
+      yb[dx] = sb;
+      if (SPLIT) { yg[dx] = sg; }
+   }
+   #pragma unroll
+   for (int dx = DLO; dx < DHI; dx++)
+   {
+      const double a = SPLIT ? yb[dx] + yg[dx] : yb[dx];
+      if (ATOMIC) { if (g[dx] >= 0) { g_red_add(y + g[dx], a); } }
+      else { y[e * ND + D * t1 + dx] = a; }
+   }
+}
+
 template <int P, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
 __global__ void __launch_bounds__(GroupCfg<P>::THREADS, GroupCfg<P>::MINB)
 k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restrict__ gmap,
@@ -67,7 +171,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
 {
    using C = GroupCfg<P>;
    constexpr int D = C::D, Q = C::Q, T = C::T, ND = C::ND, Q2 = Q * Q;
-   constexpr int RS = C::RS, PS = C::PS, RSTR = C::RSTR, PST = C::PST;
+   constexpr int RS = C::RS, PS = C::PS, RSTR = C::RSTR;
    constexpr bool GRAD = DIFF || CONV;
    extern __shared__ __align__(128) unsigned char smraw[];
    const int group_doubles = (Q * slab + 3 * RS + 2 * PS + 1) & ~1;
@@ -86,10 +190,18 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    double *gbase = reinterpret_cast<double *>(smraw) + gsafe * group_doubles;
    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smraw) + C::GPB * group_doubles) + gsafe * Q;
    double *ring = gbase, *sR0 = ring + Q * slab, *sR1 = sR0 + RS, *sR2 = sR1 + RS, *sP0 = sR2 + RS, *sP1 = sP0 + PS;
-   const bool l1 = member && t < D * D, l2 = member && t < Q * D;
+   // BAL (two-warp groups with D^2, Q D <= 32, i.e. p = 4): the x / y exchange stages, which need only D^2 = 25 or
+   // Q D = 30 threads, are run by BOTH warps, each producing one half of the stage's outputs for every line; without
+   // it the second warp idles through four of the seven stages and `barrier` is the top stall of the kernel
+   constexpr bool BAL = C::WPG == 2 && Q * D <= 32 && CDM_G_BALANCED;
+   constexpr int QH = Q / 2, DH = (D + 1) / 2;
+   const int hw = BAL ? (t >> 5) : 0;                                  // warp of the group (warp-uniform)
+   const int tl = BAL ? (t & 31) : t;
+   const bool l1 = BAL ? (gib >= 0 && tl < D * D) : (member && t < D * D);
+   const bool l2 = BAL ? (gib >= 0 && tl < Q * D) : (member && t < Q * D);
    const int t3 = member ? t : 0;                                      // L3 role: (qx,qy) = t
-   const int qx2 = l2 ? t / D : 0, dz2 = l2 ? t % D : 0;               // L2 role
-   const int t1 = l1 ? t : 0;                                          // L1 role: x-line index dy + D*dz
+   const int qx2 = l2 ? tl / D : 0, dz2 = l2 ? tl % D : 0;             // L2 role
+   const int t1 = l1 ? tl : 0;                                         // L1 role: x-line index dy + D*dz
    auto gsync = [&]()
    {
       if (C::WPG == 1) { __syncwarp(); }
@@ -155,15 +267,9 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       // ---- F1 (L1 threads): x contraction of the own x-line with B and G
       if (l1 && valid)
       {
-         #pragma unroll
-         for (int q = 0; q < Q; q++)
-         {
-            double tB = 0.0, tG = 0.0;
-            #pragma unroll
-            for (int d = 0; d < D; d++) { tB += tb.B[q * D + d] * px[d]; if (GRAD) { tG += tb.G[q * D + d] * px[d]; } }
-            sP0[q + PST * t1] = tB;
-            if (GRAD) { sP1[q + PST * t1] = tG; }
-         }
+         if (!BAL) { grp_f1<P, GRAD, 0, Q>(tb, px, sP0, sP1, t1); }
+         else if (hw == 0) { grp_f1<P, GRAD, 0, QH>(tb, px, sP0, sP1, t1); }
+         else { grp_f1<P, GRAD, QH, Q>(tb, px, sP0, sP1, t1); }
       }
       if (l1 && more)
       {
@@ -181,26 +287,9 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       // ---- F2 (L2 threads): y contraction -> (B B), (G B), (B G)
       if (l2 && valid)
       {
-         double tB[D], tG[D];
-         #pragma unroll
-         for (int dy = 0; dy < D; dy++)
-         {
-            tB[dy] = sP0[qx2 + PST * (dy + D * dz2)];
-            if (GRAD) { tG[dy] = sP1[qx2 + PST * (dy + D * dz2)]; }
-         }
-         #pragma unroll
-         for (int q = 0; q < Q; q++)
-         {
-            double vbb = 0.0, vgb = 0.0, vbg = 0.0;
-            #pragma unroll
-            for (int dy = 0; dy < D; dy++)
-            {
-               vbb += tb.B[q * D + dy] * tB[dy];
-               if (GRAD) { vgb += tb.B[q * D + dy] * tG[dy]; vbg += tb.G[q * D + dy] * tB[dy]; }
-            }
-            sR0[qx2 + Q * q + RSTR * dz2] = vbb;
-            if (GRAD) { sR1[qx2 + Q * q + RSTR * dz2] = vgb; sR2[qx2 + Q * q + RSTR * dz2] = vbg; }
-         }
+         if (!BAL) { grp_f2<P, GRAD, 0, Q>(tb, sP0, sP1, sR0, sR1, sR2, qx2, dz2); }
+         else if (hw == 0) { grp_f2<P, GRAD, 0, QH>(tb, sP0, sP1, sR0, sR1, sR2, qx2, dz2); }
+         else { grp_f2<P, GRAD, QH, Q>(tb, sP0, sP1, sR0, sR1, sR2, qx2, dz2); }
       }
       gsync();
       // ---- F3 (L3 threads): z contraction in registers
@@ -279,58 +368,17 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       // ---- B2 (L2 threads): transposed y contraction
       if (l2 && valid)
       {
-         double wx[Q], wy[Q], wb[Q];
-         #pragma unroll
-         for (int q = 0; q < Q; q++)
-         {
-            wb[q] = sR2[qx2 + Q * q + RSTR * dz2];
-            if (DIFF) { wx[q] = sR0[qx2 + Q * q + RSTR * dz2]; wy[q] = sR1[qx2 + Q * q + RSTR * dz2]; }
-         }
-         #pragma unroll
-         for (int dy = 0; dy < D; dy++)
-         {
-            double a1 = 0.0, a2 = 0.0;
-            #pragma unroll
-            for (int q = 0; q < Q; q++)
-            {
-               a2 += tb.B[q * D + dy] * wb[q];
-               if (DIFF) { a1 += tb.B[q * D + dy] * wx[q]; a2 += tb.G[q * D + dy] * wy[q]; }
-            }
-            sP1[qx2 + PST * (dy + D * dz2)] = a2;
-            if (DIFF) { sP0[qx2 + PST * (dy + D * dz2)] = a1; }
-         }
+         if (!BAL) { grp_b2<P, DIFF, 0, D>(tb, sR0, sR1, sR2, sP0, sP1, qx2, dz2); }
+         else if (hw == 0) { grp_b2<P, DIFF, 0, DH>(tb, sR0, sR1, sR2, sP0, sP1, qx2, dz2); }
+         else { grp_b2<P, DIFF, DH, D>(tb, sR0, sR1, sR2, sP0, sP1, qx2, dz2); }
       }
       gsync();
       // ---- B3 (L1 threads): transposed x contraction of the own x-line, scatter
       if (l1 && valid)
       {
-         double a1[Q], a2[Q];
-         #pragma unroll
-         for (int q = 0; q < Q; q++) { a2[q] = sP1[q + PST * t1]; if (DIFF) { a1[q] = sP0[q + PST * t1]; } }
-         // all D results first (2 D independent accumulation chains), then the scatter: a red.add inside the dx loop is
-         // a compiler barrier (asm volatile, "memory") and serialised the chains -- 15 % of the stall samples at p = 5, 6
-         constexpr bool SPLIT = P >= 5;                     // p = 4 runs at its 128-register cap: one accumulator per dx
-         double yb[D], yg[SPLIT ? D : 1];
-         #pragma unroll
-         for (int dx = 0; dx < D; dx++)
-         {
-            double sb = 0.0, sg = 0.0;
-            #pragma unroll
-            for (int q = 0; q < Q; q++)
-            {
-               sb += tb.B[q * D + dx] * a2[q];
-               if (DIFF) { if (SPLIT) { sg += tb.G[q * D + dx] * a1[q]; } else { sb += tb.G[q * D + dx] * a1[q]; } }
-            }
-            yb[dx] = sb;
-            if (SPLIT) { yg[dx] = sg; }
-         }
-         #pragma unroll
-         for (int dx = 0; dx < D; dx++)
-         {
-            const double a = SPLIT ? yb[dx] + yg[dx] : yb[dx];
-            if (ATOMIC) { if (g[dx] >= 0) { g_red_add(y + g[dx], a); } }
-            else { y[e * ND + D * t1 + dx] = a; }
-         }
+         if (!BAL) { grp_b3<P, DIFF, ATOMIC, 0, D>(tb, sP0, sP1, t1, g, y, e); }
+         else if (hw == 0) { grp_b3<P, DIFF, ATOMIC, 0, DH>(tb, sP0, sP1, t1, g, y, e); }
+         else { grp_b3<P, DIFF, ATOMIC, DH, D>(tb, sP0, sP1, t1, g, y, e); }
       }
       gsync();                                               // P buffers are rewritten by the next round's F1
    }
