@@ -25,6 +25,15 @@ int cdm_kernel_cfg(cdm_ctx *ctx, const void *kern, int threads, size_t smem, con
    int b = 0;
    CDM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, threads, smem));
    if (b < 1) { return cdm_fail(ctx, CDM_ECUDA, std::string(name) + " does not fit on an SM"); }
+   if (getenv("CDM_CFG_DEBUG"))                              // resident blocks per SM of every kernel configuration, once each
+   {
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess)
+      {
+         fprintf(stderr, "[cdm] %s: %d threads, %zu B dynamic shared memory, %d registers, %zu B local -> %d blocks per SM\n",
+                 name, threads, smem, fa.numRegs, (size_t)fa.localSizeBytes, b);
+      }
+   }
    ctx->kernel_cfg[key] = b;
    *blocks_per_sm = b;
    return CDM_OK;

@@ -34,6 +34,9 @@ struct WarpTables
 // (red.add) by neighbouring elements
 using cdmk::smem_u32;
 using cdmk::mbar_init;
+#ifndef CDM_P3_WAITALL
+#define CDM_P3_WAITALL 1
+#endif
 using cdmk::mbar_expect_tx;
 using cdmk::mbar_wait;
 using cdmk::red_add_f64;
@@ -502,10 +505,18 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
          }
       }
       // ---- point-wise D at the lane's five quadrature points (registers only)
+#if CDM_P3_WAITALL
+      // the five slabs were requested one element ago: wait for all of them first, so that the wait loops do not
+      // fence the loads of one slab from the products of the previous one
+      #pragma unroll
+      for (int qz = 0; qz < Q; qz++) { mbar_wait(&bars[qz], parity); }
+#endif
       #pragma unroll
       for (int qz = 0; qz < Q; qz++)
       {
+#if !CDM_P3_WAITALL
          mbar_wait(&bars[qz], parity);
+#endif
          const double *dp = ring + qz * slab + l3i;
          double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;
          int c = 0;

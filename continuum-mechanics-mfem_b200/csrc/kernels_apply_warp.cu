@@ -37,59 +37,105 @@ template <int P> struct GroupCfg
    #ifndef CDM_G4_GPB
 #define CDM_G4_GPB 2
 #endif
-   static constexpr int GPB = (P <= 3) ? 4 * EPW : (P == 4 ? CDM_G4_GPB : 1);   // groups per block (two-warp groups: the block IS the group)
+#ifndef CDM_G5_GPB
+#define CDM_G5_GPB 1
+#endif
+   static constexpr int GPB = (P <= 3) ? 4 * EPW : (P == 4 ? CDM_G4_GPB : (P == 5 ? CDM_G5_GPB : 1));   // groups per block (two-warp groups: the block IS the group)
    static constexpr int THREADS = (WPG == 1) ? 32 * (GPB / EPW) : 64 * GPB;
 // resident blocks per SM the register budget is sized for.  p=5: 5 blocks fit the shared memory, but the
 // 204-register cap of MINB = 5 made ptxas spill 200 B inside the element loop (53 % of the roofline);
 // MINB = 4 -> 160 registers, no spills, 73 %.  p=4 (two groups per block): MINB 3 / 4 / 5 -> 46 % / 76 % / 56 %; one group per block x 8 blocks: 52 %.
 #ifndef CDM_G_BALANCED
-#define CDM_G_BALANCED 1
+#define CDM_G_BALANCED 0
+#endif
+#ifndef CDM_G_ALIAS
+#define CDM_G_ALIAS 1
+#endif
+#ifndef CDM_G_SPLITP
+#define CDM_G_SPLITP 5
+#endif
+#ifndef CDM_G_WAITALL
+#define CDM_G_WAITALL 1
+#endif
+#ifndef CDM_G5_WAITALL
+#define CDM_G5_WAITALL 0             // p=5: 192 instead of 161 registers, i.e. 5 instead of 6 resident groups
+#endif
+#ifndef CDM_G5_INPLACE
+#define CDM_G5_INPLACE 1
+#endif
+#ifndef CDM_G6_INPLACE
+#define CDM_G6_INPLACE 1
 #endif
 #ifndef CDM_G5_MINB
-#define CDM_G5_MINB 4
+#define CDM_G5_MINB ((CDM_G_ALIAS && !CDM_G5_INPLACE) ? 6 : 4)
+#endif
+#ifndef CDM_G6_MINB
+#define CDM_G6_MINB ((CDM_G_ALIAS && !CDM_G6_INPLACE) ? 4 : 3)
 #endif
 #ifndef CDM_G4_MINB
 #define CDM_G4_MINB 4
 #endif
-   static constexpr int MINB = (P < 4) ? 4 : (P == 4 ? CDM_G4_MINB : (P == 5 ? CDM_G5_MINB : 3));        // resident blocks per SM the register budget is sized for
+   static constexpr int MINB = (P < 4) ? 4 : (P == 4 ? CDM_G4_MINB : (P == 5 ? CDM_G5_MINB : CDM_G6_MINB));        // resident blocks per SM the register budget is sized for
    // strides of the exchange layouts P(qx, line) = qx + PST line, R(qx,qy,dz) = qx + Q qy + RSTR dz.  For the
    // two-warp groups they come from a brute-force search over the 64-bit bank pattern of the four access
    // shapes (F1 write / F2 read of P, F2 write / F3 read of R): wavefronts per access, old -> new:
    // p=4  P 8 -> 4, R 4 -> 2 (ideal 4, 2);  p=6  P 41 -> 8, R 11 -> 4 (ideal 8, 4);  p=5 unchanged (8 / 5, ideal 6 / 3).
-   static constexpr int RSTR = (P == 3) ? 28 : (P == 4 ? 45 : (P == 6 ? 71 : (Q * Q + ((Q * Q) % 2 == 0 ? 1 : 2))));
+   // INPLACE: the P content lives in R0 / R1 with the R strides, P(q; dy,dz) = q + Q dy + RSTR dz.  An L2 thread (qx,dz)
+   // of F2 / B2 then reads and writes only entries qx + Q j + RSTR dz of its own (qx,dz): the y contractions are in-place
+   // transforms, no P buffers and no extra barrier.  p=5: RSTR 58 keeps the wavefront count of the separate layout
+   // (558 per element, ideal 426) and 35.6 instead of 38.8 KB per group = 6 instead of 5 groups per SM with the same code
+   // shape (no register-cap change: ptxas spills under the 168-register cap of MINB >= 5).  p=6 (L1 lanes dz-fastest):
+   // 696 instead of 600 wavefronts, kept as a variant beside ALIAS.
+   static constexpr bool INPLACE = (P == 5 && CDM_G5_INPLACE) || (P == 6 && CDM_G6_INPLACE);
+   static constexpr bool M1 = INPLACE && P == 6;             // L1 lane -> (dy,dz): dz fastest
+   static constexpr int RSTR = (P == 3) ? 28 : (P == 4 ? 45 : (P == 6 ? 71 : (INPLACE ? 58 : (Q * Q + ((Q * Q) % 2 == 0 ? 1 : 2)))));
    static constexpr int PST = (P == 4) ? 9 : (P == 6 ? 17 : Q);
+   static constexpr int PSY = INPLACE ? Q : PST, PSZ = INPLACE ? RSTR : PST * D;   // P(q; dy,dz) = q + PSY dy + PSZ dz
    static constexpr int RS = ((D - 1) * RSTR + Q * Q + 1) & ~1;
    static constexpr int PS = (PST * D * D + 1) & ~1;
+   // ALIAS (p >= 5, where shared memory bounds the resident groups): the P and the R exchange buffers share one region.
+   // P is live F1 -> F2 and B2 -> B3, R is live F2 -> F3 and B1 -> B2; they only overlap inside F2 and B2, which then
+   // read all their inputs into registers, meet at the group barrier, and write afterwards (two more barriers per
+   // element).  p=6: 66.1 -> 54.3 KB per group = 4 instead of 3 groups per SM; p=5: 38.8 -> 34.8 KB = 6 instead of 5.
+   static constexpr bool ALIAS = (P >= 5) && CDM_G_ALIAS && !INPLACE;
+   // the D stage waits for all slab barriers before its first product (the slabs were requested one element ago): the
+   // wait loops no longer fence the loads of one slab from the products of the previous one
+   static constexpr bool WAITALL = (P == 5) ? CDM_G5_WAITALL : CDM_G_WAITALL;
+   static constexpr int XS = INPLACE ? 3 * RS : (ALIAS ? (3 * RS > 2 * PS ? 3 * RS : 2 * PS) : 3 * RS + 2 * PS);   // exchange doubles per group
 };
 
 // ---- the four exchange stages as functions of a compile-time output range [LO, HI): a two-warp group can then give
 // each of its warps one half of the outputs of a stage (warp-uniform branch, coefficients stay in the constant bank)
 template <int P, bool GRAD, int QLO, int QHI>
-__device__ __forceinline__ void grp_f1(const GroupTables &tb, const double *px, double *sP0, double *sP1, int t1)
+__device__ __forceinline__ void grp_f1(const GroupTables &tb, const double *px, double *sP0, double *sP1, int pb1)
 {
-   constexpr int D = P + 1, PST = GroupCfg<P>::PST;
+   constexpr int D = P + 1;
    #pragma unroll
    for (int q = QLO; q < QHI; q++)
    {
       double tB = 0.0, tG = 0.0;
       #pragma unroll
       for (int d = 0; d < D; d++) { tB += tb.B[q * D + d] * px[d]; if (GRAD) { tG += tb.G[q * D + d] * px[d]; } }
-      sP0[q + PST * t1] = tB;
-      if (GRAD) { sP1[q + PST * t1] = tG; }
+      sP0[q + pb1] = tB;
+      if (GRAD) { sP1[q + pb1] = tG; }
    }
 }
-template <int P, bool GRAD, int QLO, int QHI>
-__device__ __forceinline__ void grp_f2(const GroupTables &tb, const double *sP0, const double *sP1, double *sR0, double *sR1, double *sR2,
-                                       int qx2, int dz2)
+template <int P, bool GRAD>
+__device__ __forceinline__ void grp_f2_load(const double *sP0, const double *sP1, int qx2, int dz2, double *tB, double *tG)
 {
-   constexpr int D = P + 1, Q = P + 2, PST = GroupCfg<P>::PST, RSTR = GroupCfg<P>::RSTR;
-   double tB[D], tG[D];
+   constexpr int D = P + 1, PSY = GroupCfg<P>::PSY, PSZ = GroupCfg<P>::PSZ;
    #pragma unroll
    for (int dy = 0; dy < D; dy++)
    {
-      tB[dy] = sP0[qx2 + PST * (dy + D * dz2)];
-      if (GRAD) { tG[dy] = sP1[qx2 + PST * (dy + D * dz2)]; }
+      tB[dy] = sP0[qx2 + PSY * dy + PSZ * dz2];
+      if (GRAD) { tG[dy] = sP1[qx2 + PSY * dy + PSZ * dz2]; }
    }
+}
+template <int P, bool GRAD, int QLO, int QHI>
+__device__ __forceinline__ void grp_f2(const GroupTables &tb, const double *tB, const double *tG, double *sR0, double *sR1, double *sR2,
+                                       int qx2, int dz2)
+{
+   constexpr int D = P + 1, Q = P + 2, RSTR = GroupCfg<P>::RSTR;
    #pragma unroll
    for (int q = QLO; q < QHI; q++)
    {
@@ -104,18 +150,23 @@ __device__ __forceinline__ void grp_f2(const GroupTables &tb, const double *sP0,
       if (GRAD) { sR1[qx2 + Q * q + RSTR * dz2] = vgb; sR2[qx2 + Q * q + RSTR * dz2] = vbg; }
    }
 }
-template <int P, bool DIFF, int DLO, int DHI>
-__device__ __forceinline__ void grp_b2(const GroupTables &tb, const double *sR0, const double *sR1, const double *sR2, double *sP0, double *sP1,
-                                       int qx2, int dz2)
+template <int P, bool DIFF>
+__device__ __forceinline__ void grp_b2_load(const double *sR0, const double *sR1, const double *sR2, int qx2, int dz2,
+                                            double *wx, double *wy, double *wb)
 {
-   constexpr int D = P + 1, Q = P + 2, PST = GroupCfg<P>::PST, RSTR = GroupCfg<P>::RSTR;
-   double wx[Q], wy[Q], wb[Q];
+   constexpr int Q = P + 2, RSTR = GroupCfg<P>::RSTR;
    #pragma unroll
    for (int q = 0; q < Q; q++)
    {
       wb[q] = sR2[qx2 + Q * q + RSTR * dz2];
       if (DIFF) { wx[q] = sR0[qx2 + Q * q + RSTR * dz2]; wy[q] = sR1[qx2 + Q * q + RSTR * dz2]; }
    }
+}
+template <int P, bool DIFF, int DLO, int DHI>
+__device__ __forceinline__ void grp_b2(const GroupTables &tb, const double *wx, const double *wy, const double *wb, double *sP0, double *sP1,
+                                       int qx2, int dz2)
+{
+   constexpr int D = P + 1, Q = P + 2, PSY = GroupCfg<P>::PSY, PSZ = GroupCfg<P>::PSZ;
    #pragma unroll
    for (int dy = DLO; dy < DHI; dy++)
    {
@@ -126,20 +177,20 @@ __device__ __forceinline__ void grp_b2(const GroupTables &tb, const double *sR0,
          a2 += tb.B[q * D + dy] * wb[q];
          if (DIFF) { a1 += tb.B[q * D + dy] * wx[q]; a2 += tb.G[q * D + dy] * wy[q]; }
       }
-      sP1[qx2 + PST * (dy + D * dz2)] = a2;
-      if (DIFF) { sP0[qx2 + PST * (dy + D * dz2)] = a1; }
+      sP1[qx2 + PSY * dy + PSZ * dz2] = a2;
+      if (DIFF) { sP0[qx2 + PSY * dy + PSZ * dz2] = a1; }
    }
 }
 template <int P, bool DIFF, bool ATOMIC, int DLO, int DHI>
-__device__ __forceinline__ void grp_b3(const GroupTables &tb, const double *sP0, const double *sP1, int t1, const int32_t *g, double *y, int64_t e)
+__device__ __forceinline__ void grp_b3(const GroupTables &tb, const double *sP0, const double *sP1, int pb1, int t1, const int32_t *g, double *y, int64_t e)
 {
-   constexpr int D = P + 1, Q = P + 2, PST = GroupCfg<P>::PST, ND = D * D * D;
+   constexpr int D = P + 1, Q = P + 2, ND = D * D * D;
    double a1[Q], a2[Q];
    #pragma unroll
-   for (int q = 0; q < Q; q++) { a2[q] = sP1[q + PST * t1]; if (DIFF) { a1[q] = sP0[q + PST * t1]; } }
+   for (int q = 0; q < Q; q++) { a2[q] = sP1[q + pb1]; if (DIFF) { a1[q] = sP0[q + pb1]; } }
    // all results first (independent accumulation chains), then the scatter: a red.add inside the dx loop is a
    // compiler barrier (asm volatile, "memory") and serialised the chains -- 15 % of the stall samples at p = 5, 6
-   constexpr bool SPLIT = P >= 5;                           // p = 4 runs at its 128-register cap: one accumulator per dx
+   constexpr bool SPLIT = P >= CDM_G_SPLITP;                          // p = 4 runs at its 128-register cap: one accumulator per dx
    double yb[D], yg[SPLIT ? D : 1];
    #pragma unroll
    for (int dx = DLO; dx < DHI; dx++)
@@ -172,9 +223,9 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    using C = GroupCfg<P>;
    constexpr int D = C::D, Q = C::Q, T = C::T, ND = C::ND, Q2 = Q * Q;
    constexpr int RS = C::RS, PS = C::PS, RSTR = C::RSTR;
-   constexpr bool GRAD = DIFF || CONV;
+   constexpr bool GRAD = DIFF || CONV, ALIAS = C::ALIAS;
    extern __shared__ __align__(128) unsigned char smraw[];
-   const int group_doubles = (Q * slab + 3 * RS + 2 * PS + 1) & ~1;
+   const int group_doubles = (Q * slab + C::XS + 1) & ~1;
    // ---- which group am I, which thread of the group
    int gib, t;                                               // group in block, thread in group
    if (C::WPG == 1)
@@ -189,7 +240,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    const int gsafe = gib >= 0 ? gib : 0;
    double *gbase = reinterpret_cast<double *>(smraw) + gsafe * group_doubles;
    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<double *>(smraw) + C::GPB * group_doubles) + gsafe * Q;
-   double *ring = gbase, *sR0 = ring + Q * slab, *sR1 = sR0 + RS, *sR2 = sR1 + RS, *sP0 = sR2 + RS, *sP1 = sP0 + PS;
+   double *ring = gbase, *sR0 = ring + Q * slab, *sR1 = sR0 + RS, *sR2 = sR1 + RS, *sP0 = (ALIAS || C::INPLACE) ? sR0 : sR2 + RS, *sP1 = C::INPLACE ? sR1 : sP0 + PS;
    // BAL (two-warp groups with D^2, Q D <= 32, i.e. p = 4): the x / y exchange stages, which need only D^2 = 25 or
    // Q D = 30 threads, are run by BOTH warps, each producing one half of the stage's outputs for every line; without
    // it the second warp idles through four of the seven stages and `barrier` is the top stall of the kernel
@@ -201,7 +252,10 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    const bool l2 = BAL ? (gib >= 0 && tl < Q * D) : (member && t < Q * D);
    const int t3 = member ? t : 0;                                      // L3 role: (qx,qy) = t
    const int qx2 = l2 ? tl / D : 0, dz2 = l2 ? tl % D : 0;             // L2 role
-   const int t1 = l1 ? tl : 0;                                         // L1 role: x-line index dy + D*dz
+   // L1 role: x-line (dy,dz), its index t1 = dy + D dz in the element, its row pb1 in the P layout
+   const int dy1 = l1 ? (C::M1 ? tl / D : tl % D) : 0, dz1 = l1 ? (C::M1 ? tl % D : tl / D) : 0;
+   const int t1 = C::INPLACE ? dy1 + D * dz1 : (l1 ? tl : 0);
+   const int pb1 = C::INPLACE ? C::PSY * dy1 + C::PSZ * dz1 : C::PST * t1;
    auto gsync = [&]()
    {
       if (C::WPG == 1) { __syncwarp(); }
@@ -267,9 +321,9 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       // ---- F1 (L1 threads): x contraction of the own x-line with B and G
       if (l1 && valid)
       {
-         if (!BAL) { grp_f1<P, GRAD, 0, Q>(tb, px, sP0, sP1, t1); }
-         else if (hw == 0) { grp_f1<P, GRAD, 0, QH>(tb, px, sP0, sP1, t1); }
-         else { grp_f1<P, GRAD, QH, Q>(tb, px, sP0, sP1, t1); }
+         if (!BAL) { grp_f1<P, GRAD, 0, Q>(tb, px, sP0, sP1, pb1); }
+         else if (hw == 0) { grp_f1<P, GRAD, 0, QH>(tb, px, sP0, sP1, pb1); }
+         else { grp_f1<P, GRAD, QH, Q>(tb, px, sP0, sP1, pb1); }
       }
       if (l1 && more)
       {
@@ -285,11 +339,16 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       }
       gsync();
       // ---- F2 (L2 threads): y contraction -> (B B), (G B), (B G)
-      if (l2 && valid)
       {
-         if (!BAL) { grp_f2<P, GRAD, 0, Q>(tb, sP0, sP1, sR0, sR1, sR2, qx2, dz2); }
-         else if (hw == 0) { grp_f2<P, GRAD, 0, QH>(tb, sP0, sP1, sR0, sR1, sR2, qx2, dz2); }
-         else { grp_f2<P, GRAD, QH, Q>(tb, sP0, sP1, sR0, sR1, sR2, qx2, dz2); }
+         double tB[D], tG[D];
+         if (l2 && valid) { grp_f2_load<P, GRAD>(sP0, sP1, qx2, dz2, tB, tG); }
+         if (ALIAS) { gsync(); }                             // R overwrites P: every input is in registers first
+         if (l2 && valid)
+         {
+            if (!BAL) { grp_f2<P, GRAD, 0, Q>(tb, tB, tG, sR0, sR1, sR2, qx2, dz2); }
+            else if (hw == 0) { grp_f2<P, GRAD, 0, QH>(tb, tB, tG, sR0, sR1, sR2, qx2, dz2); }
+            else { grp_f2<P, GRAD, QH, Q>(tb, tB, tG, sR0, sR1, sR2, qx2, dz2); }
+         }
       }
       gsync();
       // ---- F3 (L3 threads): z contraction in registers
@@ -318,10 +377,15 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       // ---- point-wise D at the thread's Q quadrature points (registers only)
       if (valid)
       {
+         if (C::WAITALL)
+         {
+            #pragma unroll
+            for (int qz = 0; qz < Q; qz++) { g_mbar_wait(&bars[qz], parity); }
+         }
          #pragma unroll
          for (int qz = 0; qz < Q; qz++)
          {
-            g_mbar_wait(&bars[qz], parity);
+            if (!C::WAITALL) { g_mbar_wait(&bars[qz], parity); }
             const double *dp = ring + qz * slab + t3;
             double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;
             int c = 0;
@@ -366,19 +430,24 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       }
       gsync();
       // ---- B2 (L2 threads): transposed y contraction
-      if (l2 && valid)
       {
-         if (!BAL) { grp_b2<P, DIFF, 0, D>(tb, sR0, sR1, sR2, sP0, sP1, qx2, dz2); }
-         else if (hw == 0) { grp_b2<P, DIFF, 0, DH>(tb, sR0, sR1, sR2, sP0, sP1, qx2, dz2); }
-         else { grp_b2<P, DIFF, DH, D>(tb, sR0, sR1, sR2, sP0, sP1, qx2, dz2); }
+         double wx[Q], wy[Q], wb[Q];
+         if (l2 && valid) { grp_b2_load<P, DIFF>(sR0, sR1, sR2, qx2, dz2, wx, wy, wb); }
+         if (ALIAS) { gsync(); }                             // P overwrites R
+         if (l2 && valid)
+         {
+            if (!BAL) { grp_b2<P, DIFF, 0, D>(tb, wx, wy, wb, sP0, sP1, qx2, dz2); }
+            else if (hw == 0) { grp_b2<P, DIFF, 0, DH>(tb, wx, wy, wb, sP0, sP1, qx2, dz2); }
+            else { grp_b2<P, DIFF, DH, D>(tb, wx, wy, wb, sP0, sP1, qx2, dz2); }
+         }
       }
       gsync();
       // ---- B3 (L1 threads): transposed x contraction of the own x-line, scatter
       if (l1 && valid)
       {
-         if (!BAL) { grp_b3<P, DIFF, ATOMIC, 0, D>(tb, sP0, sP1, t1, g, y, e); }
-         else if (hw == 0) { grp_b3<P, DIFF, ATOMIC, 0, DH>(tb, sP0, sP1, t1, g, y, e); }
-         else { grp_b3<P, DIFF, ATOMIC, DH, D>(tb, sP0, sP1, t1, g, y, e); }
+         if (!BAL) { grp_b3<P, DIFF, ATOMIC, 0, D>(tb, sP0, sP1, pb1, t1, g, y, e); }
+         else if (hw == 0) { grp_b3<P, DIFF, ATOMIC, 0, DH>(tb, sP0, sP1, pb1, t1, g, y, e); }
+         else { grp_b3<P, DIFF, ATOMIC, DH, D>(tb, sP0, sP1, pb1, t1, g, y, e); }
       }
       gsync();                                               // P buffers are rewritten by the next round's F1
    }
@@ -391,7 +460,7 @@ int launch_group(cdm_op *op, const GroupTables &tb, const int32_t *gmap, const d
    cdm_space *sp = op->sp;
    cdm_ctx *ctx = sp->ctx;
    auto kern = k_apply3d_group<P, DIFF, CONV, MASS, ATOMIC>;
-   const int group_doubles = (C::Q * op->slab + 3 * C::RS + 2 * C::PS + 1) & ~1;
+   const int group_doubles = (C::Q * op->slab + C::XS + 1) & ~1;
    const size_t smem = (size_t)C::GPB * group_doubles * sizeof(double) + (size_t)C::GPB * C::Q * sizeof(uint64_t);
    int blocks_per_sm = 0;
    { const int rc = cdm_kernel_cfg(ctx, (const void *)kern, C::THREADS, smem, "k_apply3d_group", &blocks_per_sm); if (rc) { return rc; } }
