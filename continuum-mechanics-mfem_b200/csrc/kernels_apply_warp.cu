@@ -87,8 +87,19 @@ template <int P> struct GroupCfg
    // shape (no register-cap change: ptxas spills under the 168-register cap of MINB >= 5).  p=6 (L1 lanes dz-fastest):
    // 696 instead of 600 wavefronts, kept as a variant beside ALIAS.
    static constexpr bool INPLACE = (P == 5 && CDM_G5_INPLACE) || (P == 6 && CDM_G6_INPLACE);
-   static constexpr bool M1 = INPLACE && P == 6;             // L1 lane -> (dy,dz): dz fastest
-   static constexpr int RSTR = (P == 3) ? 28 : (P == 4 ? 45 : (P == 6 ? 71 : (INPLACE ? 58 : (Q * Q + ((Q * Q) % 2 == 0 ? 1 : 2)))));
+   // Lane maps of the L1 (x-line) and L2 (qx,dz) roles when INPLACE: a half-warp is one 64-bit shared-memory
+   // wavefront, so it is given only as many lines as have distinct banks, the rest of its lanes idle:
+   //   L1MAP 1 (p=5): 12 of 16 lanes, dy = r % D, dz = 2h + r / D   (banks 7 dy + 8 (dz % 2): 12 distinct)
+   //   L1MAP 2 (p=6): 14 of 16 lanes, dy = 2h + r / D, dz = r % D   (banks 8 (dy % 2) + 7 dz: 14 distinct)
+   //   L2MAP 1 (p=5): 14 of 16 lanes, qx = r % Q, dz = 2h + r / Q   (banks qx + 8 (dz % 2))
+   // with h = half-warp of the group, r = lane in it.  Wavefronts per element of the four exchange shapes:
+   // p=5 558 -> 426, p=6 696 -> 600, both the ideal count for their lane numbers.
+#ifndef CDM_G_LANEMAP
+#define CDM_G_LANEMAP 1
+#endif
+   static constexpr int L1MAP = (INPLACE && CDM_G_LANEMAP) ? (P == 5 ? 1 : 2) : 0;
+   static constexpr int L2MAP = (INPLACE && CDM_G_LANEMAP && P == 5) ? 1 : 0;
+   static constexpr int RSTR = (P == 3) ? 28 : (P == 4 ? 45 : (P == 6 ? 71 : (INPLACE ? (L2MAP ? 56 : 58) : (Q * Q + ((Q * Q) % 2 == 0 ? 1 : 2)))));
    static constexpr int PST = (P == 4) ? 9 : (P == 6 ? 17 : Q);
    static constexpr int PSY = INPLACE ? Q : PST, PSZ = INPLACE ? RSTR : PST * D;   // P(q; dy,dz) = q + PSY dy + PSZ dz
    static constexpr int RS = ((D - 1) * RSTR + Q * Q + 1) & ~1;
@@ -248,12 +259,18 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    constexpr int QH = Q / 2, DH = (D + 1) / 2;
    const int hw = BAL ? (t >> 5) : 0;                                  // warp of the group (warp-uniform)
    const int tl = BAL ? (t & 31) : t;
-   const bool l1 = BAL ? (gib >= 0 && tl < D * D) : (member && t < D * D);
-   const bool l2 = BAL ? (gib >= 0 && tl < Q * D) : (member && t < Q * D);
+   const int hh = t >> 4, hr = t & 15;                                 // half-warp of the group, lane in it (lane maps)
+   const bool l1 = BAL ? (gib >= 0 && tl < D * D)
+                       : (C::L1MAP == 1 ? (gib >= 0 && hr < 2 * D && 2 * hh + hr / D < D)
+                          : (C::L1MAP == 2 ? (gib >= 0 && hr < 2 * D && 2 * hh + hr / D < D) : (member && t < D * D)));
+   const bool l2 = BAL ? (gib >= 0 && tl < Q * D)
+                       : (C::L2MAP == 1 ? (gib >= 0 && hr < 2 * Q && 2 * hh + hr / Q < D) : (member && t < Q * D));
    const int t3 = member ? t : 0;                                      // L3 role: (qx,qy) = t
-   const int qx2 = l2 ? tl / D : 0, dz2 = l2 ? tl % D : 0;             // L2 role
+   const int qx2 = !l2 ? 0 : (C::L2MAP == 1 ? hr % Q : tl / D);        // L2 role
+   const int dz2 = !l2 ? 0 : (C::L2MAP == 1 ? 2 * hh + hr / Q : tl % D);
    // L1 role: x-line (dy,dz), its index t1 = dy + D dz in the element, its row pb1 in the P layout
-   const int dy1 = l1 ? (C::M1 ? tl / D : tl % D) : 0, dz1 = l1 ? (C::M1 ? tl % D : tl / D) : 0;
+   const int dy1 = !l1 ? 0 : (C::L1MAP == 1 ? hr % D : (C::L1MAP == 2 ? 2 * hh + hr / D : tl % D));
+   const int dz1 = !l1 ? 0 : (C::L1MAP == 1 ? 2 * hh + hr / D : (C::L1MAP == 2 ? hr % D : tl / D));
    const int t1 = C::INPLACE ? dy1 + D * dz1 : (l1 ? tl : 0);
    const int pb1 = C::INPLACE ? C::PSY * dy1 + C::PSZ * dz1 : C::PST * t1;
    auto gsync = [&]()
