@@ -80,12 +80,13 @@ template <int P> struct GroupCfg
    // two-warp groups they come from a brute-force search over the 64-bit bank pattern of the four access
    // shapes (F1 write / F2 read of P, F2 write / F3 read of R): wavefronts per access, old -> new:
    // p=4  P 8 -> 4, R 4 -> 2 (ideal 4, 2);  p=6  P 41 -> 8, R 11 -> 4 (ideal 8, 4);  p=5 unchanged (8 / 5, ideal 6 / 3).
-   // INPLACE: the P content lives in R0 / R1 with the R strides, P(q; dy,dz) = q + Q dy + RSTR dz.  An L2 thread (qx,dz)
-   // of F2 / B2 then reads and writes only entries qx + Q j + RSTR dz of its own (qx,dz): the y contractions are in-place
-   // transforms, no P buffers and no extra barrier.  p=5: RSTR 58 keeps the wavefront count of the separate layout
-   // (558 per element, ideal 426) and 35.6 instead of 38.8 KB per group = 6 instead of 5 groups per SM with the same code
-   // shape (no register-cap change: ptxas spills under the 168-register cap of MINB >= 5).  p=6 (L1 lanes dz-fastest):
-   // 696 instead of 600 wavefronts, kept as a variant beside ALIAS.
+   // INPLACE (p = 5, 6, where shared memory bounds the resident groups): the P content lives in R0 / R1 with the R strides,
+   // P(q; dy,dz) = q + Q dy + RSTR dz.  An L2 thread (qx,dz) of F2 / B2 then reads and writes only entries
+   // qx + Q j + RSTR dz of its own (qx,dz), all inputs before the first output: the y contractions are in-place
+   // transforms, no P buffers and no extra barrier.  p=5: 35.4 instead of 38.8 KB per group = 6 instead of 5 groups per
+   // SM with the same code shape (ptxas spills under the 168-register cap of MINB >= 5, so MINB stays 4 and the 6th group
+   // fits by itself at 160 registers); p=6: 52.8 instead of 66.1 KB = 4 instead of 3 groups.  Measured at 8 M dofs:
+   // p=5 74 -> 81 %, p=6 74 -> 86 % of the HBM roofline (82 / 90 % with the lane maps below).
    static constexpr bool INPLACE = (P == 5 && CDM_G5_INPLACE) || (P == 6 && CDM_G6_INPLACE);
    // Lane maps of the L1 (x-line) and L2 (qx,dz) roles when INPLACE: a half-warp is one 64-bit shared-memory
    // wavefront, so it is given only as many lines as have distinct banks, the rest of its lanes idle:
@@ -104,14 +105,24 @@ template <int P> struct GroupCfg
    static constexpr int PSY = INPLACE ? Q : PST, PSZ = INPLACE ? RSTR : PST * D;   // P(q; dy,dz) = q + PSY dy + PSZ dz
    static constexpr int RS = ((D - 1) * RSTR + Q * Q + 1) & ~1;
    static constexpr int PS = (PST * D * D + 1) & ~1;
-   // ALIAS (p >= 5, where shared memory bounds the resident groups): the P and the R exchange buffers share one region.
-   // P is live F1 -> F2 and B2 -> B3, R is live F2 -> F3 and B1 -> B2; they only overlap inside F2 and B2, which then
-   // read all their inputs into registers, meet at the group barrier, and write afterwards (two more barriers per
-   // element).  p=6: 66.1 -> 54.3 KB per group = 4 instead of 3 groups per SM; p=5: 38.8 -> 34.8 KB = 6 instead of 5.
+   // ALIAS (variant, off when INPLACE): the P and the R exchange buffers share one region; F2 and B2 read all their
+   // inputs into registers, meet at the group barrier, and write afterwards (two more barriers per element).  p=6: 4
+   // groups, 87 %; p=5: the barriers push ptxas to 254 registers (or spills under a cap): 67 %.  Superseded by INPLACE.
    static constexpr bool ALIAS = (P >= 5) && CDM_G_ALIAS && !INPLACE;
    // the D stage waits for all slab barriers before its first product (the slabs were requested one element ago): the
    // wait loops no longer fence the loads of one slab from the products of the previous one
    static constexpr bool WAITALL = (P == 5) ? CDM_G5_WAITALL : CDM_G_WAITALL;
+#ifndef CDM_G4_FUSEZ
+#define CDM_G4_FUSEZ 0
+#endif
+#ifndef CDM_G5_FUSEZ
+#define CDM_G5_FUSEZ 0
+#endif
+#ifndef CDM_G6_FUSEZ
+#define CDM_G6_FUSEZ 0
+#endif
+   // z contraction, point-wise D and transposed z contraction fused per quadrature level (see the kernel)
+   static constexpr bool FUSEZ = (P == 4 && CDM_G4_FUSEZ) || (P == 5 && CDM_G5_FUSEZ) || (P == 6 && CDM_G6_FUSEZ);
    static constexpr int XS = INPLACE ? 3 * RS : (ALIAS ? (3 * RS > 2 * PS ? 3 * RS : 2 * PS) : 3 * RS + 2 * PS);   // exchange doubles per group
 };
 
@@ -220,6 +231,7 @@ __device__ __forceinline__ void grp_b3(const GroupTables &tb, const double *sP0,
    for (int dx = DLO; dx < DHI; dx++)
    {
       const double a = SPLIT ? yb[dx] + yg[dx] : yb[dx];
+      // (plain stores for the dofs inside the element, which belong to it alone, were measured: 2 points SLOWER than red.add)
       if (ATOMIC) { if (g[dx] >= 0) { g_red_add(y + g[dx], a); } }
       else { y[e * ND + D * t1 + dx] = a; }
    }
@@ -235,6 +247,8 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    constexpr int D = C::D, Q = C::Q, T = C::T, ND = C::ND, Q2 = Q * Q;
    constexpr int RS = C::RS, PS = C::PS, RSTR = C::RSTR;
    constexpr bool GRAD = DIFF || CONV, ALIAS = C::ALIAS;
+   // p=4 with E-vector output: the separate stages spill ~500 B at the 128-register cap, the fused form does not
+   constexpr bool FUSEZ = C::FUSEZ || (P == 4 && !ATOMIC);
    extern __shared__ __align__(128) unsigned char smraw[];
    const int group_doubles = (Q * slab + C::XS + 1) & ~1;
    // ---- which group am I, which thread of the group
@@ -368,81 +382,155 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
          }
       }
       gsync();
-      // ---- F3 (L3 threads): z contraction in registers
-      double u[Q], ux[Q], uy[Q], uz[Q];
+      if (FUSEZ)
       {
-         double vbb[D], vgb[D], vbg[D];
+         // ---- F3 + D + B1 fused per quadrature level (L3 threads): the level's u, grad u are formed from the D z-inputs,
+         // multiplied by the level's D values and accumulated straight into the 3 D transposed-z sums, so the 4 Q point
+         // values never exist together (6 D + ~10 instead of 3 D + 4 Q live doubles)
+         double vbb[D], vgb[D], vbg[D], awx[D], awy[D], awb[D];
          #pragma unroll
          for (int dz = 0; dz < D; dz++)
          {
             vbb[dz] = sR0[t3 + RSTR * dz];
             if (GRAD) { vgb[dz] = sR1[t3 + RSTR * dz]; vbg[dz] = sR2[t3 + RSTR * dz]; }
+            awx[dz] = 0.0; awy[dz] = 0.0; awb[dz] = 0.0;
          }
-         #pragma unroll
-         for (int qz = 0; qz < Q; qz++)
+         if (valid)
          {
-            double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-            #pragma unroll
-            for (int dz = 0; dz < D; dz++)
+            if (C::WAITALL)
             {
-               a += tb.B[qz * D + dz] * vbb[dz];
-               if (GRAD) { b += tb.B[qz * D + dz] * vgb[dz]; c += tb.B[qz * D + dz] * vbg[dz]; d += tb.G[qz * D + dz] * vbb[dz]; }
+               #pragma unroll
+               for (int qz = 0; qz < Q; qz++) { g_mbar_wait(&bars[qz], parity); }
             }
-            u[qz] = a; ux[qz] = b; uy[qz] = c; uz[qz] = d;
-         }
-      }
-      // ---- point-wise D at the thread's Q quadrature points (registers only)
-      if (valid)
-      {
-         if (C::WAITALL)
-         {
-            #pragma unroll
-            for (int qz = 0; qz < Q; qz++) { g_mbar_wait(&bars[qz], parity); }
-         }
-         #pragma unroll
-         for (int qz = 0; qz < Q; qz++)
-         {
-            if (!C::WAITALL) { g_mbar_wait(&bars[qz], parity); }
-            const double *dp = ring + qz * slab + t3;
-            double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;
-            int c = 0;
-            if (DIFF)
-            {
-               const double d0 = dp[0], d1 = dp[Q2], d2 = dp[2 * Q2], d3 = dp[3 * Q2], d4 = dp[4 * Q2], d5 = dp[5 * Q2];
-               fx = d0 * ux[qz] + d1 * uy[qz] + d2 * uz[qz];
-               fy = d1 * ux[qz] + d3 * uy[qz] + d4 * uz[qz];
-               fz = d2 * ux[qz] + d4 * uy[qz] + d5 * uz[qz];
-               c = 6;
-            }
-            if (CONV) { s = dp[c * Q2] * ux[qz] + dp[(c + 1) * Q2] * uy[qz] + dp[(c + 2) * Q2] * uz[qz]; c += 3; }
-            if (MASS) { s += dp[c * Q2] * u[qz]; }
-            ux[qz] = fx; uy[qz] = fy; uz[qz] = fz; u[qz] = s;
-         }
-      }
-      gsync();                                               // D tile and the R buffers are consumed
-      if (member && t == 0 && more)
-      {
-         for (int q = 0; q < Q; q++)
-         {
-            g_mbar_expect_tx(&bars[q], slab_bytes);
-            g_bulk_g2s(ring + q * slab, Dg + (en * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
-         }
-      }
-      // ---- B1 (L3 threads): transposed z contraction in registers
-      if (member && valid)
-      {
-         #pragma unroll
-         for (int dz = 0; dz < D; dz++)
-         {
-            double wx = 0.0, wy = 0.0, wb = 0.0;
             #pragma unroll
             for (int qz = 0; qz < Q; qz++)
             {
-               wb += tb.B[qz * D + dz] * u[qz];
-               if (DIFF) { wx += tb.B[qz * D + dz] * ux[qz]; wy += tb.B[qz * D + dz] * uy[qz]; wb += tb.G[qz * D + dz] * uz[qz]; }
+               double u0 = 0.0, ux0 = 0.0, uy0 = 0.0, uz0 = 0.0;
+               #pragma unroll
+               for (int dz = 0; dz < D; dz++)
+               {
+                  u0 += tb.B[qz * D + dz] * vbb[dz];
+                  if (GRAD) { ux0 += tb.B[qz * D + dz] * vgb[dz]; uy0 += tb.B[qz * D + dz] * vbg[dz]; uz0 += tb.G[qz * D + dz] * vbb[dz]; }
+               }
+               if (!C::WAITALL) { g_mbar_wait(&bars[qz], parity); }
+               const double *dp = ring + qz * slab + t3;
+               double fx = 0.0, fy = 0.0, fz = 0.0, sv = 0.0;
+               int c = 0;
+               if (DIFF)
+               {
+                  const double d0 = dp[0], d1 = dp[Q2], d2 = dp[2 * Q2], d3 = dp[3 * Q2], d4 = dp[4 * Q2], d5 = dp[5 * Q2];
+                  fx = d0 * ux0 + d1 * uy0 + d2 * uz0;
+                  fy = d1 * ux0 + d3 * uy0 + d4 * uz0;
+                  fz = d2 * ux0 + d4 * uy0 + d5 * uz0;
+                  c = 6;
+               }
+               if (CONV) { sv = dp[c * Q2] * ux0 + dp[(c + 1) * Q2] * uy0 + dp[(c + 2) * Q2] * uz0; c += 3; }
+               if (MASS) { sv += dp[c * Q2] * u0; }
+               #pragma unroll
+               for (int dz = 0; dz < D; dz++)
+               {
+                  awb[dz] += tb.B[qz * D + dz] * sv;
+                  if (DIFF) { awx[dz] += tb.B[qz * D + dz] * fx; awy[dz] += tb.B[qz * D + dz] * fy; awb[dz] += tb.G[qz * D + dz] * fz; }
+               }
             }
-            sR2[t3 + RSTR * dz] = wb;
-            if (DIFF) { sR0[t3 + RSTR * dz] = wx; sR1[t3 + RSTR * dz] = wy; }
+         }
+         gsync();                                            // D tile and the R buffers are consumed
+         if (member && t == 0 && more)
+         {
+            for (int q = 0; q < Q; q++)
+            {
+               g_mbar_expect_tx(&bars[q], slab_bytes);
+               g_bulk_g2s(ring + q * slab, Dg + (en * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+            }
+         }
+         if (member && valid)
+         {
+            #pragma unroll
+            for (int dz = 0; dz < D; dz++)
+            {
+               sR2[t3 + RSTR * dz] = awb[dz];
+               if (DIFF) { sR0[t3 + RSTR * dz] = awx[dz]; sR1[t3 + RSTR * dz] = awy[dz]; }
+            }
+         }
+      }
+      else
+      {
+         // ---- F3 (L3 threads): z contraction in registers
+         double u[Q], ux[Q], uy[Q], uz[Q];
+         {
+            double vbb[D], vgb[D], vbg[D];
+            #pragma unroll
+            for (int dz = 0; dz < D; dz++)
+            {
+               vbb[dz] = sR0[t3 + RSTR * dz];
+               if (GRAD) { vgb[dz] = sR1[t3 + RSTR * dz]; vbg[dz] = sR2[t3 + RSTR * dz]; }
+            }
+            #pragma unroll
+            for (int qz = 0; qz < Q; qz++)
+            {
+               double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+               #pragma unroll
+               for (int dz = 0; dz < D; dz++)
+               {
+                  a += tb.B[qz * D + dz] * vbb[dz];
+                  if (GRAD) { b += tb.B[qz * D + dz] * vgb[dz]; c += tb.B[qz * D + dz] * vbg[dz]; d += tb.G[qz * D + dz] * vbb[dz]; }
+               }
+               u[qz] = a; ux[qz] = b; uy[qz] = c; uz[qz] = d;
+            }
+         }
+         // ---- point-wise D at the thread's Q quadrature points (registers only)
+         if (valid)
+         {
+            if (C::WAITALL)
+            {
+               #pragma unroll
+               for (int qz = 0; qz < Q; qz++) { g_mbar_wait(&bars[qz], parity); }
+            }
+            #pragma unroll
+            for (int qz = 0; qz < Q; qz++)
+            {
+               if (!C::WAITALL) { g_mbar_wait(&bars[qz], parity); }
+               const double *dp = ring + qz * slab + t3;
+               double fx = 0.0, fy = 0.0, fz = 0.0, s = 0.0;
+               int c = 0;
+               if (DIFF)
+               {
+                  const double d0 = dp[0], d1 = dp[Q2], d2 = dp[2 * Q2], d3 = dp[3 * Q2], d4 = dp[4 * Q2], d5 = dp[5 * Q2];
+                  fx = d0 * ux[qz] + d1 * uy[qz] + d2 * uz[qz];
+                  fy = d1 * ux[qz] + d3 * uy[qz] + d4 * uz[qz];
+                  fz = d2 * ux[qz] + d4 * uy[qz] + d5 * uz[qz];
+                  c = 6;
+               }
+               if (CONV) { s = dp[c * Q2] * ux[qz] + dp[(c + 1) * Q2] * uy[qz] + dp[(c + 2) * Q2] * uz[qz]; c += 3; }
+               if (MASS) { s += dp[c * Q2] * u[qz]; }
+               ux[qz] = fx; uy[qz] = fy; uz[qz] = fz; u[qz] = s;
+            }
+         }
+         gsync();                                               // D tile and the R buffers are consumed
+         if (member && t == 0 && more)
+         {
+            for (int q = 0; q < Q; q++)
+            {
+               g_mbar_expect_tx(&bars[q], slab_bytes);
+               g_bulk_g2s(ring + q * slab, Dg + (en * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+            }
+         }
+         // ---- B1 (L3 threads): transposed z contraction in registers
+         if (member && valid)
+         {
+            #pragma unroll
+            for (int dz = 0; dz < D; dz++)
+            {
+               double wx = 0.0, wy = 0.0, wb = 0.0;
+               #pragma unroll
+               for (int qz = 0; qz < Q; qz++)
+               {
+                  wb += tb.B[qz * D + dz] * u[qz];
+                  if (DIFF) { wx += tb.B[qz * D + dz] * ux[qz]; wy += tb.B[qz * D + dz] * uy[qz]; wb += tb.G[qz * D + dz] * uz[qz]; }
+               }
+               sR2[t3 + RSTR * dz] = wb;
+               if (DIFF) { sR0[t3 + RSTR * dz] = wx; sR1[t3 + RSTR * dz] = wy; }
+            }
          }
       }
       gsync();
