@@ -29,6 +29,9 @@ __device__ __forceinline__ void g_mbar_wait(uint64_t *bar, uint32_t parity) { cd
 __device__ __forceinline__ void g_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { cdmk::bulk_g2s_stream(dst, src, bytes, bar); }
 __device__ __forceinline__ void g_red_add(double *addr, double v) { cdmk::red_add_f64(addr, v); }
 
+#ifndef CDM_G4_TRIO
+#define CDM_G4_TRIO 1
+#endif
 template <int P> struct GroupCfg
 {
    static constexpr int D = P + 1, Q = P + 2, T = Q * Q, ND = D * D * D;
@@ -41,7 +44,12 @@ template <int P> struct GroupCfg
 #define CDM_G5_GPB 1
 #endif
    static constexpr int GPB = (P <= 3) ? 4 * EPW : (P == 4 ? CDM_G4_GPB : (P == 5 ? CDM_G5_GPB : 1));   // groups per block (two-warp groups: the block IS the group)
-   static constexpr int THREADS = (WPG == 1) ? 32 * (GPB / EPW) : 64 * GPB;
+   // TRIO (p=4): the 36 columns of an element are 32 + 4 lanes, so the second warp of a group issued the whole z /
+   // point-wise stream for four lanes.  A block is now three warps for two elements: warp 0 / warp 1 own columns 0..31 of
+   // element 0 / 1 (and their x / y roles), lanes 0..3 / 4..7 of warp 2 own columns 32..35 of element 0 / 1.  Three
+   // instead of four instruction streams per two elements, block-wide barriers, 168 instead of 128 registers per thread.
+   static constexpr bool TRIO = (P == 4) && CDM_G4_TRIO;
+   static constexpr int THREADS = TRIO ? 96 : ((WPG == 1) ? 32 * (GPB / EPW) : 64 * GPB);
 // resident blocks per SM the register budget is sized for.  p=5: 5 blocks fit the shared memory, but the
 // 204-register cap of MINB = 5 made ptxas spill 200 B inside the element loop (53 % of the roofline);
 // MINB = 4 -> 160 registers, no spills, 73 %.  p=4 (two groups per block): MINB 3 / 4 / 5 -> 46 % / 76 % / 56 %; one group per block x 8 blocks: 52 %.
@@ -73,7 +81,7 @@ template <int P> struct GroupCfg
 #define CDM_G6_MINB ((CDM_G_ALIAS && !CDM_G6_INPLACE) ? 4 : 3)
 #endif
 #ifndef CDM_G4_MINB
-#define CDM_G4_MINB 4
+#define CDM_G4_MINB (CDM_G4_TRIO ? 3 : 4)     // TRIO: 165 registers under (96, 3); four blocks still fit (ptxas spills ~400 B under (96, 4))
 #endif
    static constexpr int MINB = (P < 4) ? 4 : (P == 4 ? CDM_G4_MINB : (P == 5 ? CDM_G5_MINB : CDM_G6_MINB));        // resident blocks per SM the register budget is sized for
    // strides of the exchange layouts P(qx, line) = qx + PST line, R(qx,qy,dz) = qx + Q qy + RSTR dz.  For the
@@ -260,6 +268,12 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       gib = (sub < C::EPW) ? wib * C::EPW + sub : -1;
       t = lane - sub * T;
    }
+   else if (C::TRIO)
+   {
+      const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+      if (wib < 2) { gib = wib; t = lane; }
+      else { gib = (lane < 8) ? (lane >> 2) : -1; t = 32 + (lane & 3); }
+   }
    else { gib = threadIdx.x >> 6; t = threadIdx.x & 63; }
    const bool member = gib >= 0 && t < T;
    const int gsafe = gib >= 0 ? gib : 0;
@@ -270,6 +284,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    // Q D = 30 threads, are run by BOTH warps, each producing one half of the stage's outputs for every line; without
    // it the second warp idles through four of the seven stages and `barrier` is the top stall of the kernel
    constexpr bool BAL = C::WPG == 2 && Q * D <= 32 && CDM_G_BALANCED;
+   static_assert(!(BAL && C::TRIO), "the two-warp x / y stages and the three-warp blocks exclude each other");
    constexpr int QH = Q / 2, DH = (D + 1) / 2;
    const int hw = BAL ? (t >> 5) : 0;                                  // warp of the group (warp-uniform)
    const int tl = BAL ? (t & 31) : t;
@@ -291,7 +306,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    {
       if (C::WPG == 1) { __syncwarp(); }
 #ifndef CDM_G_REGBAR
-      else if (C::GPB == 1) { __syncthreads(); }             // the block is the group: barrier 0, immediate operand (a register
+      else if (C::GPB == 1 || C::TRIO) { __syncthreads(); }  // the block is the group: barrier 0, immediate operand (a register
                                                              // barrier id showed up as 4-12 % branch_resolving stalls)
 #endif
       else { asm volatile("bar.sync %0, 64;" ::"r"(gsafe + 1) : "memory"); }
@@ -401,6 +416,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
             {
                #pragma unroll
                for (int qz = 0; qz < Q; qz++) { g_mbar_wait(&bars[qz], parity); }
+               if (C::TRIO) { __syncwarp(__activemask()); }     // warp 2 waited on the barriers of two elements: reconverge
             }
             #pragma unroll
             for (int qz = 0; qz < Q; qz++)
@@ -485,6 +501,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
             {
                #pragma unroll
                for (int qz = 0; qz < Q; qz++) { g_mbar_wait(&bars[qz], parity); }
+               if (C::TRIO) { __syncwarp(__activemask()); }     // warp 2 waited on the barriers of two elements: reconverge
             }
             #pragma unroll
             for (int qz = 0; qz < Q; qz++)
