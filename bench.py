@@ -286,6 +286,9 @@ def main():
     ms_step, launches = time_applies(op, x, y, K, W)
     gdofs = n_global / (ms_step * 1e-3) / 1e9
     halo_used = op.get_option("halo") if world > 1 else None
+    # kernel-only time of the dominant kernel (roofline), taken right after the timed steps and under the same clocks:
+    # the 400-apply run below drives the board into its power cap (profiles/r02_sustained_probe_p3.jsonl)
+    k_ms = op.time_kernel(x, y, reps=max(20, min(K, 50)), constrained=True)
     # a longer run of the same step (>= 400 applies ~ 0.2 s) so that the 100 ms clock samples fall inside timed work
     ms_long, _ = time_applies(op, x, y, max(400, K), 0)
     # the same apply as a stand-alone Operator::Mult on true-dof vectors: P on x first (its ghost entries are unknown)
@@ -300,8 +303,7 @@ def main():
     ms_det, _ = time_applies(op, x, y, max(50, K // 4), 3)
     op.set_option("scatter", scat_default)
 
-    # ---- kernel-only time of the dominant kernel (roofline)
-    k_ms = op.time_kernel(x, y, reps=20, constrained=True)
+    # ---- roofline of the dominant kernel (k_ms: measured above, next to the timed steps)
     bytes_launch = algorithmic_bytes(sp.ndof, sp.ne, args.order)
     achieved = bytes_launch / (k_ms * 1e-3) / 1e9
     traffic = None       # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
@@ -364,8 +366,10 @@ def main():
         mesh, sp, op, x, y, ng5, ne5 = build(args.config5_n)
         if world > 1:
             op.set_option("ghost_in", 1)
-        ms5, _ = time_applies(op, x, y, max(50, K // 2), 5)
+        for _ in range(3):
+            op.Mult(x, y)
         k5 = op.time_kernel(x, y, reps=10, constrained=True)
+        ms5, _ = time_applies(op, x, y, max(50, K // 2), 2)
         b5 = algorithmic_bytes(sp.ndof, sp.ne, args.order)
         kr5 = krylov_iter(sp, op, sp.ntrue, sp.ndof)
         config5 = {"workload": f"{args.config5_n}^3 elements per GPU (BASELINE config 5: weak scaling at ~25 M dofs per GPU)",
