@@ -13,6 +13,7 @@
 // two-level gather prefetch, fp64 red.add scatter (or E-vector stores).
 #include "cdm_internal.hpp"
 #include "kernels_common.cuh"
+#include <type_traits>
 
 namespace
 {
@@ -32,6 +33,9 @@ __device__ __forceinline__ void g_red_add(double *addr, double v) { cdmk::red_ad
 #ifndef CDM_G4_TRIO
 #define CDM_G4_TRIO 1
 #endif
+#ifndef CDM_G5_PENTA
+#define CDM_G5_PENTA 0               // measured: 79.1 % against 81.5 % for two warps per element (10 instead of 12 warps per SM)
+#endif
 template <int P> struct GroupCfg
 {
    static constexpr int D = P + 1, Q = P + 2, T = Q * Q, ND = D * D * D;
@@ -43,13 +47,19 @@ template <int P> struct GroupCfg
 #ifndef CDM_G5_GPB
 #define CDM_G5_GPB 1
 #endif
-   static constexpr int GPB = (P <= 3) ? 4 * EPW : (P == 4 ? CDM_G4_GPB : (P == 5 ? CDM_G5_GPB : 1));   // groups per block (two-warp groups: the block IS the group)
+   static constexpr int GPB = (P <= 3) ? 4 * EPW : (P == 4 ? CDM_G4_GPB : (P == 5 ? (CDM_G5_PENTA ? 3 : CDM_G5_GPB) : 1));   // groups per block (two-warp groups: the block IS the group)
    // TRIO (p=4): the 36 columns of an element are 32 + 4 lanes, so the second warp of a group issued the whole z /
    // point-wise stream for four lanes.  A block is now three warps for two elements: warp 0 / warp 1 own columns 0..31 of
    // element 0 / 1 (and their x / y roles), lanes 0..3 / 4..7 of warp 2 own columns 32..35 of element 0 / 1.  Three
    // instead of four instruction streams per two elements, block-wide barriers, 168 instead of 128 registers per thread.
    static constexpr bool TRIO = (P == 4) && CDM_G4_TRIO;
-   static constexpr int THREADS = TRIO ? 96 : ((WPG == 1) ? 32 * (GPB / EPW) : 64 * GPB);
+   // PENTA (p=5): 49 columns are 32 + 17 lanes.  A block is five warps for three elements: warp g < 3 owns columns 0..31 of
+   // element g and the first two half-warps of its x / y roles; half-warp k < 3 of the two helper warps owns columns 32..47
+   // and the third x / y half-warp of element k; three more lanes own column 48 of the three elements.  Five instead of six
+   // instruction streams per three elements (group size 4420 doubles = 4 mod 16: the three column-48 lanes hit distinct banks).
+   static constexpr bool PENTA = (P == 5) && CDM_G5_PENTA;
+   static constexpr bool PACKED = TRIO || PENTA;               // warps shared between the elements of a block, block-wide barriers
+   static constexpr int THREADS = TRIO ? 96 : (PENTA ? 160 : ((WPG == 1) ? 32 * (GPB / EPW) : 64 * GPB));
 // resident blocks per SM the register budget is sized for.  p=5: 5 blocks fit the shared memory, but the
 // 204-register cap of MINB = 5 made ptxas spill 200 B inside the element loop (53 % of the roofline);
 // MINB = 4 -> 160 registers, no spills, 73 %.  p=4 (two groups per block): MINB 3 / 4 / 5 -> 46 % / 76 % / 56 %; one group per block x 8 blocks: 52 %.
@@ -75,7 +85,7 @@ template <int P> struct GroupCfg
 #define CDM_G6_INPLACE 1
 #endif
 #ifndef CDM_G5_MINB
-#define CDM_G5_MINB ((CDM_G_ALIAS && !CDM_G5_INPLACE) ? 6 : 4)
+#define CDM_G5_MINB (CDM_G5_PENTA ? 1 : ((CDM_G_ALIAS && !CDM_G5_INPLACE) ? 6 : 4))
 #endif
 #ifndef CDM_G6_MINB
 #define CDM_G6_MINB ((CDM_G_ALIAS && !CDM_G6_INPLACE) ? 4 : 3)
@@ -274,6 +284,13 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       if (wib < 2) { gib = wib; t = lane; }
       else { gib = (lane < 8) ? (lane >> 2) : -1; t = 32 + (lane & 3); }
    }
+   else if (C::PENTA)
+   {
+      const int tid = threadIdx.x;
+      if (tid < 96) { gib = tid >> 5; t = tid & 31; }
+      else if (tid < 144) { gib = (tid - 96) >> 4; t = 32 + (tid & 15); }
+      else { gib = (tid < 147) ? tid - 144 : -1; t = 48; }
+   }
    else { gib = threadIdx.x >> 6; t = threadIdx.x & 63; }
    const bool member = gib >= 0 && t < T;
    const int gsafe = gib >= 0 ? gib : 0;
@@ -284,7 +301,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    // Q D = 30 threads, are run by BOTH warps, each producing one half of the stage's outputs for every line; without
    // it the second warp idles through four of the seven stages and `barrier` is the top stall of the kernel
    constexpr bool BAL = C::WPG == 2 && Q * D <= 32 && CDM_G_BALANCED;
-   static_assert(!(BAL && C::TRIO), "the two-warp x / y stages and the three-warp blocks exclude each other");
+   static_assert(!(BAL && C::PACKED), "the two-warp x / y stages and the packed blocks exclude each other");
    constexpr int QH = Q / 2, DH = (D + 1) / 2;
    const int hw = BAL ? (t >> 5) : 0;                                  // warp of the group (warp-uniform)
    const int tl = BAL ? (t & 31) : t;
@@ -306,7 +323,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    {
       if (C::WPG == 1) { __syncwarp(); }
 #ifndef CDM_G_REGBAR
-      else if (C::GPB == 1 || C::TRIO) { __syncthreads(); }  // the block is the group: barrier 0, immediate operand (a register
+      else if (C::GPB == 1 || C::PACKED) { __syncthreads(); }  // the block is the group: barrier 0, immediate operand (a register
                                                              // barrier id showed up as 4-12 % branch_resolving stalls)
 #endif
       else { asm volatile("bar.sync %0, 64;" ::"r"(gsafe + 1) : "memory"); }
@@ -318,11 +335,17 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    gsync();
-   const int64_t ngroups = (int64_t)gridDim.x * C::GPB;
-   const int64_t gg = (int64_t)blockIdx.x * C::GPB + gsafe;
+   // Element indices: 32-bit where measured faster (the launcher refuses more than 2e9 elements).  In the packed layouts
+   // gg, e, en are per-thread values; as 64-bit integers they cost 7-29 registers.  p=4 with red.add output: 92.4 -> 95.3 %
+   // of the HBM roofline; p=6 loses 6 points and p=4 with E-vector output 18 % (a different ptxas schedule), p=5 0.8.
+   constexpr bool IDX32 = (C::TRIO && ATOMIC) || C::PENTA;
+   using eidx = typename std::conditional<IDX32, int, int64_t>::type;
+   const eidx ngroups = (eidx)gridDim.x * C::GPB;
+   const eidx gg = (eidx)blockIdx.x * C::GPB + gsafe;
    // every group of a warp runs the same number of rounds (the lowest group of the block needs the most)
-   const int64_t g0 = (int64_t)blockIdx.x * C::GPB;
-   const int64_t rounds = (g0 < ne) ? (ne - g0 + ngroups - 1) / ngroups : 0;
+   const eidx g0 = (eidx)blockIdx.x * C::GPB;
+   const eidx nel = (eidx)ne;
+   const eidx rounds = (g0 < nel) ? (nel - g0 + ngroups - 1) / ngroups : 0;
    const uint32_t slab_bytes = (uint32_t)slab * 8u;
 
    // gather pipeline: indices two elements ahead, values one element ahead
@@ -330,24 +353,24 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    double px[D];
    #pragma unroll
    for (int i = 0; i < D; i++) { pg[i] = -1; pgn[i] = -1; px[i] = 0.0; }
-   if (gib >= 0 && gg < ne)
+   if (gib >= 0 && gg < nel)
    {
       if (member && t == 0)
       {
          for (int q = 0; q < Q; q++)
          {
             g_mbar_expect_tx(&bars[q], slab_bytes);
-            g_bulk_g2s(ring + q * slab, Dg + (gg * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+            g_bulk_g2s(ring + q * slab, Dg + ((int64_t)gg * Q + q) * slab, slab_bytes, &bars[q]);
          }
       }
       if (l1)
       {
          #pragma unroll
-         for (int i = 0; i < D; i++) { pg[i] = __ldg(gmap + gg * ND + D * t1 + i); }
-         if (gg + ngroups < ne)
+         for (int i = 0; i < D; i++) { pg[i] = __ldg(gmap + (int64_t)gg * ND + D * t1 + i); }
+         if (gg + ngroups < nel)
          {
             #pragma unroll
-            for (int i = 0; i < D; i++) { pgn[i] = __ldg(gmap + (gg + ngroups) * ND + D * t1 + i); }
+            for (int i = 0; i < D; i++) { pgn[i] = __ldg(gmap + (int64_t)(gg + ngroups) * ND + D * t1 + i); }
          }
          #pragma unroll
          for (int i = 0; i < D; i++) { px[i] = (pg[i] >= 0) ? __ldg(x + pg[i]) : 0.0; }
@@ -355,12 +378,12 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    }
 
    uint32_t parity = 0;
-   for (int64_t r = 0; r < rounds; r++, parity ^= 1u)
+   for (eidx r = 0; r < rounds; r++, parity ^= 1u)
    {
-      const int64_t e = gg + r * ngroups;
-      const bool valid = gib >= 0 && e < ne;
-      const int64_t en = e + ngroups;
-      const bool more = gib >= 0 && en < ne;
+      const eidx e = gg + r * ngroups;
+      const bool valid = gib >= 0 && e < nel;
+      const eidx en = e + ngroups;
+      const bool more = gib >= 0 && en < nel;
       int32_t g[D];
       #pragma unroll
       for (int i = 0; i < D; i++) { g[i] = pg[i]; }
@@ -375,10 +398,10 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
       {
          #pragma unroll
          for (int i = 0; i < D; i++) { pg[i] = pgn[i]; }
-         if (en + ngroups < ne)
+         if (en + ngroups < nel)
          {
             #pragma unroll
-            for (int i = 0; i < D; i++) { pgn[i] = __ldg(gmap + (en + ngroups) * ND + D * t1 + i); }
+            for (int i = 0; i < D; i++) { pgn[i] = __ldg(gmap + (int64_t)(en + ngroups) * ND + D * t1 + i); }
          }
          #pragma unroll
          for (int i = 0; i < D; i++) { px[i] = (pg[i] >= 0) ? __ldg(x + pg[i]) : 0.0; }
@@ -416,7 +439,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
             {
                #pragma unroll
                for (int qz = 0; qz < Q; qz++) { g_mbar_wait(&bars[qz], parity); }
-               if (C::TRIO) { __syncwarp(__activemask()); }     // warp 2 waited on the barriers of two elements: reconverge
+               if (C::PACKED) { __syncwarp(__activemask()); }   // a helper warp waited on the barriers of several elements: reconverge
             }
             #pragma unroll
             for (int qz = 0; qz < Q; qz++)
@@ -456,7 +479,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
             for (int q = 0; q < Q; q++)
             {
                g_mbar_expect_tx(&bars[q], slab_bytes);
-               g_bulk_g2s(ring + q * slab, Dg + (en * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+               g_bulk_g2s(ring + q * slab, Dg + ((int64_t)en * Q + q) * slab, slab_bytes, &bars[q]);
             }
          }
          if (member && valid)
@@ -501,7 +524,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
             {
                #pragma unroll
                for (int qz = 0; qz < Q; qz++) { g_mbar_wait(&bars[qz], parity); }
-               if (C::TRIO) { __syncwarp(__activemask()); }     // warp 2 waited on the barriers of two elements: reconverge
+               if (C::PACKED) { __syncwarp(__activemask()); }   // a helper warp waited on the barriers of several elements: reconverge
             }
             #pragma unroll
             for (int qz = 0; qz < Q; qz++)
@@ -529,7 +552,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
             for (int q = 0; q < Q; q++)
             {
                g_mbar_expect_tx(&bars[q], slab_bytes);
-               g_bulk_g2s(ring + q * slab, Dg + (en * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+               g_bulk_g2s(ring + q * slab, Dg + ((int64_t)en * Q + q) * slab, slab_bytes, &bars[q]);
             }
          }
          // ---- B1 (L3 threads): transposed z contraction in registers
@@ -590,6 +613,7 @@ int launch_group(cdm_op *op, const GroupTables &tb, const int32_t *gmap, const d
    const int64_t e0 = op->range_on ? op->e_begin : 0, e1 = op->range_on ? op->e_end : sp->ne;
    const int64_t n = e1 - e0;
    if (n <= 0) { return CDM_OK; }
+   if (n > 2000000000LL) { return 1; }                       // 32-bit element indices in the kernel: the caller falls back
    int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
    const int64_t need = (n + C::GPB - 1) / C::GPB;
    if (grid > need) { grid = need; }
