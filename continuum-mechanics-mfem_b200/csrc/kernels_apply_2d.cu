@@ -15,10 +15,14 @@
 // Algorithmic bytes per element: 8 n_D Q^2 + 4 D^2 (+ 16 B per unique dof), SURVEY.md 8(d).
 #include "cdm_internal.hpp"
 #include "kernels_common.cuh"
+#include <type_traits>
 
 namespace
 {
 using namespace cdmk;
+#ifndef CDM_2D_IDX32_FROM
+#define CDM_2D_IDX32_FROM 3
+#endif
 
 template <int P, int NW, int NBUF, int MINB, bool DIFF, bool CONV, bool MASS, bool ATOMIC>
 __global__ void __launch_bounds__(NW * 32, MINB)
@@ -26,6 +30,8 @@ k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restri
                  const double *__restrict__ Dg, const int slab, const int sstride, double *__restrict__ y)
 {
    constexpr int D = P + 1, Q = P + 1, ND = D * D, Q2 = Q * Q;
+   // chunk / element indices: 32-bit at the orders that sit at the register cap (the launcher refuses more than 2e9 elements)
+   using eidx = typename std::conditional<(P >= CDM_2D_IDX32_FROM), int, int64_t>::type;
    constexpr int OC = DIFF ? 3 : 0, OM = OC + (CONV ? 2 : 0);
    constexpr bool PF = P <= 3;              // gather one chunk ahead (order 4 has no registers to spare for it)
    // ... and the indices two chunks ahead, so that the value loads never wait for them: measured +2.5 % at p = 1, +3 % at
@@ -41,42 +47,42 @@ k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restri
       mbar_init_fence();
    }
    __syncwarp();
-   const int64_t nwarps = (int64_t)gridDim.x * NW, gw = (int64_t)blockIdx.x * NW + wib;
-   const int64_t nchunks = (ne + 31) >> 5;
+   const eidx nwarps = (eidx)gridDim.x * NW, gw = (eidx)blockIdx.x * NW + wib;
+   const eidx nel = (eidx)ne, nchunks = (eidx)((ne + 31) >> 5);
    const uint32_t slab_bytes = (uint32_t)slab * 8u;
-   auto issue = [&](int64_t chunk, int b)
+   auto issue = [&](eidx chunk, int b)
    {
-      const int64_t e = chunk * 32 + lane;
-      const int64_t left = ne - chunk * 32;
+      const eidx e = chunk * 32 + lane;
+      const eidx left = nel - chunk * 32;
       if (lane == 0) { mbar_expect_tx(&bars[b], (uint32_t)(left < 32 ? left : 32) * slab_bytes); }
       __syncwarp();
-      if (e < ne) { bulk_g2s_stream(wbuf + (size_t)(b * 32 + lane) * sstride, Dg + e * (int64_t)slab, slab_bytes, &bars[b]); }
+      if (e < nel) { bulk_g2s_stream(wbuf + (size_t)(b * 32 + lane) * sstride, Dg + e * (int64_t)slab, slab_bytes, &bars[b]); }
    };
    if (gw < nchunks) { issue(gw, 0); }
    // gather pipeline: the dofs of the next chunk are fetched while the current one is being processed
    int32_t g[ND], gn[ND], gnn[PF2 ? ND : 1];
    double u[ND];
    {
-      const int64_t e = gw * 32 + lane;
+      const eidx e = gw * 32 + lane;
       #pragma unroll
-      for (int i = 0; i < ND; i++) { gn[i] = (PF && gw < nchunks && e < ne) ? __ldg(gmap + e * ND + i) : -1; }
+      for (int i = 0; i < ND; i++) { gn[i] = (PF && gw < nchunks && e < nel) ? __ldg(gmap + (int64_t)e * ND + i) : -1; }
       if (PF2)
       {
-         const int64_t e2 = (gw + nwarps) * 32 + lane;
+         const eidx e2 = (gw + nwarps) * 32 + lane;
          #pragma unroll
-         for (int i = 0; i < ND; i++) { gnn[i] = (gw + nwarps < nchunks && e2 < ne) ? __ldg(gmap + e2 * ND + i) : -1; }
+         for (int i = 0; i < ND; i++) { gnn[i] = (gw + nwarps < nchunks && e2 < nel) ? __ldg(gmap + (int64_t)e2 * ND + i) : -1; }
       }
       #pragma unroll
       for (int i = 0; i < ND; i++) { u[i] = (PF && gn[i] >= 0) ? __ldg(x + gn[i]) : 0.0; }
    }
    int it = 0;
-   for (int64_t chunk = gw; chunk < nchunks; chunk += nwarps, it++)
+   for (eidx chunk = gw; chunk < nchunks; chunk += nwarps, it++)
    {
       const int b = (NBUF == 2) ? (it & 1) : 0;
-      const int64_t next = chunk + nwarps;
+      const eidx next = chunk + nwarps;
       if (NBUF == 2 && next < nchunks) { issue(next, b ^ 1); }     // the other buffer was consumed one iteration ago
-      const int64_t e = chunk * 32 + lane;
-      const bool valid = e < ne;
+      const eidx e = chunk * 32 + lane;
+      const bool valid = e < nel;
       if (PF)
       {
          #pragma unroll
@@ -85,7 +91,7 @@ k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restri
       else
       {
          #pragma unroll
-         for (int i = 0; i < ND; i++) { g[i] = valid ? __ldg(gmap + e * ND + i) : -1; }
+         for (int i = 0; i < ND; i++) { g[i] = valid ? __ldg(gmap + (int64_t)e * ND + i) : -1; }
          #pragma unroll
          for (int i = 0; i < ND; i++) { u[i] = (g[i] >= 0) ? __ldg(x + g[i]) : 0.0; }
       }
@@ -114,17 +120,17 @@ k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restri
          for (int i = 0; i < ND; i++) { gn[i] = gnn[i]; }
          #pragma unroll
          for (int i = 0; i < ND; i++) { u[i] = (gn[i] >= 0) ? __ldg(x + gn[i]) : 0.0; }
-         const int64_t n2 = next + nwarps, e2 = n2 * 32 + lane;
-         const bool nv = n2 < nchunks && e2 < ne;
+         const eidx n2 = next + nwarps, e2 = n2 * 32 + lane;
+         const bool nv = n2 < nchunks && e2 < nel;
          #pragma unroll
-         for (int i = 0; i < ND; i++) { gnn[i] = nv ? __ldg(gmap + e2 * ND + i) : -1; }
+         for (int i = 0; i < ND; i++) { gnn[i] = nv ? __ldg(gmap + (int64_t)e2 * ND + i) : -1; }
       }
       else if (PF)
       {
-         const int64_t en = next * 32 + lane;
-         const bool nv = next < nchunks && en < ne;
+         const eidx en = next * 32 + lane;
+         const bool nv = next < nchunks && en < nel;
          #pragma unroll
-         for (int i = 0; i < ND; i++) { gn[i] = nv ? __ldg(gmap + en * ND + i) : -1; }
+         for (int i = 0; i < ND; i++) { gn[i] = nv ? __ldg(gmap + (int64_t)en * ND + i) : -1; }
          #pragma unroll
          for (int i = 0; i < ND; i++) { u[i] = (gn[i] >= 0) ? __ldg(x + gn[i]) : 0.0; }
       }
@@ -187,7 +193,7 @@ k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restri
                if (DIFF) { v += tb.G[qx * D + dx] * a[dy][qx]; }
             }
             if (ATOMIC) { if (g[dy * D + dx] >= 0) { red_add_f64(y + g[dy * D + dx], v); } }
-            else if (valid) { y[e * ND + dy * D + dx] = v; }
+            else if (valid) { y[(int64_t)e * ND + dy * D + dx] = v; }
          }
       }
    }
@@ -210,6 +216,7 @@ int launch_2d(cdm_op *op, const BasisTables &tb, const int32_t *gmap, const doub
    const int64_t e0 = op->range_on ? op->e_begin : 0, e1 = op->range_on ? op->e_end : sp->ne;
    const int64_t n = e1 - e0;
    if (n <= 0) { return CDM_OK; }
+   if (n > 2000000000LL) { return 1; }                        // 32-bit element indices at orders >= 3: the caller falls back
    int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
    const int64_t need = (n + 32 * NW - 1) / (32 * NW);
    if (grid > need) { grid = need; }

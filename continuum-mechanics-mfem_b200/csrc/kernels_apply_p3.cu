@@ -34,6 +34,9 @@ struct WarpTables
 // (red.add) by neighbouring elements
 using cdmk::smem_u32;
 using cdmk::mbar_init;
+#ifndef CDM_P3_IDX32
+#define CDM_P3_IDX32 1
+#endif
 #ifndef CDM_P3_WAITALL
 #define CDM_P3_WAITALL 1
 #endif
@@ -403,13 +406,19 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
    }
    __syncwarp();
-   const int64_t gw = (int64_t)blockIdx.x * NW + wib, tw = (int64_t)gridDim.x * NW;
+   // element indices: 64-bit by default; 32-bit as a measured variant (CDM_P3_IDX32; the launcher then refuses > 2e9 elements)
+#if CDM_P3_IDX32
+   using eidx = int;
+#else
+   using eidx = int64_t;
+#endif
+   const eidx gw = (eidx)blockIdx.x * NW + wib, tw = (eidx)gridDim.x * NW, nel = (eidx)ne;
    const uint32_t slab_bytes = (uint32_t)slab * 8u;
    // gather pipeline: indices are fetched two elements ahead, values one element ahead, so that no
    // load is consumed in the element that issued it
    int4 pg = make_int4(-1, -1, -1, -1), pgn = make_int4(-1, -1, -1, -1);
    double px[D] = {0.0, 0.0, 0.0, 0.0};
-   if (gw < ne)
+   if (gw < nel)
    {
       if (lane == 0)
       {
@@ -417,23 +426,23 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
          for (int q = 0; q < Q; q++)
          {
             mbar_expect_tx(&bars[q], slab_bytes);
-            bulk_g2s(ring + q * slab, Dg + (gw * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+            bulk_g2s(ring + q * slab, Dg + ((int64_t)gw * Q + q) * slab, slab_bytes, &bars[q]);
          }
       }
       if (l1)
       {
-         pg = __ldg(reinterpret_cast<const int4 *>(gmap + gw * ND) + lane);
-         if (gw + tw < ne) { pgn = __ldg(reinterpret_cast<const int4 *>(gmap + (gw + tw) * ND) + lane); }
+         pg = __ldg(reinterpret_cast<const int4 *>(gmap + (int64_t)gw * ND) + lane);
+         if (gw + tw < nel) { pgn = __ldg(reinterpret_cast<const int4 *>(gmap + (int64_t)(gw + tw) * ND) + lane); }
          px[0] = (pg.x >= 0) ? __ldg(x + pg.x) : 0.0; px[1] = (pg.y >= 0) ? __ldg(x + pg.y) : 0.0;
          px[2] = (pg.z >= 0) ? __ldg(x + pg.z) : 0.0; px[3] = (pg.w >= 0) ? __ldg(x + pg.w) : 0.0;
       }
    }
 
    uint32_t parity = 0;
-   for (int64_t e = gw; e < ne; e += tw, parity ^= 1u)
+   for (eidx e = gw; e < nel; e += tw, parity ^= 1u)
    {
-      const int64_t en = e + tw;
-      const bool more = en < ne;
+      const eidx en = e + tw;
+      const bool more = en < nel;
       const int4 g = pg;
       // ---- F1 (L1 lanes): x contraction of the own x-line with B and G
       if (l1)
@@ -451,7 +460,7 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
       if (more && l1)
       {
          pg = pgn;                                           // indices of element en, loaded one element ago
-         if (en + tw < ne) { pgn = __ldg(reinterpret_cast<const int4 *>(gmap + (en + tw) * ND) + lane); }
+         if (en + tw < nel) { pgn = __ldg(reinterpret_cast<const int4 *>(gmap + (int64_t)(en + tw) * ND) + lane); }
          px[0] = (pg.x >= 0) ? __ldg(x + pg.x) : 0.0; px[1] = (pg.y >= 0) ? __ldg(x + pg.y) : 0.0;
          px[2] = (pg.z >= 0) ? __ldg(x + pg.z) : 0.0; px[3] = (pg.w >= 0) ? __ldg(x + pg.w) : 0.0;
       }
@@ -539,7 +548,7 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
          for (int q = 0; q < Q; q++)
          {
             mbar_expect_tx(&bars[q], slab_bytes);
-            bulk_g2s(ring + q * slab, Dg + (en * Q + q) * (int64_t)slab, slab_bytes, &bars[q]);
+            bulk_g2s(ring + q * slab, Dg + ((int64_t)en * Q + q) * slab, slab_bytes, &bars[q]);
          }
       }
       // ---- B1 (L3 lanes): transposed z contraction in registers
@@ -615,7 +624,7 @@ k_apply3d_warp_bg(const WarpTablesBG tb, const int64_t ne, const int32_t *__rest
          }
          else
          {
-            double2 *dst = reinterpret_cast<double2 *>(y + e * ND + D * lane);
+            double2 *dst = reinterpret_cast<double2 *>(y + (int64_t)e * ND + D * lane);
             dst[0] = make_double2(yv[0], yv[1]);
             dst[1] = make_double2(yv[2], yv[3]);
          }
@@ -638,6 +647,9 @@ int launch_bg(cdm_op *op, const WarpTablesBG &tb, const int32_t *gmap, const dou
    const int64_t e0 = op->range_on ? op->e_begin : 0, e1 = op->range_on ? op->e_end : sp->ne;
    const int64_t n = e1 - e0;
    if (n <= 0) { return CDM_OK; }
+#if CDM_P3_IDX32
+   if (n > 2000000000LL) { return 1; }
+#endif
    int64_t grid = (int64_t)ctx->sm_count * blocks_per_sm;
    const int64_t need = (n + NW - 1) / NW;
    if (grid > need) { grid = need; }
