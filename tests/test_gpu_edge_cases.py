@@ -23,7 +23,7 @@ def up(torch, a):
     return t
 
 
-@pytest.mark.parametrize("dim,p", [(2, 1), (2, 3), (3, 1), (3, 3), (3, 5)])
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 3), (2, 4), (3, 1), (3, 2), (3, 3), (3, 4), (3, 5), (3, 6)])
 def test_single_element_mesh(env, orc, dim, p):
     torch, ctx = env
     P = orc.Problem(dim, p, 1, perturb=0.0)

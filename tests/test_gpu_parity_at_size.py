@@ -176,7 +176,10 @@ def test_midsize_every_kernel_matches_oracle(torch, ctx, orc, p):
             assert rel(D.down(yd), yc_ref) < APPLY_TOL, (kernel, scatter)
 
 
-@pytest.mark.parametrize("p,n", [(1, [9, 8, 7]), (2, [7, 6, 7]), (3, [6, 7, 5]), (4, [5, 4, 5]), (5, [4, 5, 3]), (6, [3, 4, 3])])
+# (4, [5, 5, 5]): an odd element count, so that the last round of the order-4 kernel (three warps for two elements) holds a
+# block with one valid and one idle element; (5, [5, 3, 3]) likewise for the packed order-5 variant
+@pytest.mark.parametrize("p,n", [(1, [9, 8, 7]), (2, [7, 6, 7]), (3, [6, 7, 5]), (4, [5, 4, 5]), (4, [5, 5, 5]), (5, [4, 5, 3]),
+                                 (5, [5, 3, 3]), (6, [3, 4, 3])])
 @pytest.mark.parametrize("which", ["full", "mass", "diff+mass", "diff"])
 def test_capped_grid_long_loops(torch, ctx, orc, p, n, which):
     """persistent grid capped to 3 blocks: every warp / group walks through tens of elements (including a
