@@ -37,6 +37,8 @@ k_apply2d_thread(const BasisTables tb, const int64_t ne, const int32_t *__restri
    // ... and the indices two chunks ahead, so that the value loads never wait for them: measured +2.5 % at p = 1, +3 % at
    // p = 3, -1 % at p = 2 (profiles/r02_sweep2d_variants.md)
    constexpr bool PF2 = P == 1 || P == 3;
+   // (order 4, tried: not keeping the 25 dof indices across the middle stage but re-reading them before the scatter halves the
+   // spills and costs 14 points: 50.5 -> 36.9 %)
    extern __shared__ __align__(128) unsigned char smraw[];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    double *wbuf = reinterpret_cast<double *>(smraw) + (size_t)wib * NBUF * 32 * sstride;
