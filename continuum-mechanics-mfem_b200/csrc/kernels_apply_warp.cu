@@ -33,6 +33,9 @@ __device__ __forceinline__ void g_red_add(double *addr, double v) { cdmk::red_ad
 #ifndef CDM_G4_TRIO
 #define CDM_G4_TRIO 1
 #endif
+#ifndef CDM_G5_IDX32
+#define CDM_G5_IDX32 0
+#endif
 #ifndef CDM_G5_PENTA
 #define CDM_G5_PENTA 0               // measured: 79.1 % against 81.5 % for two warps per element (10 instead of 12 warps per SM)
 #endif
@@ -338,7 +341,7 @@ k_apply3d_group(const GroupTables tb, const int64_t ne, const int32_t *__restric
    // Element indices: 32-bit where measured faster (the launcher refuses more than 2e9 elements).  In the packed layouts
    // gg, e, en are per-thread values; as 64-bit integers they cost 7-29 registers.  p=4 with red.add output: 92.4 -> 95.3 %
    // of the HBM roofline; p=6 loses 6 points and p=4 with E-vector output 18 % (a different ptxas schedule), p=5 0.8.
-   constexpr bool IDX32 = (C::TRIO && ATOMIC) || C::PENTA;
+   constexpr bool IDX32 = (C::TRIO && ATOMIC) || C::PENTA || (P == 5 && CDM_G5_IDX32);
    using eidx = typename std::conditional<IDX32, int, int64_t>::type;
    const eidx ngroups = (eidx)gridDim.x * C::GPB;
    const eidx gg = (eidx)blockIdx.x * C::GPB + gsafe;

@@ -205,6 +205,33 @@ def test_capped_grid_long_loops(torch, ctx, orc, p, n, which):
             assert rel(D.down(yd), yc_ref) < APPLY_TOL, (kernel, scatter)
 
 
+@pytest.mark.parametrize("p", [3, 4, 5, 6])
+def test_repeated_applies_are_stable(torch, ctx, orc, p):
+    """The exchange stages of the high-order kernels reuse shared memory in place (orders 5, 6) and share warps between
+    elements (order 4): a missing barrier would show up as run-to-run differences.  30 applies of the same input: with
+    E-vector output (no atomics) every run must be bit-identical, with red.add output every run must match the oracle
+    (compute-sanitizer is not available on the GPU pool, so the check is done by repetition)."""
+    P, mesh, sp = make(ctx, orc, 3, p, MID[p], perturb=0.12)
+    D = Dev(torch, ctx)
+    x = np.random.default_rng(300 + p).uniform(-1, 1, P.ndof)
+    y_ref = P.pa_apply_fast(x).copy()
+    op = make_op(P, sp)
+    xd, yd = D.up(x), D.zeros(P.ndof)
+    op.set_option("scatter", 0)
+    op.MultUnconstrained(xd, yd)
+    first = D.down(yd).copy()
+    assert rel(first, y_ref) < APPLY_TOL
+    for _ in range(30):
+        op.MultUnconstrained(xd, yd)
+        assert np.array_equal(D.down(yd), first)
+    op.set_option("scatter", 1)
+    worst = 0.0
+    for _ in range(30):
+        op.MultUnconstrained(xd, yd)
+        worst = max(worst, rel(D.down(yd), y_ref))
+    assert worst < APPLY_TOL, worst
+
+
 @pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6])
 def test_midsize_kronecker_golden_every_order(torch, ctx, p):
     """default kernels against the oracle-independent Kronecker golden on graded rectilinear meshes"""
