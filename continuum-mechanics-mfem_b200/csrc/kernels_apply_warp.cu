@@ -2,15 +2,26 @@
 // generalised to every order p = 1..6 in 3D (kernel option 4).
 //
 // One *group* of T = Q1D^2 threads owns one element at a time:
-//   p = 1 : T =  9, three groups per warp        p = 4 : T = 36, two warps per group
+//   p = 1 : T =  9, three groups per warp        p = 4 : T = 36, three warps for two elements (32 + 32 + 2 x 4 lanes)
 //   p = 2 : T = 16, two groups per warp          p = 5 : T = 49, two warps per group
 //   p = 3 : T = 25, one group per warp           p = 6 : T = 64, two warps per group
-// Sub-warp groups synchronise with __syncwarp, two-warp groups with a named barrier
-// (bar.sync id, 64).  Everything else is the design documented in kernels_apply_p3.cu:
-// quadrature data streamed by cp.async.bulk into a per-group ring of Q1D z-slabs guarded by
-// mbarriers, x / y contractions through two conflict-aware exchange buffers with constant-bank
-// coefficients, z contraction + point-wise D + transposed z contraction in registers,
-// two-level gather prefetch, fp64 red.add scatter (or E-vector stores).
+// Sub-warp groups synchronise with __syncwarp, two-warp groups and the packed order-4 blocks with the block barrier.
+// Everything else is the design documented in kernels_apply_p3.cu: quadrature data streamed by cp.async.bulk into a
+// per-group ring of Q1D z-slabs guarded by mbarriers, x / y contractions through conflict-aware exchange buffers with
+// constant-bank coefficients (orders 5, 6: in place, see GroupCfg), z contraction + point-wise D + transposed z
+// contraction in registers, two-level gather prefetch, fp64 red.add scatter (or E-vector stores).
+//
+// Compile-time variants (-D...; defaults are the measured best, profiles/r02_sweep_config4.md):
+//   CDM_G4_TRIO 1        order 4: three warps for two elements (0: two warps per element, 80.7 instead of 95.3 %)
+//   CDM_G5_INPLACE 1, CDM_G6_INPLACE 1   y contractions in place (0: separate P buffers, one resident group fewer)
+//   CDM_G_LANEMAP 1      padded half-warp lane maps of the x / y roles at orders 5, 6
+//   CDM_G_WAITALL 1, CDM_G5_WAITALL 0    point-wise stage waits for all slab barriers first
+//   CDM_G_ALIAS 1        (only without INPLACE) P and R buffers share a region, two more barriers per element
+//   CDM_G5_PENTA 0       order 5: five warps for three elements (79.1 instead of 81.5 %)
+//   CDM_G4_FUSEZ / G5 / G6 0   z contraction, point-wise D, transposed z contraction fused per level (slower; always on for
+//                              order 4 with E-vector output, where the separate stages spill)
+//   CDM_G_BALANCED 0     order 4 without TRIO: both warps run the x / y stages (neutral)
+//   CDM_G5_IDX32 0       32-bit element indices at order 5 (order 4 with red.add output always uses them)
 #include "cdm_internal.hpp"
 #include "kernels_common.cuh"
 #include <type_traits>
