@@ -28,7 +28,11 @@ struct NcclApi
    nccl_result (*GroupEnd)() = nullptr;
    const char *(*GetErrorString)(nccl_result) = nullptr;
    nccl_result (*CommSplit)(ncclComm *, int, int, ncclComm **, void *) = nullptr;   // optional (NCCL >= 2.18)
+   nccl_result (*GetVersion)(int *) = nullptr;                                      // optional (NCCL >= 2.3.4)
+   int version = 0;
 };
+// The prototypes above and these enumerators are the NCCL 2.x ABI (nccl.h: ncclFloat64 = 8, ncclUint8 = 1, ncclSum = 0,
+// ncclUniqueId = 128 bytes); api() refuses a library whose ncclGetVersion reports another major version.
 const int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_UINT8 = 1;
 
 NcclApi *api()
@@ -46,6 +50,13 @@ NcclApi *api()
    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
    *(void **)(&a.CommSplit) = dlsym(a.h, "ncclCommSplit");
+   *(void **)(&a.GetVersion) = dlsym(a.h, "ncclGetVersion");
+   if (a.GetVersion && a.GetVersion(&a.version) == 0)
+   {
+      // version code: major * 10000 + minor * 100 + patch since 2.9, major * 1000 + minor * 100 + patch before
+      const int major = (a.version >= 10000) ? a.version / 10000 : a.version / 1000;
+      if (major != 2) { a.h = nullptr; return nullptr; }
+   }
    return &a;
 }
 }  // namespace
