@@ -6,6 +6,10 @@
 // partially assembled BilinearForm builds from it (MFEM fem/restriction.cpp,
 // upstream, not vendored).  Numbering conventions: SURVEY.md Appendix C.1-C.3.
 #include "cdm_internal.hpp"
+#include <chrono>
+#include <thread>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -142,72 +146,74 @@ void cdm_host_basis(int p, int q1d, double *B, double *G, double *qw, double *no
 // --------------------------------------------------------------- numbering
 namespace
 {
+// phase times of the host-side setup on stderr when CDM_CFG_DEBUG is set
+struct PhaseTimer
+{
+   bool on; std::chrono::steady_clock::time_point t0;
+   PhaseTimer() : on(getenv("CDM_CFG_DEBUG") != nullptr), t0(std::chrono::steady_clock::now()) {}
+   void lap(const char *what)
+   {
+      if (!on) { return; }
+      const auto t1 = std::chrono::steady_clock::now();
+      fprintf(stderr, "[cdm] host setup: %s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+      t0 = t1;
+   }
+};
+
 const int HEX_E[12][2] = {{0,1},{1,2},{3,2},{0,3},{4,5},{5,6},{7,6},{4,7},{0,4},{1,5},{2,6},{3,7}};
 const int HEX_F[6][4] = {{3,2,1,0},{0,1,5,4},{1,2,6,5},{2,3,7,6},{3,0,4,7},{4,5,6,7}};
 const int QUAD_E[4][2] = {{0,1},{1,2},{2,3},{3,0}};
 
-inline uint64_t mix(uint64_t k)
-{
-   k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
-   return k;
-}
-
 // flat open-addressing map: 64-bit key -> id in first-insertion order
+// Edge and face tables: first-insertion ids, rows keyed by the smallest vertex id of the entity, the entries of a row chained
+// through a node pool in insertion order (the shape of MFEM's DSTable / STable3D).  A mesh whose vertices are numbered with
+// spatial locality touches rows and nodes it created a few elements ago, so the build runs out of cache: open-addressing hash
+// tables (rounds 1-2) scattered 66 M probes of a 30 M-dof mesh over 1 GB and took 8 of the 11.5 s of the space setup.
 struct EdgeMap
 {
-   std::vector<uint64_t> keys; std::vector<int32_t> ids; uint64_t mask = 0; int32_t count = 0;
-   explicit EdgeMap(size_t expect)
-   {
-      size_t cap = 64; while (cap < 2 * expect + 16) { cap <<= 1; }
-      keys.assign(cap, ~0ULL); ids.assign(cap, -1); mask = cap - 1;
-   }
+   struct Node { int32_t hi, id, next; };
+   std::vector<int32_t> head; std::vector<Node> pool; int32_t count = 0;
+   EdgeMap(size_t nv, size_t expect) { head.assign(nv, -1); pool.reserve(expect); }
    int32_t get(int32_t a, int32_t b, bool insert)
    {
-      const uint64_t lo = (uint32_t)std::min(a, b), hi = (uint32_t)std::max(a, b);
-      const uint64_t key = (lo << 32) | hi;
-      for (uint64_t s = mix(key) & mask;; s = (s + 1) & mask)
-      {
-         if (keys[s] == key) { return ids[s]; }
-         if (keys[s] == ~0ULL)
-         {
-            if (!insert) { return -1; }
-            keys[s] = key; ids[s] = count;
-            return count++;
-         }
-      }
+      const int32_t lo = std::min(a, b), hi = std::max(a, b);
+      for (int32_t n = head[lo]; n >= 0; n = pool[n].next) { if (pool[n].hi == hi) { return pool[n].id; } }
+      if (!insert) { return -1; }
+      pool.push_back(Node{hi, count, head[lo]});
+      head[lo] = (int32_t)pool.size() - 1;
+      return count++;
    }
 };
 
 // quad faces keyed by their three smallest vertex ids (unique in a conforming mesh)
 struct FaceMap
 {
-   struct Slot { int32_t a, b, c, id; };
-   std::vector<Slot> slots; uint64_t mask = 0; int32_t count = 0;
+   struct Node { int32_t b, c, id, next; };
+   std::vector<int32_t> head; std::vector<Node> pool; int32_t count = 0;
    std::vector<int32_t> base;    // 4 vertices per face, as seen by the creating element
-   explicit FaceMap(size_t expect)
+   FaceMap(size_t nv, size_t expect) { head.assign(nv, -1); pool.reserve(expect); base.reserve(4 * expect); }
+   // the three smallest of four vertex ids, ascending (five compare-exchanges)
+   static void smallest3(const int32_t *v, int32_t *s4)
    {
-      size_t cap = 64; while (cap < 2 * expect + 16) { cap <<= 1; }
-      slots.assign(cap, Slot{-1, -1, -1, -1}); mask = cap - 1;
-      base.reserve(4 * expect);
+      int32_t a = v[0], b = v[1], c = v[2], d = v[3], t;
+#define CDM_CSWAP(x, y) if (x > y) { t = x; x = y; y = t; }
+      CDM_CSWAP(a, b) CDM_CSWAP(c, d) CDM_CSWAP(a, c) CDM_CSWAP(b, d) CDM_CSWAP(b, c)
+#undef CDM_CSWAP
+      s4[0] = a; s4[1] = b; s4[2] = c; s4[3] = d;
    }
    int32_t get(const int32_t *v, bool insert)
    {
-      int32_t s4[4] = {v[0], v[1], v[2], v[3]};
-      std::sort(s4, s4 + 4);
-      const uint64_t h = mix(((uint64_t)(uint32_t)s4[0] << 32 | (uint32_t)s4[1]) * 0x9E3779B97F4A7C15ULL
-                             ^ (uint64_t)(uint32_t)s4[2]);
-      for (uint64_t s = h & mask;; s = (s + 1) & mask)
+      int32_t s4[4];
+      smallest3(v, s4);
+      for (int32_t n = head[s4[0]]; n >= 0; n = pool[n].next)
       {
-         Slot &t = slots[s];
-         if (t.id >= 0 && t.a == s4[0] && t.b == s4[1] && t.c == s4[2]) { return t.id; }
-         if (t.id < 0)
-         {
-            if (!insert) { return -1; }
-            t = Slot{s4[0], s4[1], s4[2], count};
-            base.insert(base.end(), v, v + 4);
-            return count++;
-         }
+         if (pool[n].b == s4[1] && pool[n].c == s4[2]) { return pool[n].id; }
       }
+      if (!insert) { return -1; }
+      pool.push_back(Node{s4[1], s4[2], count, head[s4[0]]});
+      head[s4[0]] = (int32_t)pool.size() - 1;
+      base.insert(base.end(), v, v + 4);
+      return count++;
    }
 };
 
@@ -288,9 +294,10 @@ int64_t cdm_host_h1_numbering(const cdm_mesh &m, int p, std::vector<int32_t> &el
    const int nd = (dim == 2) ? p1 * p1 : p1 * p1 * p1;
    const int nvpe = (dim == 2) ? 4 : 8, nepe = (dim == 2) ? 4 : 12;
    const bool need_tabs = pm1 > 0;
-   EdgeMap em(need_tabs ? (size_t)(dim == 2 ? 2 : 3) * m.ne + m.nv : 0);
-   FaceMap fm((need_tabs && dim == 3) ? (size_t)3 * m.ne + m.nbe : 0);
+   EdgeMap em(need_tabs ? (size_t)m.nv : 0, need_tabs ? (size_t)(dim == 2 ? 2 : 3) * m.ne + m.nv : 0);
+   FaceMap fm((need_tabs && dim == 3) ? (size_t)m.nv : 0, (need_tabs && dim == 3) ? (size_t)3 * m.ne + m.nbe : 0);
    std::vector<int32_t> e_edge, e_face;        // per element entity ids (first pass)
+   PhaseTimer tm_;
    if (need_tabs)
    {
       e_edge.resize((size_t)m.ne * nepe);
@@ -303,14 +310,20 @@ int64_t cdm_host_h1_numbering(const cdm_mesh &m, int p, std::vector<int32_t> &el
             const int *le = (dim == 2) ? QUAD_E[k] : HEX_E[k];
             e_edge[(size_t)e * nepe + k] = em.get(v[le[0]], v[le[1]], true);
          }
-         if (dim == 3)
+      }
+      tm_.lap("edge table");
+      if (dim == 3)
+         for (int64_t e = 0; e < m.ne; e++)
+         {
+            const int32_t *v = &m.ev[(size_t)e * nvpe];
             for (int k = 0; k < 6; k++)
             {
                const int32_t fv[4] = {v[HEX_F[k][0]], v[HEX_F[k][1]], v[HEX_F[k][2]], v[HEX_F[k][3]]};
                e_face[(size_t)e * 6 + k] = fm.get(fv, true);
             }
-      }
+         }
    }
+   tm_.lap("face table");
    const int64_t nedges = em.count, nfaces = fm.count;
    const int64_t edge0 = m.nv, face0 = edge0 + nedges * pm1;
    const int64_t int0 = face0 + nfaces * (int64_t)pm1 * pm1;
@@ -321,38 +334,53 @@ int64_t cdm_host_h1_numbering(const cdm_mesh &m, int p, std::vector<int32_t> &el
 
    std::vector<int> l2n;
    lex_to_native(dim, p, l2n);
-   std::vector<int32_t> native(nd);
    elem_dof.resize((size_t)m.ne * nd);
-   for (int64_t e = 0; e < m.ne; e++)
+   // the elements are independent here: slices of the element range on the host threads
+   auto number_range = [&](int64_t eb, int64_t ee)
    {
-      const int32_t *v = &m.ev[(size_t)e * nvpe];
-      int o = 0;
-      for (int k = 0; k < nvpe; k++) { native[o++] = v[k]; }
-      if (need_tabs)
+      std::vector<int32_t> native(nd);
+      for (int64_t e = eb; e < ee; e++)
       {
-         for (int k = 0; k < nepe; k++)
+         const int32_t *v = &m.ev[(size_t)e * nvpe];
+         int o = 0;
+         for (int k = 0; k < nvpe; k++) { native[o++] = v[k]; }
+         if (need_tabs)
          {
-            const int *le = (dim == 2) ? QUAD_E[k] : HEX_E[k];
-            const bool fwd = v[le[0]] < v[le[1]];
-            const int64_t b = edge0 + (int64_t)e_edge[(size_t)e * nepe + k] * pm1;
-            for (int i = 0; i < pm1; i++) { native[o++] = (int32_t)(b + (fwd ? i : pm1 - 1 - i)); }
-         }
-         if (dim == 3)
-            for (int k = 0; k < 6; k++)
+            for (int k = 0; k < nepe; k++)
             {
-               const int32_t fv[4] = {v[HEX_F[k][0]], v[HEX_F[k][1]], v[HEX_F[k][2]], v[HEX_F[k][3]]};
-               const int32_t id = e_face[(size_t)e * 6 + k];
-               const int ori = quad_ori(&fm.base[(size_t)4 * id], fv);
-               const int64_t b = face0 + (int64_t)id * pm1 * pm1;
-               for (int j = 0; j < pm1; j++)
-                  for (int i = 0; i < pm1; i++) { native[o++] = (int32_t)(b + quad_perm(ori, pm1, i, j)); }
+               const int *le = (dim == 2) ? QUAD_E[k] : HEX_E[k];
+               const bool fwd = v[le[0]] < v[le[1]];
+               const int64_t b = edge0 + (int64_t)e_edge[(size_t)e * nepe + k] * pm1;
+               for (int i = 0; i < pm1; i++) { native[o++] = (int32_t)(b + (fwd ? i : pm1 - 1 - i)); }
             }
-         for (int i = 0; i < nint; i++) { native[o++] = (int32_t)(int0 + e * nint + i); }
+            if (dim == 3)
+               for (int k = 0; k < 6; k++)
+               {
+                  const int32_t fv[4] = {v[HEX_F[k][0]], v[HEX_F[k][1]], v[HEX_F[k][2]], v[HEX_F[k][3]]};
+                  const int32_t id = e_face[(size_t)e * 6 + k];
+                  const int ori = quad_ori(&fm.base[(size_t)4 * id], fv);
+                  const int64_t b = face0 + (int64_t)id * pm1 * pm1;
+                  for (int j = 0; j < pm1; j++)
+                     for (int i = 0; i < pm1; i++) { native[o++] = (int32_t)(b + quad_perm(ori, pm1, i, j)); }
+               }
+            for (int i = 0; i < nint; i++) { native[o++] = (int32_t)(int0 + e * nint + i); }
+         }
+         int32_t *out = &elem_dof[(size_t)e * nd];
+         for (int l = 0; l < nd; l++) { out[l] = native[l2n[l]]; }
       }
-      int32_t *out = &elem_dof[(size_t)e * nd];
-      for (int l = 0; l < nd; l++) { out[l] = native[l2n[l]]; }
+   };
+   {
+      unsigned nt = std::thread::hardware_concurrency();
+      if (nt > 16) { nt = 16; }
+      if (nt < 2 || m.ne < 65536) { number_range(0, m.ne); }
+      else
+      {
+         std::vector<std::thread> th;
+         for (unsigned t = 0; t < nt; t++) { th.emplace_back(number_range, m.ne * t / nt, m.ne * (t + 1) / nt); }
+         for (auto &x : th) { x.join(); }
+      }
    }
-
+   tm_.lap("element dofs");
    // dofs of each boundary element (closure: vertices, edges, face interior)
    const int nvpf = (dim == 2) ? 2 : 4;
    bdr_off.assign(m.nbe + 1, 0);
@@ -386,6 +414,7 @@ int64_t cdm_host_h1_numbering(const cdm_mesh &m, int p, std::vector<int32_t> &el
 void cdm_host_restriction(int64_t ne, int nd, int64_t ndof, const std::vector<int32_t> &gather,
                           std::vector<int32_t> &offsets, std::vector<int32_t> &indices)
 {
+   PhaseTimer tm_;
    const int64_t n = ne * nd;
    offsets.assign(ndof + 1, 0);
    indices.resize(n);
@@ -393,4 +422,5 @@ void cdm_host_restriction(int64_t ne, int nd, int64_t ndof, const std::vector<in
    for (int64_t g = 0; g < ndof; g++) { offsets[g + 1] += offsets[g]; }
    std::vector<int32_t> cur(offsets.begin(), offsets.end() - 1);
    for (int64_t i = 0; i < n; i++) { indices[cur[gather[i]]++] = (int32_t)i; }
+   tm_.lap("restriction transpose (offsets, indices)");
 }
