@@ -2,6 +2,7 @@
 // Every exported symbol is declared in include/cdm_b200.h together with the
 // reference interface it stands behind.
 #include "cdm_internal.hpp"
+#include <thread>
 #include "kernels_common.cuh"
 #include <algorithm>
 #include <chrono>
@@ -117,12 +118,26 @@ static int space_finish(cdm_ctx *ctx, const cdm_mesh *mesh, cdm_space *sp)
    // per-element vertex coordinates (order-1 mesh nodes)
    const int nvpe = (sp->geom == 1) ? sp->dim + 1 : ((sp->dim == 2) ? 4 : 8);
    sp->elem_x.resize((size_t)sp->ne * nvpe * sp->dim);
-   for (int64_t e = 0; e < sp->ne; e++)
+   auto fill_x = [&](int64_t eb, int64_t ee)
    {
-      const int64_t em = sp->elem_perm.empty() ? e : sp->elem_perm[e];      // element index in the mesh
-      for (int k = 0; k < nvpe; k++)
-         for (int c = 0; c < sp->dim; c++)
-            sp->elem_x[((size_t)e * nvpe + k) * sp->dim + c] = mesh->vx[(size_t)mesh->ev[(size_t)em * nvpe + k] * sp->dim + c];
+      for (int64_t e = eb; e < ee; e++)
+      {
+         const int64_t em = sp->elem_perm.empty() ? e : sp->elem_perm[e];      // element index in the mesh
+         for (int k = 0; k < nvpe; k++)
+            for (int c = 0; c < sp->dim; c++)
+               sp->elem_x[((size_t)e * nvpe + k) * sp->dim + c] = mesh->vx[(size_t)mesh->ev[(size_t)em * nvpe + k] * sp->dim + c];
+      }
+   };
+   {
+      unsigned nt = std::thread::hardware_concurrency();      // independent elements: slices on the host threads
+      if (nt > 16) { nt = 16; }
+      if (nt < 2 || sp->ne < 65536) { fill_x(0, sp->ne); }
+      else
+      {
+         std::vector<std::thread> th;
+         for (unsigned t = 0; t < nt; t++) { th.emplace_back(fill_x, sp->ne * t / nt, sp->ne * (t + 1) / nt); }
+         for (auto &x : th) { x.join(); }
+      }
    }
    cdm_host_restriction(sp->ne, sp->nd, sp->ndof, sp->gather, sp->offsets, sp->indices);
    if (ctx->device >= 0)
