@@ -79,6 +79,7 @@ SIGNATURES = {
     "cdm_mesh_cartesian_sfc": (_ci, [_vp, _ci, C.POINTER(_i64), C.POINTER(_cd), _cd, _pp]),
     "cdm_grid_sfc_ordering": (_ci, [_ci, C.POINTER(_i64), _vp]),
     "cdm_mesh_geometry": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_ci), C.POINTER(_ci)]),
+    "cdm_mesh_uniform_refine": (_ci, [_vp, _vp, _pp]),
     "cdm_mesh_sizes": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "cdm_mesh_get": (_ci, [_vp, _vp, _vp, _vp, _vp]),
     "cdm_mesh_destroy": (_ci, [_vp]),
@@ -313,6 +314,16 @@ class Mesh:
         ctx.check(lib().cdm_mesh_from_arrays(ctx.h, vx.shape[1], vx.shape[0], _ptr(vx), ev.shape[0], _ptr(ev),
                                              bv.shape[0], _ptr(bv), _ptr(battr), C.byref(h)))
         return cls(ctx, h)
+
+    def uniform_refine(self, levels=1):
+        """Mesh::UniformRefinement() `levels` times (2D triangle / quadrilateral meshes; serial_ref_levels + par_ref_levels of the
+        reference's drivers, linear_convection_diffusion_2D.cpp:295-298)"""
+        mesh = self
+        for _ in range(int(levels)):
+            h = C.c_void_p()
+            self.ctx.check(lib().cdm_mesh_uniform_refine(self.ctx.h, mesh.h, C.byref(h)))
+            mesh = Mesh(self.ctx, h)
+        return mesh
 
     def partition_box(self, parts, rank):
         pp = (C.c_int * 3)(*(list(parts) + [1] * (3 - len(parts))))

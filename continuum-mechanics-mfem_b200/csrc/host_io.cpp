@@ -170,6 +170,101 @@ int cdm_mesh_from_arrays_simplex(cdm_ctx *ctx, int dim, int64_t nv, const double
    return CDM_OK;
 }
 
+// ------------------------------------------------------------------------------------------- uniform refinement (2D)
+// Mesh::UniformRefinement() of a conforming triangle or quadrilateral mesh (linear_convection_diffusion_2D.cpp:295-298,
+// serial_ref_levels / par_ref_levels; Input/input_diffusion_mms.yaml refines Mesh/unit_square.msh once).  MFEM's
+// UniformRefinement2D_base, restated: edges are numbered in first-encounter order over the elements (local edges (0,1),
+// (1,2), (2,0) resp. (0,1), (1,2), (2,3), (3,0)); new vertices = old vertices, then one midpoint per edge (id nv + edge),
+// then one centre per quadrilateral; element i becomes its four children in the order
+//   triangle (v0, e0, e2), (e1, e2, e0), (e0, v1, e1), (e2, e1, v2)
+//   quad     (v0, e0, c, e3), (e0, v1, e1, c), (c, e1, v2, e2), (e3, c, e2, v3)
+// and a boundary segment (a, b) becomes (a, m), (m, b) with its attribute.  Averages as in Mesh::AverageVertices: the
+// coordinates are summed in the listed order and multiplied by 1/n.
+int cdm_mesh_uniform_refine(cdm_ctx *ctx, const cdm_mesh *m, cdm_mesh **refined)
+{
+   if (!m || !refined) { return cdm_fail(ctx, CDM_EINVAL, "cdm_mesh_uniform_refine: bad arguments"); }
+   if (m->dim != 2) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_mesh_uniform_refine: 2D meshes only (triangles, quadrilaterals)"); }
+   if (m->is_part) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_mesh_uniform_refine: refine before partitioning"); }
+   const int nvpe = (m->geom == 1) ? 3 : 4;
+   // edge ids in first-encounter order: rows keyed by the smaller vertex, chained entries (as in host_space.cpp)
+   struct Node { int32_t hi, id, next; };
+   std::vector<int32_t> head((size_t)m->nv, -1);
+   std::vector<Node> pool;
+   pool.reserve((size_t)m->ne * 2 + (size_t)m->nv);
+   int32_t nedges = 0;
+   auto edge = [&](int32_t a, int32_t b, bool insert) -> int32_t
+   {
+      const int32_t lo = std::min(a, b), hi = std::max(a, b);
+      for (int32_t n = head[lo]; n >= 0; n = pool[n].next) { if (pool[n].hi == hi) { return pool[n].id; } }
+      if (!insert) { return -1; }
+      pool.push_back(Node{hi, nedges, head[lo]});
+      head[lo] = (int32_t)pool.size() - 1;
+      return nedges++;
+   };
+   std::vector<int32_t> el_edge((size_t)m->ne * nvpe);
+   for (int64_t e = 0; e < m->ne; e++)
+   {
+      const int32_t *v = &m->ev[(size_t)e * nvpe];
+      for (int k = 0; k < nvpe; k++) { el_edge[(size_t)e * nvpe + k] = edge(v[k], v[(k + 1) % nvpe], true); }
+   }
+   const int64_t nquad = (m->geom == 1) ? 0 : m->ne;
+   const int64_t oedge = m->nv, oelem = oedge + nedges, nv2 = oelem + nquad;
+   if (nv2 > 2147483000LL || m->ne * 4 > 2147483000LL) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_mesh_uniform_refine: more than 2^31 vertices or elements"); }
+   cdm_mesh *r = new (std::nothrow) cdm_mesh;
+   if (!r) { return cdm_fail(ctx, CDM_ENOMEM, "out of memory"); }
+   r->geom = m->geom; r->dim = 2; r->nv = nv2; r->ne = m->ne * 4; r->nbe = m->nbe * 2;
+   r->vx.assign((size_t)nv2 * 2, 0.0);
+   std::copy(m->vx.begin(), m->vx.end(), r->vx.begin());
+   r->ev.resize((size_t)r->ne * nvpe);
+   auto average = [&](const int32_t *idx, int n, int64_t dst)
+   {
+      for (int c = 0; c < 2; c++)
+      {
+         double s = 0.0;
+         for (int k = 0; k < n; k++) { s += r->vx[(size_t)idx[k] * 2 + c]; }
+         r->vx[(size_t)dst * 2 + c] = s * (1.0 / n);
+      }
+   };
+   for (int64_t e = 0; e < m->ne; e++)
+   {
+      const int32_t *v = &m->ev[(size_t)e * nvpe];
+      int32_t em[4];
+      for (int k = 0; k < nvpe; k++)
+      {
+         em[k] = (int32_t)(oedge + el_edge[(size_t)e * nvpe + k]);
+         const int32_t pair[2] = {v[k], v[(k + 1) % nvpe]};
+         average(pair, 2, em[k]);
+      }
+      int32_t *o = &r->ev[(size_t)e * 4 * nvpe];
+      if (m->geom == 1)
+      {
+         const int32_t ch[12] = {v[0], em[0], em[2],  em[1], em[2], em[0],  em[0], v[1], em[1],  em[2], em[1], v[2]};
+         std::copy(ch, ch + 12, o);
+      }
+      else
+      {
+         const int32_t c = (int32_t)(oelem + e);
+         average(v, 4, c);
+         const int32_t ch[16] = {v[0], em[0], c, em[3],  em[0], v[1], em[1], c,  c, em[1], v[2], em[2],  em[3], c, em[2], v[3]};
+         std::copy(ch, ch + 16, o);
+      }
+   }
+   r->bv.resize((size_t)r->nbe * 2);
+   r->battr.resize((size_t)r->nbe);
+   for (int64_t b = 0; b < m->nbe; b++)
+   {
+      const int32_t a0 = m->bv[(size_t)b * 2], a1 = m->bv[(size_t)b * 2 + 1];
+      const int32_t id = edge(a0, a1, false);
+      if (id < 0) { delete r; return cdm_fail(ctx, CDM_EINVAL, "cdm_mesh_uniform_refine: boundary element is not an edge of the mesh"); }
+      const int32_t mid = (int32_t)(oedge + id);
+      r->bv[(size_t)b * 4 + 0] = a0; r->bv[(size_t)b * 4 + 1] = mid;
+      r->bv[(size_t)b * 4 + 2] = mid; r->bv[(size_t)b * 4 + 3] = a1;
+      r->battr[(size_t)b * 2] = r->battr[(size_t)b * 2 + 1] = m->battr[(size_t)b];
+   }
+   *refined = r;
+   return CDM_OK;
+}
+
 int cdm_mesh_geometry(const cdm_mesh *m, int *geom, int *verts_per_elem, int *verts_per_bdr)
 {
    if (!m) { return CDM_EINVAL; }

@@ -5,7 +5,7 @@
     python examples/convdiff_from_yaml.py Input/input_2d.yaml        (run from the directory the YAML's paths refer to)
 
 Same sequence as the app's main(): LoadParams (:62-127) -> PETSc options file (:268-282) -> Mesh(mesh_file, 1, 1) +
-UniformRefinement (:290-298, refinement of Gmsh meshes is not implemented: serial_ref_levels / par_ref_levels must be 0)
+UniformRefinement (:290-298: serial_ref_levels + par_ref_levels uniform refinements, cdm_mesh_uniform_refine)
 -> H1 space (:311-312) -> all boundary attributes essential (:319-322) -> Diffusion + Convection + Mass (:335-339) ->
 DomainLFIntegrator(f) (:341-343) -> ProjectBdrCoefficient(u_exact) (:345-347) -> FormLinearSystem (:351) -> KSP solve
 (:368-374) -> L2 errors with rules of order max(2, 2p+3) (:383-392) -> error CSV (:405-419) -> ParaView (:421-433).
@@ -49,8 +49,8 @@ def main(argv):
             raise RuntimeError("kappa must be > 0.")
         if p["n"] <= 0 or p["m"] <= 0:
             raise RuntimeError("mode_n and mode_m must be positive integers.")
-        if p["sref"] or p["pref"]:
-            raise RuntimeError("uniform refinement of Gmsh meshes is not implemented: use serial_ref_levels = par_ref_levels = 0")
+        if p["sref"] < 0 or p["pref"] < 0:
+            raise RuntimeError("serial_ref_levels and par_ref_levels must be >= 0.")
     except Exception as e:                                       # noqa: BLE001  (:255-262 -> exit code 2)
         print(e, file=sys.stderr)
         return 2
@@ -67,6 +67,7 @@ def main(argv):
         mesh = cdm.Mesh.read_gmsh(ctx, p["mesh_file"], refine=True)
         if mesh.dim != 2:
             raise RuntimeError("The mesh must be 2D.")
+        mesh = mesh.uniform_refine(p["sref"] + p["pref"])          # one rank: the serial and the parallel levels (:295-304)
         sp = cdm.H1Space(mesh, p["order"])
         print(f"Global true dofs: {sp.ndof}")
         _, _, _, battr = mesh.arrays()

@@ -87,6 +87,11 @@ int  cdm_mesh_read_gmsh(cdm_ctx *ctx, const char *path, int mark_for_refinement,
    listed along the generalised Hilbert curve; cdm_grid_sfc_ordering returns the curve itself, coords[k*dim + c]. */
 int  cdm_mesh_cartesian_sfc(cdm_ctx *ctx, int dim, const int64_t n[3], const double size[3], double perturb, cdm_mesh **mesh);
 int  cdm_grid_sfc_ordering(int dim, const int64_t n[3], int64_t *coords);
+/* Mesh::UniformRefinement() (linear_convection_diffusion_2D.cpp:295-298: serial_ref_levels / par_ref_levels) of a 2D
+   triangle or quadrilateral mesh: edge midpoints (then quadrilateral centres) appended to the vertices, four children per
+   element in MFEM's order, boundary segments halved; 3D meshes: CDM_EUNSUP.  The result is a plain mesh (no Cartesian
+   provenance: partition with a per-element rank array, not cdm_mesh_partition_box). */
+int  cdm_mesh_uniform_refine(cdm_ctx *ctx, const cdm_mesh *mesh, cdm_mesh **refined);
 /* geom: 0 tensor-product elements, 1 simplices */
 int  cdm_mesh_geometry(const cdm_mesh *mesh, int *geom, int *verts_per_elem, int *verts_per_bdr);
 int  cdm_mesh_sizes(const cdm_mesh *mesh, int *dim, int64_t *nv, int64_t *ne, int64_t *nbe);

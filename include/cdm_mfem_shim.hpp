@@ -124,6 +124,14 @@ public:
    Mesh(Mesh &&o) noexcept : ctx_(o.ctx_), h_(o.h_) { o.h_ = nullptr; }
    ~Mesh() { if (h_) { cdm_mesh_destroy(h_); } }
    int Dimension() const { int d; cdm_mesh_sizes(h_, &d, nullptr, nullptr, nullptr); return d; }
+   // mfem::Mesh::UniformRefinement() (linear_convection_diffusion_2D.cpp:295-298); 2D meshes
+   void UniformRefinement()
+   {
+      cdm_mesh *r = nullptr;
+      check(ctx_, cdm_mesh_uniform_refine(ctx_, h_, &r), "cdm_mesh_uniform_refine");
+      cdm_mesh_destroy(h_);
+      h_ = r;
+   }
    cdm_mesh *handle() const { return h_; }
    cdm_ctx *ctx() const { return ctx_; }
 private:

@@ -145,6 +145,91 @@ def test_triangle_numbering_matches_independent_restatement(ctx, mesh, p):
         assert np.array_equal(sp.essential_dofs(mk), Px.ess)
 
 
+@pytest.mark.parametrize("mesh", ["square_tri", "disk_tri", "quads", "ref_unit_square"])
+def test_uniform_refinement_matches_independent_restatement(ctx, mesh):
+    """Mesh::UniformRefinement (serial_ref_levels of the reference's drivers; Input/input_diffusion_mms.yaml refines
+    Mesh/unit_square.msh once): the C++ host code against the numpy restatement, bit-exact in every array (the midpoint
+    coordinates too: same summation order), twice in a row; counts, areas, conformity, inherited boundary attributes"""
+    from oracle import tri_oracle as T
+    if mesh == "quads":
+        m = cdm.Mesh.cartesian(ctx, 2, [5, 3], perturb=0.15)
+    elif mesh == "ref_unit_square":
+        path = os.path.join(REF, "Mesh", "unit_square.msh")
+        if not os.path.exists(path):
+            pytest.skip("reference tree not present")
+        m = cdm.Mesh.read_gmsh(ctx, path)
+    else:
+        m = cdm.Mesh.read_gmsh(ctx, os.path.join(GOLD, mesh + ".msh"))
+    arrays = m.arrays()
+    area0 = None
+    for level in range(2):
+        vx, ev, bv, ba = arrays
+        m = m.uniform_refine()
+        got = m.arrays()
+        want = T.uniform_refine_2d(vx, ev, bv, ba)
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and np.array_equal(g, w)
+        k = ev.shape[1]
+        nedges = len({tuple(sorted((int(e[j]), int(e[(j + 1) % k])))) for e in ev for j in range(k)})
+        assert m.nv == len(vx) + nedges + (len(ev) if k == 4 else 0) and m.ne == 4 * len(ev) and m.nbe == 2 * len(bv)
+        X = got[0][got[1]]
+        x, y = X[:, :, 0], X[:, :, 1]
+        area = 0.5 * np.sum(x * np.roll(y, -1, 1) - np.roll(x, -1, 1) * y, axis=1)
+        assert area.min() > 0                                     # children keep the orientation
+        if area0 is None:
+            X0 = vx[ev]
+            area0 = 0.5 * np.sum(X0[:, :, 0] * np.roll(X0[:, :, 1], -1, 1) - np.roll(X0[:, :, 0], -1, 1) * X0[:, :, 1], axis=1).sum()
+        assert abs(area.sum() - area0) < 1e-13
+        # conforming: every interior edge is shared by exactly two children, every boundary edge is a boundary element
+        cnt = {}
+        for e in got[1]:
+            for j in range(k):
+                key = tuple(sorted((int(e[j]), int(e[(j + 1) % k]))))
+                cnt[key] = cnt.get(key, 0) + 1
+        bset = {tuple(sorted((int(a), int(b)))) for a, b in got[2]}
+        assert all((c == 2) != (key in bset) for key, c in cnt.items()) and all(cnt[key] == 1 for key in bset)
+        # the space on the refined mesh numbers like the restatement (triangles) / builds (quads)
+        sp = cdm.H1Space(m, 2)
+        if k == 3:
+            P = T.TriProblem(2, *got)
+            assert sp.ndof == P.ndof and np.array_equal(sp.maps()[0], P.elem_dof)
+        else:
+            assert sp.ndof == m.nv + len(cnt) + m.ne
+        arrays = got
+
+
+def test_refined_triangle_meshes_converge_at_the_expected_rate(ctx):
+    """the steady MMS problem of linear_convection_diffusion_2D.cpp:159-215 on square_tri.msh and on its uniform refinement
+    (CPU oracle solve): the L2 error falls by ~2^(p+1) per level"""
+    import scipy.sparse.linalg as spla
+    from oracle import tri_oracle as T
+    kappa, cx, cy, s, n, mm = 0.1, 1.0, -2.0, 1.0, 1, 1
+    uex = lambda x, y: np.sin(n * np.pi * x) * np.sin(mm * np.pi * y)
+    f = lambda x, y: (kappa * (n * n + mm * mm) * np.pi ** 2 + s) * uex(x, y) \
+        + cx * n * np.pi * np.cos(n * np.pi * x) * np.sin(mm * np.pi * y) + cy * mm * np.pi * np.sin(n * np.pi * x) * np.cos(mm * np.pi * y)
+    m = cdm.Mesh.read_gmsh(ctx, os.path.join(GOLD, "square_tri.msh"))
+    for p in (1, 2):
+        errs = []
+        mesh = m
+        for level in range(2):
+            vx, ev, bv, ba = mesh.arrays()
+            P = T.TriProblem(p, vx, ev, bv, ba, kappa=kappa, vel=(cx, cy), mass=s)
+            A = P.csr().to_scipy().tocsr()
+            nq = p + 3
+            xq = P.rule_coords(nq)
+            b = P.domain_lf(f(xq[..., 0], xq[..., 1]), nq)
+            X = P.coords()
+            u = np.zeros(P.ndof)
+            u[P.ess] = uex(X[P.ess, 0], X[P.ess, 1])
+            free = np.flatnonzero(P.ess_mark == 0)
+            rhs = b - A @ u
+            u[free] = spla.spsolve(A[free][:, free].tocsc(), rhs[free])
+            errs.append(P.l2_error(u, uex(xq[..., 0], xq[..., 1]), nq))
+            mesh = mesh.uniform_refine()
+        rate = np.log2(errs[0] / errs[1])
+        assert p + 0.6 < rate < p + 1.6, (p, errs, rate)
+
+
 def test_triangle_oracle_known_answers():
     """the numpy triangle oracle itself: K 1 = 0, C 1 = 0, 1^T M 1 = area, symmetry, exactness of the nodal interpolation"""
     from oracle import tri_oracle as T
