@@ -84,6 +84,7 @@ SIGNATURES = {
     "cdm_mesh_get": (_ci, [_vp, _vp, _vp, _vp, _vp]),
     "cdm_mesh_destroy": (_ci, [_vp]),
     "cdm_mesh_partition_box": (_ci, [_vp, _vp, C.POINTER(_ci), _ci, _pp]),
+    "cdm_mesh_partition_elements": (_ci, [_vp, _vp, C.POINTER(C.c_int32), _ci, _ci, _pp]),
     "cdm_space_create_h1": (_ci, [_vp, _vp, _ci, _pp]),
     "cdm_space_create_from_table": (_ci, [_vp, _vp, _ci, _i64, _vp, _pp]),
     "cdm_space_sizes": (_ci, [_vp, C.POINTER(_ci), C.POINTER(_ci), C.POINTER(_i64), C.POINTER(_i64),
@@ -329,6 +330,16 @@ class Mesh:
         pp = (C.c_int * 3)(*(list(parts) + [1] * (3 - len(parts))))
         h = C.c_void_p()
         self.ctx.check(lib().cdm_mesh_partition_box(self.ctx.h, self.h, pp, rank, C.byref(h)))
+        return Mesh(self.ctx, h)
+
+    def partition_elements(self, elem_rank, nranks, rank):
+        """ParMesh(comm, mesh) with a per-element rank array (METIS-style): this rank's submesh of a quad / hex mesh"""
+        er = np.ascontiguousarray(elem_rank, np.int32)
+        if er.shape != (self.ne,):
+            raise ValueError("elem_rank must have one entry per element")
+        h = C.c_void_p()
+        self.ctx.check(lib().cdm_mesh_partition_elements(self.ctx.h, self.h, er.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                         int(nranks), int(rank), C.byref(h)))
         return Mesh(self.ctx, h)
 
     def arrays(self):

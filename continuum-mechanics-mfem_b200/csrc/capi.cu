@@ -227,6 +227,12 @@ static cdm_space *space_new(cdm_ctx *ctx, const cdm_mesh *mesh, int order)
 }
 
 // shared-dof plan of a box-partitioned Cartesian space + owned-first renumbering
+// one shared dof as seen from this rank: P / P^T plan (owner <-> each ghost holder) and symmetric plan (every other sharer)
+struct PShare { int64_t key; int32_t dof; int peer; bool mine; };
+struct PSymShare { int64_t key; int32_t dof; int peer; };
+static void finish_partition(cdm_space *sp, int me, const std::vector<int64_t> &key, const std::vector<int> &owner,
+                             std::vector<PShare> &shares, std::vector<PSymShare> &sym);
+
 static void build_partition(const cdm_mesh *m, cdm_space *sp)
 {
    const int dim = sp->dim, p = sp->p, d1d = sp->d1d;
@@ -254,10 +260,8 @@ static void build_partition(const cdm_mesh *m, cdm_space *sp)
    }
    const int me = m->rank;
    std::vector<int> owner(sp->ndof, me);
-   struct Share { int64_t key; int32_t dof; int peer; bool mine; };
-   std::vector<Share> shares;
-   struct SymShare { int64_t key; int32_t dof; int peer; };
-   std::vector<SymShare> sym;                 // (dof, every other rank of its sharing group)
+   std::vector<PShare> shares;
+   std::vector<PSymShare> sym;                // (dof, every other rank of its sharing group)
    for (int64_t g = 0; g < sp->ndof; g++)
    {
       const int64_t k = key[g];
@@ -289,6 +293,15 @@ static void build_partition(const cdm_mesh *m, cdm_space *sp)
       if (own == me) { for (int i = 0; i < cnt; i++) if (ranks[i] != me) { shares.push_back({k, (int32_t)g, ranks[i], true}); } }
       else { shares.push_back({k, (int32_t)g, own, false}); }
    }
+   finish_partition(sp, me, key, owner, shares, sym);
+}
+
+// The part of the plan that does not depend on how the sharing ranks were found: owned-first renumbering, boundary-first
+// element order, the P / P^T peer lists and the symmetric exchange plan (both in key order, so that the two sides of a pair
+// build the same lists without talking to each other).
+static void finish_partition(cdm_space *sp, int me, const std::vector<int64_t> &key, const std::vector<int> &owner,
+                             std::vector<PShare> &shares, std::vector<PSymShare> &sym)
+{
    // owned-first renumbering
    std::vector<int32_t> newid(sp->ndof);
    int64_t nown = 0;
@@ -302,7 +315,7 @@ static void build_partition(const cdm_mesh *m, cdm_space *sp)
    // exchange can overlap the interior elements
    {
       std::vector<uint8_t> shared(sp->ndof, 0);
-      for (const Share &s : shares) { shared[newid[s.dof]] = 1; }
+      for (const PShare &s : shares) { shared[newid[s.dof]] = 1; }
       std::vector<uint8_t> isb(sp->ne, 0);
       for (int64_t e = 0; e < sp->ne; e++)
          for (int l = 0; l < sp->nd; l++)
@@ -318,19 +331,19 @@ static void build_partition(const cdm_mesh *m, cdm_space *sp)
    }
    sp->dof_global.assign(sp->ndof, 0);
    for (int64_t g = 0; g < sp->ndof; g++) { sp->dof_global[newid[g]] = key[g]; }
-   std::sort(shares.begin(), shares.end(), [](const Share &a, const Share &b)
+   std::sort(shares.begin(), shares.end(), [](const PShare &a, const PShare &b)
    { return a.peer != b.peer ? a.peer < b.peer : a.key < b.key; });
-   for (const Share &s : shares)
+   for (const PShare &s : shares)
    {
       if (sp->peers.empty() || sp->peers.back().rank != s.peer) { sp->peers.emplace_back(); sp->peers.back().rank = s.peer; }
       (s.mine ? sp->peers.back().own_idx : sp->peers.back().ghost_idx).push_back(newid[s.dof]);
    }
    // symmetric plan: per peer the dofs shared with it in key order (both sides of a pair build the same list);
    // per shared dof the contributions in ascending rank order, the own value at this rank's position
-   std::sort(sym.begin(), sym.end(), [](const SymShare &a, const SymShare &b)
+   std::sort(sym.begin(), sym.end(), [](const PSymShare &a, const PSymShare &b)
    { return a.peer != b.peer ? a.peer < b.peer : a.key < b.key; });
    cdm_sym_plan &sy = sp->sym;
-   for (const SymShare &s : sym)
+   for (const PSymShare &s : sym)
    {
       if (sy.peers.empty() || sy.peers.back().rank != s.peer)
       { sy.peers.emplace_back(); sy.peers.back().rank = s.peer; sy.peers.back().off = (int64_t)sy.all.size(); }
@@ -364,6 +377,64 @@ static void build_partition(const cdm_mesh *m, cdm_space *sp)
    }
 }
 
+// Element-wise partition (cdm_mesh_partition_elements): the parent mesh is replicated, so every rank numbers the GLOBAL space
+// itself (same routine, same ids everywhere) and reads off, for each of its dofs, the global id (the key both sides of a pair
+// sort by) and the set of ranks whose elements contain it.  No setup communication, like the box partition.
+static int build_partition_general(const cdm_mesh *m, cdm_space *sp)
+{
+   const cdm_part_info &pi = *m->pinfo;
+   const int nd = sp->nd, me = m->rank;
+   std::vector<int32_t> gg, off, flat;
+   int64_t ndof_g;
+   {
+      cdm_mesh parent;
+      parent.geom = 0; parent.dim = pi.dim; parent.nv = pi.nv; parent.ne = pi.ne; parent.nbe = 0; parent.ev = pi.ev;
+      ndof_g = cdm_host_h1_numbering(parent, sp->p, gg, off, flat);
+   }
+   if (ndof_g < 0 || ndof_g > 2147483000LL) { return -1; }
+   std::vector<int64_t> key(sp->ndof, -1);
+   for (int64_t e = 0; e < sp->ne; e++)
+      for (int l = 0; l < nd; l++)
+      {
+         const int64_t k = gg[(size_t)m->eglobal[e] * nd + l];
+         int64_t &slot = key[sp->gather[(size_t)e * nd + l]];
+         if (slot >= 0 && slot != k) { return -1; }            // a local dof must be one global dof
+         slot = k;
+      }
+   std::vector<int32_t> g2l((size_t)ndof_g, -1);
+   for (int64_t d = 0; d < sp->ndof; d++)
+   {
+      if (key[d] < 0 || g2l[key[d]] >= 0) { return -1; }       // ... and the other way round
+      g2l[key[d]] = (int32_t)d;
+   }
+   std::vector<uint64_t> mask(sp->ndof, 0);
+   for (int64_t e = 0; e < pi.ne; e++)
+   {
+      const uint64_t bit = 1ull << pi.elem_rank[e];
+      for (int l = 0; l < nd; l++) { const int32_t d = g2l[gg[(size_t)e * nd + l]]; if (d >= 0) { mask[d] |= bit; } }
+   }
+   std::vector<int> owner(sp->ndof, me);
+   std::vector<PShare> shares;
+   std::vector<PSymShare> sym;
+   for (int64_t d = 0; d < sp->ndof; d++)
+   {
+      const uint64_t mk = mask[d];
+      if (!(mk >> me & 1ull)) { return -1; }
+      const int own = __builtin_ctzll(mk);
+      owner[d] = own;
+      if ((mk & (mk - 1)) == 0) { continue; }                  // a single rank
+      for (int r = 0; r < pi.nranks; r++)
+      {
+         if (r == me || !(mk >> r & 1ull)) { continue; }
+         sym.push_back({key[d], (int32_t)d, r});
+         if (own == me) { shares.push_back({key[d], (int32_t)d, r, true}); }
+      }
+      if (own != me) { shares.push_back({key[d], (int32_t)d, own, false}); }
+   }
+   finish_partition(sp, me, key, owner, shares, sym);
+   return 0;
+}
+
 int cdm_space_create_h1(cdm_ctx *ctx, const cdm_mesh *mesh, int order, cdm_space **space)
 {
    if (!ctx || !mesh || !space) { return cdm_fail(ctx, CDM_EINVAL, "cdm_space_create_h1: bad arguments"); }
@@ -382,7 +453,15 @@ int cdm_space_create_h1(cdm_ctx *ctx, const cdm_mesh *mesh, int order, cdm_space
    if (sp->ndof < 0) { delete sp; return cdm_fail(ctx, CDM_EINVAL, "cdm_space_create_h1: boundary element not found in mesh"); }
    if (sp->ndof > 2147483000LL) { delete sp; return cdm_fail(ctx, CDM_EUNSUP, "cdm_space_create_h1: more than 2^31 dofs on one rank"); }
    sp->ntrue = sp->ndof;
-   if (mesh->is_part && mesh->parts[0] * mesh->parts[1] * mesh->parts[2] > 1) { build_partition(mesh, sp); sp->class_off.clear(); }
+   if (mesh->is_part && mesh->pinfo)
+   {
+      if (mesh->pinfo->nranks > 1)
+      {
+         if (build_partition_general(mesh, sp)) { delete sp; return cdm_fail(ctx, CDM_EINVAL, "cdm_space_create_h1: inconsistent element-wise partition"); }
+         sp->class_off.clear();
+      }
+   }
+   else if (mesh->is_part && mesh->parts[0] * mesh->parts[1] * mesh->parts[2] > 1) { build_partition(mesh, sp); sp->class_off.clear(); }
    int rc = space_finish(ctx, mesh, sp);
    if (rc) { cdm_space_destroy(sp); return rc; }
    *space = sp;

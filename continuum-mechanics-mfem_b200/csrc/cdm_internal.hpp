@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -47,6 +48,16 @@ struct cdm_ctx
    int allreduce_mode = 1;         // 1: peer-memory all-reduce when available, 0: always ncclAllReduce
 };
 
+// what a submesh of an element-wise partition (cdm_mesh_partition_elements) remembers of its parent: enough to number the
+// global H1 space and to find, for every local dof, the ranks that share it
+struct cdm_part_info
+{
+   int dim = 0, nranks = 1;
+   int64_t nv = 0, ne = 0;
+   std::vector<int32_t> ev;          // parent element -> vertices
+   std::vector<int32_t> elem_rank;   // parent element -> rank
+};
+
 struct cdm_mesh
 {
    int geom = 0;                    // 0: tensor elements (quads / hexes), 1: simplices (triangles)
@@ -64,6 +75,8 @@ struct cdm_mesh
    int parts[3] = {1, 1, 1};
    int rank = 0;
    std::vector<int64_t> vglobal;    // local vertex -> global vertex id of the parent mesh
+   std::vector<int64_t> eglobal;    // local element -> parent element (element-wise partitions)
+   std::shared_ptr<const cdm_part_info> pinfo;   // set on submeshes produced by cdm_mesh_partition_elements
    int64_t gn[3] = {0, 0, 0};       // parent mesh element counts
    int64_t lo[3] = {0, 0, 0};       // first parent element of this box along each axis
 };

@@ -5,6 +5,8 @@
 // of BASELINE.json; numbering follows MFEM Mesh::MakeCartesian2D/3D with
 // sfc_ordering=false.
 #include "cdm_internal.hpp"
+#include <algorithm>
+#include <memory>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -239,6 +241,87 @@ int cdm_mesh_partition_box(cdm_ctx *ctx, const cdm_mesh *g, const int parts[3], 
    fill_box(*m, dim, g->n, it->second.s, it->second.perturb, lo, hi);
    m->is_part = true; m->rank = rank;
    for (int d = 0; d < 3; d++) { m->parts[d] = pp[d]; m->gn[d] = g->n[d]; m->n[d] = hi[d] - lo[d]; m->lo[d] = lo[d]; }
+   *local = m;
+   return CDM_OK;
+}
+
+// Element-wise partition of a quadrilateral / hexahedral mesh (what ParMesh(comm, mesh) does with the METIS array,
+// linear_convection_diffusion_2D.cpp:300): this rank's elements in parent order, their vertices renumbered in ascending parent
+// id (edge and face orientations are then the parent's), the parent boundary elements that are faces of local elements.
+int cdm_mesh_partition_elements(cdm_ctx *ctx, const cdm_mesh *g, const int32_t *elem_rank, int nranks, int rank, cdm_mesh **local)
+{
+   if (!g || !elem_rank || !local) { return cdm_fail(ctx, CDM_EINVAL, "cdm_mesh_partition_elements: bad arguments"); }
+   if (g->geom != 0) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_mesh_partition_elements: quadrilateral / hexahedral meshes only"); }
+   if (g->is_part) { return cdm_fail(ctx, CDM_EINVAL, "cdm_mesh_partition_elements: the mesh is already a part"); }
+   if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks)
+      return cdm_fail(ctx, CDM_EINVAL, "cdm_mesh_partition_elements: 1 <= nranks <= 64 and 0 <= rank < nranks");
+   const int dim = g->dim, nvpe = 1 << dim, nvpf = 1 << (dim - 1);
+   for (int64_t e = 0; e < g->ne; e++)
+      if (elem_rank[e] < 0 || elem_rank[e] >= nranks) { return cdm_fail(ctx, CDM_EINVAL, "cdm_mesh_partition_elements: rank id out of range"); }
+   cdm_mesh *m = new (std::nothrow) cdm_mesh;
+   if (!m) { return cdm_fail(ctx, CDM_ENOMEM, "out of memory"); }
+   m->geom = 0; m->dim = dim;
+   std::vector<int32_t> g2l((size_t)g->nv, -1);
+   for (int64_t e = 0; e < g->ne; e++)
+      if (elem_rank[e] == rank)
+      {
+         m->eglobal.push_back(e);
+         for (int k = 0; k < nvpe; k++) { g2l[g->ev[(size_t)e * nvpe + k]] = 0; }
+      }
+   if (m->eglobal.empty()) { delete m; return cdm_fail(ctx, CDM_EINVAL, "cdm_mesh_partition_elements: this rank owns no element"); }
+   for (int64_t v = 0; v < g->nv; v++)
+      if (g2l[v] == 0)
+      {
+         g2l[v] = (int32_t)m->vglobal.size();
+         m->vglobal.push_back(v);
+         for (int c = 0; c < dim; c++) { m->vx.push_back(g->vx[(size_t)v * dim + c]); }
+      }
+   m->nv = (int64_t)m->vglobal.size(); m->ne = (int64_t)m->eglobal.size();
+   m->ev.resize((size_t)m->ne * nvpe);
+   for (int64_t e = 0; e < m->ne; e++)
+      for (int k = 0; k < nvpe; k++) { m->ev[(size_t)e * nvpe + k] = g2l[g->ev[(size_t)m->eglobal[e] * nvpe + k]]; }
+   // faces of the local elements, keyed by their sorted parent vertex ids
+   static const int QE[4][2] = {{0,1},{1,2},{2,3},{3,0}};
+   static const int HF[6][4] = {{3,2,1,0},{0,1,5,4},{1,2,6,5},{2,3,7,6},{3,0,4,7},{4,5,6,7}};
+   struct FKey { int32_t v[4]; bool operator<(const FKey &o) const { return std::lexicographical_compare(v, v + 4, o.v, o.v + 4); }
+                 bool operator==(const FKey &o) const { return std::equal(v, v + 4, o.v); } };
+   auto make_key = [&](const int32_t *fv)
+   {
+      FKey k = {{-1, -1, -1, -1}};
+      for (int i = 0; i < nvpf; i++)                              // insertion sort of 2 or 4 ids
+      {
+         int j = i;
+         while (j > 0 && k.v[j - 1] > fv[i]) { k.v[j] = k.v[j - 1]; j--; }
+         k.v[j] = fv[i];
+      }
+      return k;
+   };
+   std::vector<FKey> faces;
+   faces.reserve((size_t)m->ne * (dim == 2 ? 4 : 6));
+   for (int64_t e = 0; e < m->ne; e++)
+   {
+      const int32_t *v = &g->ev[(size_t)m->eglobal[e] * nvpe];
+      for (int k = 0; k < (dim == 2 ? 4 : 6); k++)
+      {
+         int32_t fv[4];
+         for (int i = 0; i < nvpf; i++) { fv[i] = (dim == 2) ? v[QE[k][i]] : v[HF[k][i]]; }
+         faces.push_back(make_key(fv));
+      }
+   }
+   std::sort(faces.begin(), faces.end());
+   for (int64_t b = 0; b < g->nbe; b++)
+   {
+      const int32_t *bv = &g->bv[(size_t)b * nvpf];
+      if (!std::binary_search(faces.begin(), faces.end(), make_key(bv))) { continue; }
+      for (int i = 0; i < nvpf; i++) { m->bv.push_back(g2l[bv[i]]); }
+      m->battr.push_back(g->battr[(size_t)b]);
+   }
+   m->nbe = (int64_t)m->battr.size();
+   auto info = std::make_shared<cdm_part_info>();
+   info->dim = dim; info->nranks = nranks; info->nv = g->nv; info->ne = g->ne;
+   info->ev = g->ev; info->elem_rank.assign(elem_rank, elem_rank + g->ne);
+   m->pinfo = info;
+   m->is_part = true; m->rank = rank;
    *local = m;
    return CDM_OK;
 }

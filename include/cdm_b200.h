@@ -103,6 +103,12 @@ int  cdm_mesh_destroy(cdm_mesh *mesh);
    Shared-dof bookkeeping happens in cdm_space_create_h1 on the returned mesh. */
 int  cdm_mesh_partition_box(cdm_ctx *ctx, const cdm_mesh *global, const int parts[3], int rank,
                             cdm_mesh **local);
+/* ParMesh(comm, mesh) with a per-element rank array (what METIS hands MFEM; linear_convection_diffusion_2D.cpp:300), for
+   quadrilateral / hexahedral meshes that are not Cartesian boxes (Gmsh input, refined meshes): every rank holds the parent
+   mesh and the same array elem_rank[parent elements] (values 0 .. nranks-1, nranks <= 64) and gets its submesh; a space
+   created on it carries the same shared-dof plans as a box part (owner = lowest rank of the sharing group). */
+int  cdm_mesh_partition_elements(cdm_ctx *ctx, const cdm_mesh *global, const int32_t *elem_rank, int nranks, int rank,
+                                 cdm_mesh **local);
 
 /* ------------------------------------------------------------------ space */
 /* H1_FECollection(order,dim) + (Par)FiniteElementSpace

@@ -48,6 +48,9 @@ def main():
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--mesh", type=int, nargs=3, default=[6, 5, 4])
     ap.add_argument("--p2p", action="store_true", help="also check the peer-memory P / P^T exchange (option halo=1)")
+    ap.add_argument("--partition", default="box", choices=["box", "checker", "random", "slabs"],
+                    help="box: cdm_mesh_partition_box; the others: cdm_mesh_partition_elements with a per-element rank array "
+                    "(checker: (i+j+k) mod ranks, every element face is a partition boundary; random: seeded; slabs: z-slabs)")
     ap.add_argument("--halo", type=int, default=2, help="shared-dof protocol of the main checks: 2 symmetric peer-memory (default), 0 NCCL")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -83,11 +86,28 @@ def main():
 
     # ---- this rank's part
     gm = cdm.Mesh.cartesian(ctx, 3, args.mesh, perturb=0.1)
-    lm = gm.partition_box(parts, rank)
+    if args.partition == "box":
+        lm = gm.partition_box(parts, rank)
+    else:
+        # METIS-style input: one rank id per element of the replicated parent mesh (ParMesh(comm, mesh), :300)
+        e = np.arange(P.ne)
+        n0, n1 = args.mesh[0], args.mesh[1]
+        ei, ej, ek = e % n0, (e // n0) % n1, e // (n0 * n1)
+        if args.partition == "checker":
+            er = (ei + ej + ek) % world
+        elif args.partition == "slabs":
+            er = np.minimum(ek * world // args.mesh[2], world - 1)
+        else:
+            er = np.random.default_rng(7).integers(0, world, P.ne)
+            er[:world] = np.arange(world)                         # every rank owns something
+        lm = gm.partition_elements(er, world, rank)
+        assert lm.ne == int((er == rank).sum())
     sp = cdm.H1Space(lm, p)
     keys = sp.dof_global()
     nt = sp.ntrue
-    mine = inv[keys]                                             # local dof -> global oracle dof
+    # box parts key their dofs by lattice position; element-wise parts by the global dof id of the parent space, which is the
+    # oracle's own numbering (bit-exact, tests/test_host_abi.py)
+    mine = inv[keys] if args.partition == "box" else keys        # local dof -> global oracle dof
     assert np.abs(sp.dof_coords() - P.coords()[mine]).max() < 1e-13
     tot = torch.tensor([nt], dtype=torch.int64, device="cuda" if gpu else "cpu")
     dist.all_reduce(tot)

@@ -34,6 +34,17 @@ def test_partitioned_apply_gloo(nproc, order, mesh):
     assert out.count("host-emulated symmetric exchange") == nproc
 
 
+@pytest.mark.parametrize("nproc,order,mesh,kind", [(2, 3, (5, 4, 3), "checker"), (4, 2, (6, 5, 4), "random"), (3, 1, (4, 4, 6), "slabs"),
+                                                   (8, 2, (4, 4, 4), "checker")])
+def test_elementwise_partition_gloo(nproc, order, mesh, kind):
+    """cdm_mesh_partition_elements (a per-element rank array as METIS would give): the plans of the space -- owners, P / P^T
+    peer lists, symmetric exchange -- reproduce the un-partitioned oracle apply on every rank; "checker" makes every element face
+    a partition boundary (dofs shared by up to 8 ranks), "random" gives irregular sharing groups"""
+    out = _run(nproc, "cpu", order, n=mesh, extra=("--partition", kind))
+    assert out.count("host-emulated partitioned apply") == nproc
+    assert out.count("host-emulated symmetric exchange") == nproc
+
+
 @pytest.mark.gpu
 def test_partitioned_apply_and_gmres_nccl():
     import torch
