@@ -317,7 +317,7 @@ class Mesh:
         return cls(ctx, h)
 
     def uniform_refine(self, levels=1):
-        """Mesh::UniformRefinement() `levels` times (2D triangle / quadrilateral meshes; serial_ref_levels + par_ref_levels of the
+        """Mesh::UniformRefinement() `levels` times (triangles, quadrilaterals, hexahedra; serial_ref_levels + par_ref_levels of the
         reference's drivers, linear_convection_diffusion_2D.cpp:295-298)"""
         mesh = self
         for _ in range(int(levels)):

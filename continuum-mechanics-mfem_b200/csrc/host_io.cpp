@@ -170,6 +170,124 @@ int cdm_mesh_from_arrays_simplex(cdm_ctx *ctx, int dim, int64_t nv, const double
    return CDM_OK;
 }
 
+// ------------------------------------------------------------------------------------------- uniform refinement (hexes)
+// MFEM's UniformRefinement3D_base for hexahedra, restated: edges and quadrilateral faces numbered in first-encounter order
+// over the elements (local edges / faces of hex_t); new vertices = old vertices, edge midpoints, face centres, element
+// centres; child k of an element sits at its corner k, vertices listed in hex order; a boundary quadrilateral becomes four
+// (children at its corners).  Averages as in Mesh::AverageVertices, recomputed by every element that visits an entity (the
+// last visitor's summation order stays).
+static int refine_hexes(cdm_ctx *ctx, const cdm_mesh *m, cdm_mesh **refined)
+{
+   static const int HE[12][2] = {{0,1},{1,2},{3,2},{0,3},{4,5},{5,6},{7,6},{4,7},{0,4},{1,5},{2,6},{3,7}};
+   static const int HF[6][4] = {{3,2,1,0},{0,1,5,4},{1,2,6,5},{2,3,7,6},{3,0,4,7},{4,5,6,7}};
+   struct ENode { int32_t hi, id, next; };
+   struct FNode { int32_t b, c, id, next; };
+   std::vector<int32_t> ehead((size_t)m->nv, -1), fhead((size_t)m->nv, -1);
+   std::vector<ENode> epool; std::vector<FNode> fpool;
+   int32_t nedges = 0, nfaces = 0;
+   auto edge = [&](int32_t a, int32_t b, bool insert) -> int32_t
+   {
+      const int32_t lo = std::min(a, b), hi = std::max(a, b);
+      for (int32_t n = ehead[lo]; n >= 0; n = epool[n].next) { if (epool[n].hi == hi) { return epool[n].id; } }
+      if (!insert) { return -1; }
+      epool.push_back(ENode{hi, nedges, ehead[lo]});
+      ehead[lo] = (int32_t)epool.size() - 1;
+      return nedges++;
+   };
+   auto face = [&](const int32_t *fv, bool insert) -> int32_t
+   {
+      int32_t s4[4] = {fv[0], fv[1], fv[2], fv[3]};
+      std::sort(s4, s4 + 4);
+      for (int32_t n = fhead[s4[0]]; n >= 0; n = fpool[n].next) { if (fpool[n].b == s4[1] && fpool[n].c == s4[2]) { return fpool[n].id; } }
+      if (!insert) { return -1; }
+      fpool.push_back(FNode{s4[1], s4[2], nfaces, fhead[s4[0]]});
+      fhead[s4[0]] = (int32_t)fpool.size() - 1;
+      return nfaces++;
+   };
+   std::vector<int32_t> el_edge((size_t)m->ne * 12), el_face((size_t)m->ne * 6);
+   for (int64_t e = 0; e < m->ne; e++)
+   {
+      const int32_t *v = &m->ev[(size_t)e * 8];
+      for (int k = 0; k < 12; k++) { el_edge[(size_t)e * 12 + k] = edge(v[HE[k][0]], v[HE[k][1]], true); }
+   }
+   for (int64_t e = 0; e < m->ne; e++)
+   {
+      const int32_t *v = &m->ev[(size_t)e * 8];
+      for (int k = 0; k < 6; k++)
+      {
+         const int32_t fv[4] = {v[HF[k][0]], v[HF[k][1]], v[HF[k][2]], v[HF[k][3]]};
+         el_face[(size_t)e * 6 + k] = face(fv, true);
+      }
+   }
+   const int64_t oedge = m->nv, oface = oedge + nedges, oelem = oface + nfaces, nv2 = oelem + m->ne;
+   if (nv2 > 2147483000LL || m->ne * 8 > 2147483000LL) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_mesh_uniform_refine: more than 2^31 vertices or elements"); }
+   cdm_mesh *r = new (std::nothrow) cdm_mesh;
+   if (!r) { return cdm_fail(ctx, CDM_ENOMEM, "out of memory"); }
+   r->geom = 0; r->dim = 3; r->nv = nv2; r->ne = m->ne * 8; r->nbe = m->nbe * 4;
+   r->vx.assign((size_t)nv2 * 3, 0.0);
+   std::copy(m->vx.begin(), m->vx.end(), r->vx.begin());
+   auto average = [&](const int32_t *idx, int n, int64_t dst)
+   {
+      for (int c = 0; c < 3; c++)
+      {
+         double s = 0.0;
+         for (int k = 0; k < n; k++) { s += r->vx[(size_t)idx[k] * 3 + c]; }
+         r->vx[(size_t)dst * 3 + c] = s * (1.0 / n);
+      }
+   };
+   r->ev.resize((size_t)r->ne * 8);
+   for (int64_t i = 0; i < m->ne; i++)
+   {
+      const int32_t *v = &m->ev[(size_t)i * 8];
+      int32_t e[12], f[6];
+      const int32_t c = (int32_t)(oelem + i);
+      average(v, 8, c);
+      for (int k = 0; k < 6; k++)
+      {
+         f[k] = (int32_t)(oface + el_face[(size_t)i * 6 + k]);
+         const int32_t fv[4] = {v[HF[k][0]], v[HF[k][1]], v[HF[k][2]], v[HF[k][3]]};
+         average(fv, 4, f[k]);
+      }
+      for (int k = 0; k < 12; k++)
+      {
+         e[k] = (int32_t)(oedge + el_edge[(size_t)i * 12 + k]);
+         const int32_t pair[2] = {v[HE[k][0]], v[HE[k][1]]};
+         average(pair, 2, e[k]);
+      }
+      const int32_t ch[64] = {
+         v[0], e[0], f[0], e[3], e[8], f[1], c, f[4],
+         e[0], v[1], e[1], f[0], f[1], e[9], f[2], c,
+         f[0], e[1], v[2], e[2], c, f[2], e[10], f[3],
+         e[3], f[0], e[2], v[3], f[4], c, f[3], e[11],
+         e[8], f[1], c, f[4], v[4], e[4], f[5], e[7],
+         f[1], e[9], f[2], c, e[4], v[5], e[5], f[5],
+         c, f[2], e[10], f[3], f[5], e[5], v[6], e[6],
+         f[4], c, f[3], e[11], e[7], f[5], e[6], v[7]};
+      std::copy(ch, ch + 64, &r->ev[(size_t)i * 64]);
+   }
+   r->bv.resize((size_t)r->nbe * 4);
+   r->battr.resize((size_t)r->nbe);
+   for (int64_t b = 0; b < m->nbe; b++)
+   {
+      const int32_t *v = &m->bv[(size_t)b * 4];
+      int32_t e[4];
+      for (int k = 0; k < 4; k++)
+      {
+         const int32_t id = edge(v[k], v[(k + 1) % 4], false);
+         if (id < 0) { delete r; return cdm_fail(ctx, CDM_EINVAL, "cdm_mesh_uniform_refine: boundary element is not a face of the mesh"); }
+         e[k] = (int32_t)(oedge + id);
+      }
+      const int32_t fid = face(v, false);
+      if (fid < 0) { delete r; return cdm_fail(ctx, CDM_EINVAL, "cdm_mesh_uniform_refine: boundary element is not a face of the mesh"); }
+      const int32_t q = (int32_t)(oface + fid);
+      const int32_t ch[16] = {v[0], e[0], q, e[3],  e[0], v[1], e[1], q,  q, e[1], v[2], e[2],  e[3], q, e[2], v[3]};
+      std::copy(ch, ch + 16, &r->bv[(size_t)b * 16]);
+      for (int k = 0; k < 4; k++) { r->battr[(size_t)b * 4 + k] = m->battr[(size_t)b]; }
+   }
+   *refined = r;
+   return CDM_OK;
+}
+
 // ------------------------------------------------------------------------------------------- uniform refinement (2D)
 // Mesh::UniformRefinement() of a conforming triangle or quadrilateral mesh (linear_convection_diffusion_2D.cpp:295-298,
 // serial_ref_levels / par_ref_levels; Input/input_diffusion_mms.yaml refines Mesh/unit_square.msh once).  MFEM's
@@ -183,8 +301,9 @@ int cdm_mesh_from_arrays_simplex(cdm_ctx *ctx, int dim, int64_t nv, const double
 int cdm_mesh_uniform_refine(cdm_ctx *ctx, const cdm_mesh *m, cdm_mesh **refined)
 {
    if (!m || !refined) { return cdm_fail(ctx, CDM_EINVAL, "cdm_mesh_uniform_refine: bad arguments"); }
-   if (m->dim != 2) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_mesh_uniform_refine: 2D meshes only (triangles, quadrilaterals)"); }
    if (m->is_part) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_mesh_uniform_refine: refine before partitioning"); }
+   if (m->dim == 3 && m->geom == 0) { return refine_hexes(ctx, m, refined); }
+   if (m->dim != 2) { return cdm_fail(ctx, CDM_EUNSUP, "cdm_mesh_uniform_refine: triangles, quadrilaterals and hexahedra only"); }
    const int nvpe = (m->geom == 1) ? 3 : 4;
    // edge ids in first-encounter order: rows keyed by the smaller vertex, chained entries (as in host_space.cpp)
    struct Node { int32_t hi, id, next; };

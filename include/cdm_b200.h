@@ -87,10 +87,10 @@ int  cdm_mesh_read_gmsh(cdm_ctx *ctx, const char *path, int mark_for_refinement,
    listed along the generalised Hilbert curve; cdm_grid_sfc_ordering returns the curve itself, coords[k*dim + c]. */
 int  cdm_mesh_cartesian_sfc(cdm_ctx *ctx, int dim, const int64_t n[3], const double size[3], double perturb, cdm_mesh **mesh);
 int  cdm_grid_sfc_ordering(int dim, const int64_t n[3], int64_t *coords);
-/* Mesh::UniformRefinement() (linear_convection_diffusion_2D.cpp:295-298: serial_ref_levels / par_ref_levels) of a 2D
-   triangle or quadrilateral mesh: edge midpoints (then quadrilateral centres) appended to the vertices, four children per
-   element in MFEM's order, boundary segments halved; 3D meshes: CDM_EUNSUP.  The result is a plain mesh without Cartesian
-   provenance (cdm_mesh_partition_box does not apply to it; refine before partitioning is not offered either). */
+/* Mesh::UniformRefinement() (linear_convection_diffusion_2D.cpp:295-298: serial_ref_levels / par_ref_levels) of a triangle,
+   quadrilateral or hexahedral mesh: edge midpoints, then face / element centres appended to the vertices, four (2D) or eight
+   (3D) children per element in MFEM's order, boundary elements split the same way.  The result is a plain mesh without
+   Cartesian provenance: partition it with cdm_mesh_partition_elements (a part cannot be refined). */
 int  cdm_mesh_uniform_refine(cdm_ctx *ctx, const cdm_mesh *mesh, cdm_mesh **refined);
 /* geom: 0 tensor-product elements, 1 simplices */
 int  cdm_mesh_geometry(const cdm_mesh *mesh, int *geom, int *verts_per_elem, int *verts_per_bdr);

@@ -124,7 +124,7 @@ public:
    Mesh(Mesh &&o) noexcept : ctx_(o.ctx_), h_(o.h_) { o.h_ = nullptr; }
    ~Mesh() { if (h_) { cdm_mesh_destroy(h_); } }
    int Dimension() const { int d; cdm_mesh_sizes(h_, &d, nullptr, nullptr, nullptr); return d; }
-   // mfem::Mesh::UniformRefinement() (linear_convection_diffusion_2D.cpp:295-298); 2D meshes
+   // mfem::Mesh::UniformRefinement() (linear_convection_diffusion_2D.cpp:295-298)
    void UniformRefinement()
    {
       cdm_mesh *r = nullptr;

@@ -216,42 +216,3 @@ class TriProblem:
         uh = np.zeros((self.ne, len(w))) if u is None else np.einsum("qi,ei->eq", B, np.asarray(u)[self.elem_dof])
         ex = 0.0 if uex_q is None else np.asarray(uex_q).reshape(self.ne, -1)
         return float(np.sqrt(np.sum(np.abs(det)[:, None] * w[None] * (uh - ex) ** 2)))
-
-
-def uniform_refine_2d(vx, ev, bv, battr):
-    """Mesh::UniformRefinement() of a conforming 2D triangle or quadrilateral mesh, restated independently of the C++ host
-    code (dictionary-based edge table, numpy arrays) -- linear_convection_diffusion_2D.cpp:295-298; conventions of MFEM's
-    UniformRefinement2D_base [MFEM-upstream, from memory]: edges numbered in first-encounter order over the elements, new
-    vertices = old, edge midpoints, (quadrilateral centres); children of element i listed consecutively,
-    triangle: (v0,e0,e2) (e1,e2,e0) (e0,v1,e1) (e2,e1,v2); quad: (v0,e0,c,e3) (e0,v1,e1,c) (c,e1,v2,e2) (e3,c,e2,v3);
-    boundary segment (a,b) -> (a,m), (m,b)."""
-    vx, ev, bv, battr = np.asarray(vx, float), np.asarray(ev), np.asarray(bv), np.asarray(battr)
-    nv, (ne, k) = len(vx), ev.shape
-    edges = {}
-    el_edge = np.zeros((ne, k), np.int64)
-    for e in range(ne):
-        for j in range(k):
-            a, b = int(ev[e, j]), int(ev[e, (j + 1) % k])
-            el_edge[e, j] = edges.setdefault((min(a, b), max(a, b)), len(edges))
-    nedges = len(edges)
-    out_v = np.zeros((nv + nedges + (ne if k == 4 else 0), 2))
-    out_v[:nv] = vx
-    out_e = np.zeros((4 * ne, k), np.int32)
-    for e in range(ne):
-        v = [int(t) for t in ev[e]]
-        m = [nv + int(el_edge[e, j]) for j in range(k)]
-        for j in range(k):
-            out_v[m[j]] = (0.0 + vx[v[j]] + vx[v[(j + 1) % k]]) * 0.5
-        if k == 3:
-            out_e[4 * e:4 * e + 4] = [[v[0], m[0], m[2]], [m[1], m[2], m[0]], [m[0], v[1], m[1]], [m[2], m[1], v[2]]]
-        else:
-            c = nv + nedges + e
-            out_v[c] = (((0.0 + vx[v[0]]) + vx[v[1]]) + vx[v[2]] + vx[v[3]]) * 0.25
-            out_e[4 * e:4 * e + 4] = [[v[0], m[0], c, m[3]], [m[0], v[1], m[1], c], [c, m[1], v[2], m[2]], [m[3], c, m[2], v[3]]]
-    out_b = np.zeros((2 * len(bv), 2), np.int32)
-    out_a = np.repeat(battr, 2).astype(np.int32)
-    for b in range(len(bv)):
-        a0, a1 = int(bv[b, 0]), int(bv[b, 1])
-        mid = nv + edges[(min(a0, a1), max(a0, a1))]
-        out_b[2 * b], out_b[2 * b + 1] = (a0, mid), (mid, a1)
-    return out_v, out_e, out_b, out_a

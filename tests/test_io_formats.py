@@ -150,6 +150,7 @@ def test_uniform_refinement_matches_independent_restatement(ctx, mesh):
     """Mesh::UniformRefinement (serial_ref_levels of the reference's drivers; Input/input_diffusion_mms.yaml refines
     Mesh/unit_square.msh once): the C++ host code against the numpy restatement, bit-exact in every array (the midpoint
     coordinates too: same summation order), twice in a row; counts, areas, conformity, inherited boundary attributes"""
+    from oracle import refine_oracle as R
     from oracle import tri_oracle as T
     if mesh == "quads":
         m = cdm.Mesh.cartesian(ctx, 2, [5, 3], perturb=0.15)
@@ -166,7 +167,7 @@ def test_uniform_refinement_matches_independent_restatement(ctx, mesh):
         vx, ev, bv, ba = arrays
         m = m.uniform_refine()
         got = m.arrays()
-        want = T.uniform_refine_2d(vx, ev, bv, ba)
+        want = R.uniform_refine_2d(vx, ev, bv, ba)
         for g, w in zip(got, want):
             assert g.shape == w.shape and np.array_equal(g, w)
         k = ev.shape[1]
@@ -195,6 +196,59 @@ def test_uniform_refinement_matches_independent_restatement(ctx, mesh):
             assert sp.ndof == P.ndof and np.array_equal(sp.maps()[0], P.elem_dof)
         else:
             assert sp.ndof == m.nv + len(cnt) + m.ne
+        arrays = got
+
+
+@pytest.mark.parametrize("shuffle", [None, 4])
+def test_hexahedral_uniform_refinement(ctx, orc, shuffle):
+    """UniformRefinement of hexahedral meshes (perturbed Cartesian, natural and shuffled vertex numbering): bit-exact against the
+    numpy restatement, volumes of the children positive and summing to the parents', conforming faces, boundary attributes
+    inherited; the H1 numbering and the essential dofs of the C++ host code on the refined mesh equal the oracle's"""
+    from oracle import refine_oracle as R
+    P0 = orc.Problem(3, 1, [3, 2, 2], perturb=0.12, shuffle_seed=shuffle)
+    m = cdm.Mesh.from_arrays(ctx, P0.vx, P0.ev, P0.bv, P0.battr)
+    gp = np.array([0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)])
+
+    def volumes(vx, ev):
+        X = vx[ev]                                                # (ne, 8, 3), MFEM hex vertex order
+        vol = np.zeros(len(ev))
+        for x in gp:
+            for y in gp:
+                for z in gp:
+                    dN = np.array([[-(1 - y) * (1 - z), -(1 - x) * (1 - z), -(1 - x) * (1 - y)], [(1 - y) * (1 - z), -x * (1 - z), -x * (1 - y)],
+                                   [y * (1 - z), x * (1 - z), -x * y], [-y * (1 - z), (1 - x) * (1 - z), -(1 - x) * y],
+                                   [-(1 - y) * z, -(1 - x) * z, (1 - x) * (1 - y)], [(1 - y) * z, -x * z, x * (1 - y)],
+                                   [y * z, x * z, x * y], [-y * z, (1 - x) * z, (1 - x) * y]])
+                    J = np.einsum("ekr,kc->erc", X, dN)
+                    vol += np.linalg.det(J) / 8.0
+        return vol
+
+    arrays = m.arrays()
+    v0 = volumes(arrays[0], arrays[1]).sum()
+    for level in range(2):
+        vx, ev, bv, ba = arrays
+        m = m.uniform_refine()
+        got = m.arrays()
+        want = R.uniform_refine_3d(vx, ev, bv, ba)
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and np.array_equal(g, w)
+        assert m.ne == 8 * len(ev) and m.nbe == 4 * len(bv)
+        vol = volumes(got[0], got[1])
+        assert vol.min() > 0 and abs(vol.sum() - v0) < 1e-13
+        cnt = {}
+        for e in got[1]:
+            for f in R.HEX_F:
+                key = tuple(sorted(int(e[i]) for i in f))
+                cnt[key] = cnt.get(key, 0) + 1
+        bset = {tuple(sorted(int(t) for t in b)) for b in got[2]}
+        assert all((c == 2) != (key in bset) for key, c in cnt.items()) and all(cnt[key] == 1 for key in bset) and len(bset) == m.nbe
+        for p in (2, 3):
+            sp = cdm.H1Space(m, p)
+            ndof, elem_dof, _, _ = orc.h1_build(3, p, m.nv, got[1])
+            assert sp.ndof == ndof and np.array_equal(sp.maps()[0], elem_dof)
+            marker = np.array([1, 0, 1, 1, 0, 1], np.int32)
+            mark = orc.h1_bdr_dofs(3, p, m.nv, got[1], got[2], got[3], marker, ndof)
+            assert np.array_equal(sp.essential_dofs(marker), np.nonzero(mark)[0].astype(np.int32))
         arrays = got
 
 
